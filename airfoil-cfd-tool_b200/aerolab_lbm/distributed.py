@@ -1,0 +1,330 @@
+"""Multi-GPU driver: y-slab decomposition with a one-row population halo.
+
+One process per GPU (``torchrun``); ``torch.distributed`` is plumbing only
+(rendezvous, exchanging CUDA-IPC blobs, scalar reductions, barriers).  The
+halo itself has two transports:
+
+``p2p`` (default)  the step kernel stores its edge rows straight into the
+                   neighbour's ghost rows through CUDA-IPC-mapped peer memory
+                   (NVLink), and stream-ordered flag kernels order the steps;
+                   no host involvement per step.
+``nccl``           a plain ``torch.distributed`` send/recv of the six rows
+                   between single steps (fallback; also what the CPU ``gloo``
+                   tests exercise through :class:`TorchHaloExchange`).
+
+The reference has nothing to mirror here (it is single-GPU WebGL); the slab
+rules follow SURVEY.md section 8(e): rows are contiguous, inlet/outlet columns
+stay local, the bottom/top slabs own the equilibrium rows, the pull scheme
+needs f2,f5,f6 from below and f4,f7,f8 from above.
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+LO_POPS = (4, 7, 8)     # leave through the bottom face (e_y = -1)
+HI_POPS = (2, 5, 6)     # leave through the top face (e_y = +1)
+
+
+def slab_rows(ny: int, world: int, rank: int):
+    """Rows [y0, y0+n) owned by `rank`: equal shares, the first ny % world ranks get one more."""
+    base, rem = divmod(ny, world)
+    y0 = rank * base + min(rank, rem)
+    return y0, base + (1 if rank < rem else 0)
+
+
+class Comm:
+    """Thin wrapper over torch.distributed; a no-op for a single process."""
+
+    def __init__(self, world: int = 1, rank: int = 0, device: Optional[str] = None):
+        self.world, self.rank = world, rank
+        self.device = device
+        self._dist = None
+        if world > 1:
+            import torch.distributed as dist
+            self._dist = dist
+
+    def _tensor(self, data, dtype):
+        import torch
+        return torch.tensor(data, dtype=dtype, device=self.device or "cpu")
+
+    def barrier(self):
+        if self._dist:
+            self._dist.barrier()
+
+    def max_float(self, x: float) -> float:
+        if not self._dist:
+            return float(x)
+        import torch
+        t = self._tensor([x], torch.float64)
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allreduce(self, arr: np.ndarray, op: str = "sum") -> np.ndarray:
+        """Element-wise reduction of a small float64 or int64 array (int sums are exact)."""
+        if not self._dist:
+            return np.array(arr, copy=True)
+        import torch
+        dt = torch.int64 if np.issubdtype(np.asarray(arr).dtype, np.integer) else torch.float64
+        t = self._tensor(np.asarray(arr).tolist(), dt)
+        ops = {"sum": self._dist.ReduceOp.SUM, "max": self._dist.ReduceOp.MAX, "min": self._dist.ReduceOp.MIN}
+        self._dist.all_reduce(t, op=ops[op])
+        return t.cpu().numpy()
+
+    def all_gather_bytes(self, b: bytes) -> List[bytes]:
+        if not self._dist:
+            return [b]
+        out = [None] * self.world
+        self._dist.all_gather_object(out, b)
+        return out
+
+    def gather_arrays(self, a: np.ndarray, dst: int = 0):
+        """Gather NumPy arrays on `dst` (slow path, for tests and dumps)."""
+        if not self._dist:
+            return [a]
+        out = [None] * self.world
+        self._dist.all_gather_object(out, a)
+        return out if self.rank == dst else None
+
+    def shutdown(self):
+        if self._dist and self._dist.is_initialized():
+            self._dist.destroy_process_group()
+
+
+def init_comm(world: int, rank: int, local_rank: int = 0, backend: Optional[str] = None) -> Comm:
+    """Initialise torch.distributed from the torchrun environment (MASTER_ADDR/PORT)."""
+    if world <= 1:
+        return Comm()
+    import torch
+    import torch.distributed as dist
+    cuda = torch.cuda.is_available()
+    backend = backend or ("nccl" if cuda else "gloo")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    if not dist.is_initialized():
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kw["device_id"] = torch.device(f"cuda:{local_rank}")
+        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+    return Comm(world, rank, f"cuda:{local_rank}" if backend == "nccl" else "cpu")
+
+
+class TorchHaloExchange:
+    """Move the six halo rows with torch.distributed point-to-point calls.
+
+    ``rows()`` must return ``dict(send_lo, send_hi, recv_lo, recv_hi)`` of three
+    1-D torch tensors each (CPU tensors under gloo, CUDA tensors under NCCL) that
+    alias the slab's CURRENT state.
+    """
+
+    def __init__(self, comm: Comm, rows):
+        self.comm = comm
+        self.rows = rows
+
+    def exchange(self):
+        dist = self.comm._dist
+        if dist is None:
+            return
+        r = self.rows()
+        rank, world = self.comm.rank, self.comm.world
+        ops = []
+        for k in range(3):
+            if rank > 0:
+                ops.append(dist.P2POp(dist.isend, r["send_lo"][k], rank - 1, tag=k))
+                ops.append(dist.P2POp(dist.irecv, r["recv_lo"][k], rank - 1, tag=3 + k))
+            if rank < world - 1:
+                ops.append(dist.P2POp(dist.isend, r["send_hi"][k], rank + 1, tag=3 + k))
+                ops.append(dist.P2POp(dist.irecv, r["recv_hi"][k], rank + 1, tag=k))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+
+class _DevRow:
+    """Expose a raw device address as a CUDA array so torch can wrap it without a copy."""
+
+    def __init__(self, addr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (addr, False), "version": 2}
+
+
+class DistributedTunnel:
+    """A lattice split into one y-slab per rank; same control surface as WindTunnel."""
+
+    def __init__(self, nx: int, ny: int, comm: Optional[Comm] = None, device: int = 0, halo: str = "p2p",
+                 u0: float = 0.06, tau: float = 0.58):
+        from .tunnel import WindTunnel
+        self.comm = comm or Comm()
+        self.nx, self.ny = nx, ny
+        self.y0, self.ny_local = slab_rows(ny, self.comm.world, self.comm.rank)
+        if self.ny_local < 1:
+            raise ValueError("more ranks than lattice rows")
+        self.t = WindTunnel(nx, ny, device, u0=u0, tau=tau, y0=self.y0, ny_local=self.ny_local)
+        self.halo = halo if self.comm.world > 1 else "none"
+        self._xchg = None
+        self._row_cache = {}
+        self.device = device
+        self.cl_smooth = None
+        self.cd_smooth = None
+        self.sep_frac = 0.0
+        self.max_s, self.cp_min, self.cp_max = 0.6, -1.0, 1.0
+        if self.halo == "p2p":
+            blobs = self.comm.all_gather_bytes(self.t.ipc_export())
+            r, w = self.comm.rank, self.comm.world
+            self.t.ipc_connect(blobs[r - 1] if r > 0 else None, blobs[r + 1] if r < w - 1 else None)
+            self.comm.barrier()
+        elif self.halo == "nccl":
+            self.t.set_external_halo(True)
+            self._xchg = TorchHaloExchange(self.comm, self._torch_rows)
+
+    # -- halo rows as torch tensors (nccl transport) ---------------------------------
+    def _torch_rows(self):
+        import torch
+        ptrs = self.t.halo_ptrs()
+        key = tuple(ptrs["send_lo"])
+        if key not in self._row_cache:
+            dev = f"cuda:{self.device}"
+            self._row_cache[key] = {k: [torch.as_tensor(_DevRow(a, self.nx), device=dev) for a in v]
+                                    for k, v in ptrs.items()}
+        return self._row_cache[key]
+
+    # -- control surface ---------------------------------------------------------------
+    def load_coords(self, coords, name="", alpha=None):
+        self.t.load_coords(coords, name=name, alpha=alpha)
+        return self
+
+    def load_shape(self, key, alpha=None):
+        self.t.load_shape(key, alpha=alpha)
+        return self
+
+    def set_alpha(self, alpha):
+        self.t.set_alpha(alpha)
+        return self
+
+    def set_params(self, u0, tau):
+        self.t.set_params(u0, tau)
+        return self
+
+    def reset(self, u0=None):
+        self.t.reset(u0)
+        self.cl_smooth = self.cd_smooth = None
+        self.sep_frac = 0.0
+        return self
+
+    def step(self, n: int = 1):
+        if self.halo == "nccl":
+            for _ in range(n):
+                self.t.step(1)
+                self.t.sync()
+                self._xchg.exchange()
+                import torch
+                torch.cuda.current_stream().synchronize()
+        else:
+            self.t.step(n)
+        return self
+
+    def sync(self):
+        self.t.sync()
+        return self
+
+    def last_step_ms(self) -> float:
+        return self.t.last_step_ms()
+
+    @property
+    def steps(self) -> int:
+        return self.t.steps
+
+    def close(self):
+        self.t.sync()
+        self.comm.barrier()
+        self.t.close()
+
+    # -- diagnostics (partials reduced over ranks; host logic of HTML:611-613, 672-699) ----
+    def update_stats(self) -> dict:
+        p = self.t.stats_partial()
+        mx = self.comm.allreduce(np.array([p[0], p[2]]), "max")
+        mn = self.comm.allreduce(np.array([p[1]]), "min")
+        if mx[0] > 0:
+            self.max_s = float(mx[0])
+        if math.isfinite(mn[0]):
+            self.cp_min = float(mn[0])
+        if math.isfinite(mx[1]):
+            self.cp_max = float(mx[1])
+        self.t.set_stats(self.max_s, self.cp_min, self.cp_max)
+        return dict(maxS=self.max_s, cpMin=self.cp_min, cpMax=self.cp_max)
+
+    def forces(self) -> dict:
+        part = self.comm.allreduce(self.t.forces_partial(), "sum")
+        fx, fy, surf, rev = (float(v) for v in part)
+        u0, _ = self.t.params()
+        q = 0.5 * u0 * u0 * (self.nx / (1.42 - (-0.42)))
+        out = dict(fx=fx, fy=fy, surf=int(surf), rev=int(rev), any=surf > 0)
+        if surf > 0:
+            cl, cd = fy / q, fx / q
+            self.cl_smooth = cl if self.cl_smooth is None else self.cl_smooth * 0.9 + cl * 0.1
+            self.cd_smooth = cd if self.cd_smooth is None else self.cd_smooth * 0.9 + cd * 0.1
+            self.sep_frac = self.sep_frac * 0.85 + (rev / surf) * 0.15
+            out.update(CL_raw=cl, CD_raw=cd)
+        out.update(CL=self.cl_smooth, CD=self.cd_smooth, sep_frac=self.sep_frac)
+        if self.t.steps > 0:
+            me = self.comm.allreduce(self.t.me_history(1)[0], "sum")
+            fxm, fym = float(me[0]) / 2.0 ** 40, float(me[1]) / 2.0 ** 40
+            out.update(Fx_me=fxm, Fy_me=fym, CL_me=fym / q, CD_me=fxm / q)
+        return out
+
+    def frame(self) -> dict:
+        """The reference frame (HTML:902-930) across slabs: 4 steps, autoscale, forces every 3rd."""
+        self.step(4)
+        out = {"stats": self.update_stats()}
+        self._frames = getattr(self, "_frames", 0) + 1
+        if self._frames % 3 == 0:
+            out["forces"] = self.forces()
+        return out
+
+    def gather(self, what: str = "macro"):
+        """Assemble whole-lattice arrays on rank 0 (tests / dumps)."""
+        if what == "macro":
+            parts = [self.comm.gather_arrays(a) for a in self.t.macro()]
+            return None if parts[0] is None else tuple(np.concatenate(p, axis=0) for p in parts)
+        if what == "populations":
+            p = self.comm.gather_arrays(self.t.populations())
+            return None if p is None else np.concatenate(p, axis=1)
+        if what == "mask":
+            p = self.comm.gather_arrays(self.t.mask())
+            return None if p is None else np.concatenate(p, axis=0)
+        raise ValueError(what)
+
+
+def bench_e2e(tun: DistributedTunnel, comm: Comm, steps: int, cells_global: int) -> dict:
+    """End-to-end rate through the public API with host-side control, as a user drives it.
+
+    Every frame: the host passes the control inputs (U0, tau) through the C ABI,
+    launches 4 steps, and reads back the frame's results (autoscale statistics
+    every frame, pressure + momentum-exchange forces every 3rd frame) into host
+    memory -- the reference's frame loop (HTML:902-930) with its per-frame
+    readPixels replaced by on-device reductions.  Wall clock, max over ranks.
+    """
+    nframes = max(3, steps // 4)
+    u0, tau = tun.t.params()
+    for _ in range(3):
+        tun.frame()
+    tun.sync()
+    comm.barrier()
+    t0 = time.perf_counter()
+    for _ in range(nframes):
+        tun.set_params(u0, tau)
+        tun.frame()
+    tun.sync()
+    dt = comm.max_float(time.perf_counter() - t0)
+    comm.barrier()
+    diag_blocks = 148 * 4
+    d2h_frame = diag_blocks * 3 * 8 + (diag_blocks * 4 * 8 + 16) / 3.0
+    return {"value": cells_global * 4 * nframes / dt / 1e9, "unit": "GLUPS",
+            "h2d_bytes_per_step": 16 / 4.0, "d2h_bytes_per_step": d2h_frame / 4.0,
+            "frames": nframes, "steps_per_frame": 4,
+            "what": "WindTunnel frame loop through the C ABI: set_params + 4 steps + stats readback per "
+                    "frame, forces readback every 3rd frame; host wall clock, max over ranks"}

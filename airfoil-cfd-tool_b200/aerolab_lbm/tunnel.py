@@ -1,0 +1,397 @@
+"""`WindTunnel`: the reference page's control surface, driven from Python.
+
+Mirrors the operator surface of ``pages/airfoil_flow_lbm_aerolab.html``
+("HTML:n"): ``applyGeometry`` (579), the ``U0`` slider (956-959), ``TAU`` (78),
+``fieldMode`` (527, 953), ``simStep`` (510), ``readMacro`` (547),
+``updateFieldsFromMacro`` (596), ``computeForces`` (650), ``updateStatsUI``
+(862) and ``frame`` (902); and the Python bridge ``build_lbm_component`` of
+``pages/Airfoil_Analysis.py:20-42``.
+
+Every computation happens in libaerolab_lbm.so on the GPU; this file only
+marshals NumPy buffers through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from . import geometry as geom
+from ._ffi import AerolabLbmError, check, ptr
+
+FIELD_MODES = {"speed": 0, "cp": 1, "vort": 2, 0: 0, 1: 1, 2: 2}
+
+# reference constants
+DEFAULT_NX, DEFAULT_NY = 320, 160     # HTML:76
+DEFAULT_U0 = 0.06                     # HTML:472
+DEFAULT_TAU = 0.58                    # HTML:78
+DEFAULT_ALPHA = 6.0                   # HTML:26, 970
+STEPS_PER_FRAME = 4                   # HTML:80
+FORCES_EVERY_FRAMES = 3               # HTML:914
+# backend limits reused for validation (main.py:39-45)
+MIN_POINTS, MAX_POINTS = 10, 500
+
+
+class WindTunnel:
+    """One D2Q9 lattice on one GPU.
+
+    ``nx`` x ``ny`` cells over the fixed world window x in [-0.42, 1.42],
+    y in [-0.46, 0.46] (HTML:73); cells are square when nx = 2*ny.
+    """
+
+    def __init__(self, nx: int = DEFAULT_NX, ny: int = DEFAULT_NY, device: int = 0,
+                 u0: float = DEFAULT_U0, tau: float = DEFAULT_TAU, *,
+                 y0: int = 0, ny_local: Optional[int] = None):
+        self._lib = _ffi.lib()
+        self._h = C.c_void_p()
+        self.nx, self.ny = int(nx), int(ny)
+        self.y0 = int(y0)
+        self.ny_local = self.ny if ny_local is None else int(ny_local)
+        self.device = int(device)
+        check(self._lib.alb_create_slab(self.nx, self.ny, self.y0, self.ny_local, self.device,
+                                        C.byref(self._h)))
+        self.name = ""
+        self.coords: Optional[np.ndarray] = None
+        self.alpha = DEFAULT_ALPHA
+        self._frame_counter = 0
+        if u0 != DEFAULT_U0 or tau != DEFAULT_TAU:
+            self.reset(u0)
+            self.set_tau(tau)
+
+    # -- lifetime ---------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.alb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, code: int) -> None:
+        check(code, self._h)
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    @property
+    def shape(self):
+        return (self.ny_local, self.nx)
+
+    # -- geometry ---------------------------------------------------------------
+    def load_coords(self, coords: Iterable[Sequence[float]], name: str = "", alpha: Optional[float] = None):
+        """Use injected coordinates (``USER_COORDS``, HTML:561-563) and rasterise them."""
+        arr = np.ascontiguousarray(np.asarray(list(coords), dtype=np.float64).reshape(-1, 2))
+        if arr.shape[0] < 2:
+            raise AerolabLbmError(_ffi.ALB_ERR_INVALID, "need at least 2 coordinate pairs")
+        self.coords = arr
+        self.name = name
+        return self.set_alpha(self.alpha if alpha is None else alpha)
+
+    def load_shape(self, key: str, alpha: Optional[float] = None):
+        """One of the page's built-in ``SHAPES`` (HTML:123-129)."""
+        return self.load_coords(geom.SHAPES[key](), name=key, alpha=alpha)
+
+    def load_naca(self, digits: str, alpha: Optional[float] = None):
+        return self.load_coords(geom.naca_digits(digits), name=f"NACA {digits}", alpha=alpha)
+
+    def load_dat(self, path: str, parser: Optional[Callable] = None, alpha: Optional[float] = None):
+        """Parse a ``.dat`` file and inject it like the Streamlit page does.
+
+        ``parser`` defaults to the host application's own
+        ``main.parse_dat_file`` (main.py:59-113), which returns
+        ``(coords, fixes)``; the coordinates are then rounded to 6 decimals as
+        in pages/Airfoil_Analysis.py:34-36.
+        """
+        from .dat import resolve_parser
+        coords, fixes = resolve_parser(parser)(path)
+        self.parser_fixes = fixes
+        return self.load_coords(geom.round_coords(coords), name=str(path), alpha=alpha)
+
+    def set_alpha(self, alpha_deg: float, want_mask: bool = False):
+        """``applyGeometry`` (HTML:579-586): new mask, flow NOT re-initialised."""
+        if self.coords is None:
+            raise AerolabLbmError(_ffi.ALB_ERR_STATE, "no geometry loaded")
+        out = np.empty(self.shape, np.uint8) if want_mask else None
+        self._ck(self._lib.alb_rasterize(self._h, ptr(self.coords), self.coords.shape[0],
+                                         float(alpha_deg), ptr(out)))
+        self.alpha = float(alpha_deg)
+        return out if want_mask else self
+
+    def set_mask(self, mask_global: np.ndarray):
+        m = np.ascontiguousarray(mask_global, dtype=np.uint8)
+        if m.shape != (self.ny, self.nx):
+            raise AerolabLbmError(_ffi.ALB_ERR_INVALID, f"mask must be {(self.ny, self.nx)}")
+        self._ck(self._lib.alb_set_mask(self._h, ptr(m)))
+        return self
+
+    def mask(self) -> np.ndarray:
+        out = np.empty(self.shape, np.uint8)
+        self._ck(self._lib.alb_get_mask(self._h, ptr(out)))
+        return out
+
+    def panels(self):
+        xp = np.empty(_ffi.ALB_NPANEL + 1)
+        yp = np.empty(_ffi.ALB_NPANEL + 1)
+        self._ck(self._lib.alb_get_panels(self._h, ptr(xp), ptr(yp)))
+        return xp, yp
+
+    # -- parameters -------------------------------------------------------------
+    def params(self):
+        u0, tau = C.c_double(), C.c_double()
+        self._ck(self._lib.alb_get_params(self._h, C.byref(u0), C.byref(tau)))
+        return u0.value, tau.value
+
+    def set_u0(self, u0: float):
+        """Inlet-speed slider (HTML:956-959): changes the uniform only."""
+        self._ck(self._lib.alb_set_params(self._h, float(u0), self.params()[1]))
+        return self
+
+    def set_tau(self, tau: float):
+        """Relaxation time (a constant 0.58 in the reference, HTML:78)."""
+        self._ck(self._lib.alb_set_params(self._h, self.params()[0], float(tau)))
+        return self
+
+    def set_viscosity(self, nu_lattice: float):
+        """nu = (tau - 0.5)/3 (HTML:79)."""
+        return self.set_tau(3.0 * float(nu_lattice) + 0.5)
+
+    def reset(self, u0: Optional[float] = None):
+        """``initSim`` (HTML:492-500)."""
+        self._ck(self._lib.alb_reset(self._h, float(self.params()[0] if u0 is None else u0)))
+        self._lib.alb_reset_force_emas(self._h)
+        self._frame_counter = 0
+        return self
+
+    # -- stepping ---------------------------------------------------------------
+    def step(self, n: int = 1):
+        """``simStep`` x n (HTML:510-525); asynchronous."""
+        self._ck(self._lib.alb_step(self._h, int(n)))
+        return self
+
+    def sync(self):
+        self._ck(self._lib.alb_sync(self._h))
+        return self
+
+    @property
+    def steps(self) -> int:
+        v = C.c_longlong()
+        self._ck(self._lib.alb_step_count(self._h, C.byref(v)))
+        return v.value
+
+    def last_step_ms(self) -> float:
+        v = C.c_float()
+        self._ck(self._lib.alb_last_step_ms(self._h, C.byref(v)))
+        return v.value
+
+    # -- state ------------------------------------------------------------------
+    def populations(self) -> np.ndarray:
+        out = np.empty((9,) + self.shape, np.float32)
+        self._ck(self._lib.alb_get_populations(self._h, ptr(out)))
+        return out
+
+    def set_populations(self, f: np.ndarray):
+        f = np.ascontiguousarray(f, dtype=np.float32)
+        if f.shape != (9,) + self.shape:
+            raise AerolabLbmError(_ffi.ALB_ERR_INVALID, f"populations must be {(9,) + self.shape}")
+        self._ck(self._lib.alb_set_populations(self._h, ptr(f)))
+        return self
+
+    def macro(self):
+        """``readMacro`` (HTML:547-552): rho, ux, uy of the current state."""
+        rho = np.empty(self.shape, np.float32)
+        ux = np.empty(self.shape, np.float32)
+        uy = np.empty(self.shape, np.float32)
+        self._ck(self._lib.alb_get_macro(self._h, ptr(rho), ptr(ux), ptr(uy)))
+        return rho, ux, uy
+
+    def set_macro(self, rho, ux, uy):
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (rho, ux, uy)]
+        self._ck(self._lib.alb_set_macro(self._h, *[ptr(a) for a in arrs]))
+        return self
+
+    def total_mass(self) -> float:
+        v = C.c_double()
+        self._ck(self._lib.alb_total_mass(self._h, C.byref(v)))
+        return v.value
+
+    def dump_state(self) -> dict:
+        rho, ux, uy = self.macro()
+        u0, tau = self.params()
+        return dict(f=self.populations(), rho=rho, ux=ux, uy=uy, mask=self.mask(), u0=u0, tau=tau,
+                    steps=self.steps, alpha=self.alpha, nx=self.nx, ny=self.ny)
+
+    def load_state(self, st: dict):
+        self._ck(self._lib.alb_set_params(self._h, float(st["u0"]), float(st["tau"])))
+        if self.ny_local == self.ny:
+            self.set_mask(st["mask"])
+        self.set_populations(st["f"])
+        self.set_macro(st["rho"], st["ux"], st["uy"])
+        self.alpha = float(st.get("alpha", self.alpha))
+        return self
+
+    # -- diagnostics ------------------------------------------------------------
+    def update_stats(self, want_fields: bool = False):
+        """``updateFieldsFromMacro`` (HTML:596-614).  Returns dict(maxS, cpMin, cpMax[, U, V, Cp])."""
+        st = np.zeros(3)
+        U = V = Cp = None
+        if want_fields:
+            U = np.empty(self.shape, np.float32)
+            V = np.empty(self.shape, np.float32)
+            Cp = np.empty(self.shape, np.float32)
+        self._ck(self._lib.alb_update_stats(self._h, ptr(st), ptr(U), ptr(V), ptr(Cp)))
+        out = dict(maxS=st[0], cpMin=st[1], cpMax=st[2])
+        if want_fields:
+            out.update(U=U, V=V, Cp=Cp)
+        return out
+
+    def stats(self):
+        st = np.zeros(3)
+        self._ck(self._lib.alb_get_stats(self._h, ptr(st)))
+        return dict(maxS=st[0], cpMin=st[1], cpMax=st[2])
+
+    def field(self, mode="speed") -> np.ndarray:
+        """Scalar the render shader feeds to its palette (HTML:395-420); NaN in solids."""
+        out = np.empty(self.shape, np.float32)
+        self._ck(self._lib.alb_get_field(self._h, FIELD_MODES[mode], ptr(out)))
+        return out
+
+    def rgba(self, mode="speed") -> np.ndarray:
+        out = np.empty(self.shape + (4,), np.uint8)
+        self._ck(self._lib.alb_get_rgba(self._h, FIELD_MODES[mode], ptr(out)))
+        return out
+
+    def forces(self) -> dict:
+        """``computeForces`` (HTML:650-700) plus the momentum-exchange force of the last step."""
+        o = np.zeros(10)
+        self._ck(self._lib.alb_compute_forces(self._h, ptr(o)))
+        out = dict(fx=o[0], fy=o[1], CL_raw=o[2], CD_raw=o[3], CL=o[4], CD=o[5], sep_frac=o[6],
+                   surf=int(o[7]), rev=int(o[8]), any=bool(o[9]))
+        if self.steps > 0:
+            m = np.zeros(4)
+            self._ck(self._lib.alb_get_me_forces(self._h, ptr(m)))
+            out.update(Fx_me=m[0], Fy_me=m[1], CL_me=m[2], CD_me=m[3])
+        return out
+
+    def forces_partial(self) -> np.ndarray:
+        o = np.zeros(4)
+        self._ck(self._lib.alb_forces_partial(self._h, ptr(o)))
+        return o
+
+    def me_history(self, n: int) -> np.ndarray:
+        """Fixed-point (2^-40) momentum-exchange Fx, Fy of the last n steps, shape (n, 2) int64."""
+        out = np.zeros((int(n), 2), np.int64)
+        self._ck(self._lib.alb_get_me_history(self._h, int(n), ptr(out)))
+        return out
+
+    def clamp_hits(self) -> int:
+        v = C.c_longlong()
+        self._ck(self._lib.alb_clamp_hits(self._h, C.byref(v)))
+        return v.value
+
+    def reynolds(self) -> float:
+        v = C.c_double()
+        self._ck(self._lib.alb_reynolds(self._h, C.byref(v)))
+        return v.value
+
+    def stall_state(self) -> str:
+        """Text of the separation card (HTML:869-884)."""
+        st, pct = C.c_int(), C.c_int()
+        self._ck(self._lib.alb_stall_state(self._h, C.byref(st), C.byref(pct)))
+        if st.value == 0:
+            return "Attached"
+        if st.value == 1:
+            return f"{pct.value}% sep"
+        return f"STALL ≈ {pct.value}% sep"
+
+    # -- multi-GPU y-slabs (one-row population halo) -----------------------------
+    def connect_local(self, lo: "Optional[WindTunnel]", hi: "Optional[WindTunnel]"):
+        """Neighbouring slabs driven by the same process (lo = below, hi = above)."""
+        self._ck(self._lib.alb_connect_local(self._h, lo._h if lo is not None else None,
+                                             hi._h if hi is not None else None))
+        return self
+
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(_ffi.ALB_IPC_BYTES)
+        self._ck(self._lib.alb_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_connect(self, lo_blob: Optional[bytes], hi_blob: Optional[bytes]):
+        lo = C.create_string_buffer(lo_blob, _ffi.ALB_IPC_BYTES) if lo_blob else None
+        hi = C.create_string_buffer(hi_blob, _ffi.ALB_IPC_BYTES) if hi_blob else None
+        self._ck(self._lib.alb_ipc_connect(self._h, lo, hi))
+        return self
+
+    def halo_prime(self):
+        self._ck(self._lib.alb_halo_prime(self._h))
+        return self
+
+    def set_external_halo(self, on: bool):
+        self._ck(self._lib.alb_set_external_halo(self._h, int(bool(on))))
+        return self
+
+    def halo_ptrs(self):
+        """Device addresses (ints) of the rows crossing each face in the CURRENT state:
+        dict(send_lo, send_hi, recv_lo, recv_hi), three pointers each, nx floats per row."""
+        arrs = [(C.c_void_p * 3)() for _ in range(4)]
+        self._ck(self._lib.alb_halo_ptrs(self._h, *arrs))
+        keys = ("send_lo", "send_hi", "recv_lo", "recv_hi")
+        return {k: [int(a[i] or 0) for i in range(3)] for k, a in zip(keys, arrs)}
+
+    def stats_partial(self) -> np.ndarray:
+        o = np.zeros(3)
+        self._ck(self._lib.alb_stats_partial(self._h, ptr(o), None, None, None))
+        return o
+
+    def set_stats(self, max_s: float, cp_min: float, cp_max: float):
+        self._ck(self._lib.alb_set_stats(self._h, float(max_s), float(cp_min), float(cp_max)))
+        return self
+
+    def set_params(self, u0: float, tau: float):
+        self._ck(self._lib.alb_set_params(self._h, float(u0), float(tau)))
+        return self
+
+    # -- the reference's frame loop ---------------------------------------------
+    def frame(self, want_field: Optional[str] = None) -> dict:
+        """One animation frame (HTML:902-930): 4 steps, render with the previous
+        frame's autoscale, refresh the autoscale, forces every 3rd frame."""
+        self.step(STEPS_PER_FRAME)
+        out = {}
+        if want_field is not None:
+            out["field"] = self.field(want_field)
+        out["stats"] = self.update_stats()
+        self._frame_counter += 1
+        if self._frame_counter % FORCES_EVERY_FRAMES == 0:
+            out["forces"] = self.forces()
+        return out
+
+    def png_name(self) -> str:
+        """File name convention of the page's PNG export (HTML:990-992)."""
+        base = (self.name or "airfoil").split()
+        return f"{'_'.join(base)}_alpha{self.alpha:.1f}deg_lbm.png"
+
+
+def build_lbm_component(coords_after, airfoil_name: str = "", *, nx: int = DEFAULT_NX,
+                        ny: int = DEFAULT_NY, device: int = 0) -> WindTunnel:
+    """Drop-in for pages/Airfoil_Analysis.py:20-42.
+
+    Same arguments; instead of rendering an iframe it returns a running
+    ``WindTunnel`` primed exactly like the page at start-up: coordinates
+    rounded to 6 decimals, U0 = 0.06, tau = 0.58, alpha = 6 degrees
+    (HTML:969-970).
+    """
+    t = WindTunnel(nx, ny, device)
+    t.load_coords(geom.round_coords(coords_after), name=airfoil_name or "Uploaded airfoil",
+                  alpha=DEFAULT_ALPHA)
+    return t

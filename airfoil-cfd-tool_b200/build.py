@@ -1,0 +1,61 @@
+"""Build libaerolab_lbm.so for sm_100a with nvcc (in-tree, no JIT cache).
+
+    python airfoil-cfd-tool_b200/build.py [--force] [--verbose]
+
+Flags that matter for correctness ("Arithmetic contract"):
+  -fmad=false                      nvcc must not contract a*b+c into an FMA
+  -Xcompiler -ffp-contract=off     same for the host-side float code
+  (-prec-div/-prec-sqrt stay at their IEEE defaults; no --use_fast_math)
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "aerolab_lbm", "_lib")
+OUT = os.path.join(OUT_DIR, "libaerolab_lbm.so")
+SOURCES = ["alb_api.cu", "alb_step.cu", "alb_geometry.cu", "alb_diag.cu"]
+DEPS = SOURCES + ["alb_common.cuh", os.path.join("..", "..", "include", "aerolab_lbm.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-fmad=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2",
+    "-shared", "-cudart", "static",
+]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def up_to_date() -> bool:
+    if not os.path.exists(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    paths = [os.path.join(CSRC, d) for d in DEPS] + [os.path.abspath(__file__)]
+    return all(os.path.getmtime(p) <= t for p in paths)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and up_to_date():
+        return OUT
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = [nvcc_path(), *NVCC_FLAGS]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

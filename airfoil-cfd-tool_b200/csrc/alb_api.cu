@@ -1,0 +1,890 @@
+// C ABI of libaerolab_lbm.so (declared in include/aerolab_lbm.h).
+//
+// Host-side driver around the kernels: the CUDA equivalent of the reference
+// page's WebGL plumbing, initSim/simStep/readMacro and the stats/forces host
+// code (pages/airfoil_flow_lbm_aerolab.html:424-552, 579-614, 641-700,
+// 862-885).  No CPU fallback exists: every entry point that computes needs a
+// CUDA device and reports ALB_ERR_CUDA otherwise.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "alb_common.cuh"
+
+using namespace alb;
+
+namespace {
+
+constexpr int ME_RING = ALB_ME_HISTORY + 1;   // 4096 slots of {Fx, Fy}
+constexpr int DIAG_BLOCKS = 148 * 4;          // fixed reduction grid -> deterministic partials
+constexpr long long WAIT_TIMEOUT_NS = 20LL * 1000 * 1000 * 1000;
+
+thread_local std::string g_create_error;
+
+struct Peer {
+    float *base = nullptr;      // the neighbour's population block (f[0] at base, f[1] at base + 9*plane)
+    int *flags = nullptr;       // the neighbour's flag words (device memory, peer mapped)
+    size_t plane = 0;
+    int nyl = 0;
+    void *ipc_base = nullptr;   // non-null when opened through CUDA IPC (to close on destroy)
+};
+
+struct IpcBlob {
+    cudaIpcMemHandle_t mem;     // 64 bytes
+    int nx, nyl, pitch, device;
+    unsigned long long plane;
+    unsigned long long flags_offset_bytes;
+    int magic;
+};
+static_assert(sizeof(IpcBlob) <= ALB_IPC_BYTES, "blob too large");
+
+}  // namespace
+
+struct alb_handle {
+    int nx = 0, ny_global = 0, y0 = 0, nyl = 0, nrows = 0, pitch = 0, tpr = 0, device = 0;
+    size_t plane = 0;
+    char *block = nullptr;        // one allocation: f[0], f[1], flag words (exported through IPC)
+    float *f[2] = {nullptr, nullptr};
+    int *flags = nullptr;         // [0] steps completed by the lower neighbour, [1] by the upper one
+    int cur = 0;
+    float *rho = nullptr, *ux = nullptr, *uy = nullptr;
+    bool macro_valid = true;
+    uint8_t *mask = nullptr;
+    uint16_t *info = nullptr;
+    uint8_t *tclass = nullptr;
+    double u0 = 0.06, tau = 0.58;
+    float u0f = 0, tauf = 0, inv_tau = 0;
+    float feq0[9];
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    long long steps = 0;          // user-visible step count
+    long long sync_steps = 0;     // monotonic, drives the halo flags and the ME ring
+    long long *me_ring = nullptr;
+    unsigned long long *clamp_hits = nullptr;
+    double *d_xp = nullptr, *d_yp = nullptr;
+    double xp[ALB_NPANEL + 1], yp[ALB_NPANEL + 1];
+    bool have_panels = false;
+    double *d_part = nullptr, *h_part = nullptr;
+    float *d_tmp[3] = {nullptr, nullptr, nullptr};   // dense staging for U/V/Cp, field, rgba
+    double maxS = 0.6, cpMin = -1.0, cpMax = 1.0;    // HTML:593
+    bool ema_valid = false;
+    double cl_smooth = 0, cd_smooth = 0, sep_frac = 0;
+    Peer lo, hi;
+    bool external_halo = false;
+    int *h_err = nullptr;         // mapped pinned: set by a wait kernel that timed out
+    int *d_err = nullptr;
+    std::string err;
+
+    int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
+        char buf[512];
+        if (e != cudaSuccess)
+            snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+        else
+            snprintf(buf, sizeof buf, "%s", what);
+        err = buf;
+        return code;
+    }
+    bool whole() const { return y0 == 0 && nyl == ny_global; }
+    double chord_l() const { return nx / (DX1 - DX0); }   // HTML:77
+    double qdyn() const { return 0.5 * u0 * u0 * chord_l(); }   // HTML:676
+};
+
+#define CK(expr)                                                          \
+    do {                                                                  \
+        cudaError_t e_ = (expr);                                          \
+        if (e_ != cudaSuccess) return h->fail(ALB_ERR_CUDA, #expr, e_);   \
+    } while (0)
+#define NEED(h) \
+    if (!(h)) return ALB_ERR_INVALID; \
+    if (cudaSetDevice((h)->device) != cudaSuccess) return (h)->fail(ALB_ERR_CUDA, "cudaSetDevice")
+#define ARG(cond, msg) \
+    if (!(cond)) return h->fail(ALB_ERR_INVALID, msg)
+
+namespace {
+
+__global__ void wait_kernel(volatile int *flag_a, volatile int *flag_b, int target, int *err,
+                            long long timeout_ns) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((flag_a && (int)(*flag_a - target) < 0) || (flag_b && (int)(*flag_b - target) < 0)) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if ((long long)(t1 - t0) > timeout_ns) {
+            *err = 1;
+            break;
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
+__global__ void signal_kernel(int *peer_a, int *peer_b, int value) {
+    __threadfence_system();
+    if (peer_a) *(volatile int *)peer_a = value;
+    if (peer_b) *(volatile int *)peer_b = value;
+    __threadfence_system();
+}
+
+void refresh_params(alb_handle *h) {
+    h->u0f = (float)h->u0;
+    h->tauf = (float)h->tau;
+    h->inv_tau = 1.0f / h->tauf;
+    host_feq0(h->u0f, h->feq0);
+}
+
+StepParams make_params(alb_handle *h, int src_idx) {
+    StepParams p;
+    memset(&p, 0, sizeof p);
+    p.src = h->f[src_idx];
+    p.dst = h->f[1 - src_idx];
+    p.info = h->info;
+    p.tclass = h->tclass;
+    p.plane = h->plane;
+    p.pitch = h->pitch;
+    p.tpr = h->tpr;
+    p.ntasks = h->nyl * h->tpr;
+    p.nyl = h->nyl;
+    p.nx = h->nx;
+    p.tau = h->tauf;
+    p.inv_tau = h->inv_tau;
+    p.u0 = h->u0f;
+    memcpy(p.feq0, h->feq0, sizeof p.feq0);
+    p.rho = h->rho;
+    p.ux = h->ux;
+    p.uy = h->uy;
+    p.clamp_hits = h->clamp_hits;
+    return p;
+}
+
+// Materialise rho/ux/uy of the current state: they are a function of the
+// PREVIOUS state (still intact in the other ping-pong buffer), the mask and the
+// parameters the last step ran with -- so this is called before any of those
+// change.  Costs one read of the populations instead of 12 B/cell on every step.
+int ensure_macro(alb_handle *h) {
+    if (h->macro_valid) return ALB_OK;
+    StepParams p = make_params(h, 1 - h->cur);
+    CK(launch_macro(p, h->stream));
+    h->macro_valid = true;
+    return ALB_OK;
+}
+
+int rebuild_info(alb_handle *h) {
+    CK(launch_build_info(h->mask, h->info, h->tclass, h->pitch, h->nx, h->ny_global, h->y0 - 1, h->nrows,
+                         h->stream));
+    return ALB_OK;
+}
+
+int do_reset(alb_handle *h, double u0) {
+    // HTML:474-490: float64 equilibrium at rho = 1, u = (u0, 0), rounded to fp32 on store
+    const double w0 = 4.0 / 9.0, ws = 1.0 / 9.0, wd = 1.0 / 36.0;
+    const double W[9] = {w0, ws, ws, ws, ws, wd, wd, wd, wd};
+    const int EX[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+    float e[9];
+    for (int i = 0; i < 9; i++) {
+        volatile double eu = EX[i] * u0, uu = u0 * u0;
+        volatile double t1 = 3 * eu, s1 = 1 + t1, t2 = 4.5 * eu, t3 = t2 * eu, s2 = s1 + t3;
+        volatile double t4 = 1.5 * uu, s3 = s2 - t4;
+        e[i] = (float)(W[i] * s3);
+    }
+    h->u0 = u0;
+    refresh_params(h);
+    CK(launch_fill_init(h->f[0], h->f[1], h->plane, e, h->rho, h->ux, h->uy, (float)u0, h->stream));
+    CK(cudaMemsetAsync(h->me_ring, 0, sizeof(long long) * 2 * ME_RING, h->stream));
+    CK(cudaMemsetAsync(h->clamp_hits, 0, sizeof(unsigned long long), h->stream));
+    h->cur = 0;
+    h->steps = 0;
+    h->macro_valid = true;
+    return ALB_OK;
+}
+
+int copy_out_rows(alb_handle *h, void *dst_host, const void *src_dev_row1, size_t elem) {
+    // dense [nyl][nx] <- padded rows 1..nyl
+    CK(cudaMemcpy2DAsync(dst_host, (size_t)h->nx * elem, src_dev_row1, (size_t)h->pitch * elem,
+                         (size_t)h->nx * elem, h->nyl, cudaMemcpyDeviceToHost, h->stream));
+    return ALB_OK;
+}
+
+int check_wait_error(alb_handle *h) {
+    if (h->h_err && *h->h_err) {
+        *h->h_err = 0;
+        return h->fail(ALB_ERR_TIMEOUT, "timed out waiting for a neighbouring slab's halo");
+    }
+    return ALB_OK;
+}
+
+void free_handle(alb_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->lo.ipc_base) cudaIpcCloseMemHandle(h->lo.ipc_base);
+    if (h->hi.ipc_base) cudaIpcCloseMemHandle(h->hi.ipc_base);
+    cudaFree(h->block);
+    cudaFree(h->rho);
+    cudaFree(h->ux);
+    cudaFree(h->uy);
+    cudaFree(h->mask);
+    cudaFree(h->info);
+    cudaFree(h->tclass);
+    cudaFree(h->me_ring);
+    cudaFree(h->clamp_hits);
+    cudaFree(h->d_xp);
+    cudaFree(h->d_yp);
+    cudaFree(h->d_part);
+    for (auto &t : h->d_tmp) cudaFree(t);
+    if (h->h_part) cudaFreeHost(h->h_part);
+    if (h->h_err) cudaFreeHost(h->h_err);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int ensure_tmp(alb_handle *h, int k) {
+    if (!h->d_tmp[k]) CK(cudaMalloc(&h->d_tmp[k], sizeof(float) * (size_t)h->nx * h->nyl));
+    return ALB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int alb_version(void) { return ALB_VERSION; }
+
+const char *alb_error_string(int code) {
+    switch (code) {
+        case ALB_OK: return "ok";
+        case ALB_ERR_INVALID: return "invalid argument";
+        case ALB_ERR_CUDA: return "CUDA error";
+        case ALB_ERR_NOMEM: return "out of memory";
+        case ALB_ERR_STATE: return "invalid state";
+        case ALB_ERR_TIMEOUT: return "halo wait timed out";
+        default: return "unknown error";
+    }
+}
+
+const char *alb_last_error(const alb_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int alb_device_count(int *count) {
+    if (!count) return ALB_ERR_INVALID;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        g_create_error = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+        return ALB_ERR_CUDA;
+    }
+    return ALB_OK;
+}
+
+int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb_handle **out) {
+    if (!out) return ALB_ERR_INVALID;
+    *out = nullptr;
+    if (nx < 3 || ny_global < 3 || ny_local < 1 || y0 < 0 || y0 + ny_local > ny_global ||
+        ny_global > 65000 || nx > (1 << 24)) {
+        g_create_error = "alb_create: need 3 <= nx <= 2^24, 3 <= ny <= 65000, 0 <= y0, y0 + ny_local <= ny";
+        return ALB_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device (this library has no CPU fallback): ") +
+                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return ALB_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "alb_create: device index out of range";
+        return ALB_ERR_INVALID;
+    }
+    alb_handle *h = new (std::nothrow) alb_handle;
+    if (!h) return ALB_ERR_NOMEM;
+    h->nx = nx;
+    h->ny_global = ny_global;
+    h->y0 = y0;
+    h->nyl = ny_local;
+    h->nrows = ny_local + 2;
+    h->pitch = (nx + TASK_CELLS - 1) / TASK_CELLS * TASK_CELLS;
+    h->tpr = h->pitch / TASK_CELLS;
+    h->plane = (size_t)h->nrows * h->pitch;
+    h->device = device;
+    int rc = ALB_OK;
+    auto body = [&]() -> int {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&h->ev0));
+        CK(cudaEventCreate(&h->ev1));
+        const size_t pop_bytes = sizeof(float) * 18 * h->plane;
+        CK(cudaMalloc(&h->block, pop_bytes + 256));
+        h->f[0] = reinterpret_cast<float *>(h->block);
+        h->f[1] = h->f[0] + 9 * h->plane;
+        h->flags = reinterpret_cast<int *>(h->block + pop_bytes);
+        CK(cudaMemsetAsync(h->flags, 0, 256, h->stream));
+        CK(cudaMalloc(&h->rho, sizeof(float) * h->plane));
+        CK(cudaMalloc(&h->ux, sizeof(float) * h->plane));
+        CK(cudaMalloc(&h->uy, sizeof(float) * h->plane));
+        CK(cudaMalloc(&h->mask, h->plane));
+        CK(cudaMalloc(&h->info, sizeof(uint16_t) * h->plane));
+        CK(cudaMalloc(&h->tclass, (size_t)h->nrows * h->tpr));
+        CK(cudaMalloc(&h->me_ring, sizeof(long long) * 2 * ME_RING));
+        CK(cudaMalloc(&h->clamp_hits, sizeof(unsigned long long)));
+        CK(cudaMalloc(&h->d_xp, sizeof(double) * 1024));
+        CK(cudaMalloc(&h->d_yp, sizeof(double) * 1024));
+        CK(cudaMalloc(&h->d_part, sizeof(double) * 4 * DIAG_BLOCKS));
+        CK(cudaHostAlloc(&h->h_part, sizeof(double) * 4 * DIAG_BLOCKS, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&h->h_err, sizeof(int), cudaHostAllocMapped));
+        *h->h_err = 0;
+        CK(cudaHostGetDevicePointer(&h->d_err, h->h_err, 0));
+        CK(cudaMemsetAsync(h->mask, 0, h->plane, h->stream));
+        int r = rebuild_info(h);
+        if (r) return r;
+        r = do_reset(h, 0.06);   // HTML:472, 503
+        if (r) return r;
+        CK(cudaStreamSynchronize(h->stream));
+        return ALB_OK;
+    };
+    rc = body();
+    if (rc != ALB_OK) {
+        g_create_error = h->err;
+        free_handle(h);
+        return rc;
+    }
+    *out = h;
+    return ALB_OK;
+}
+
+int alb_create(int nx, int ny, int device, alb_handle **out) {
+    return alb_create_slab(nx, ny, 0, ny, device, out);
+}
+
+int alb_destroy(alb_handle *h) {
+    if (!h) return ALB_ERR_INVALID;
+    free_handle(h);
+    return ALB_OK;
+}
+
+int alb_get_dims(const alb_handle *h, int *nx, int *ny_global, int *y0, int *ny_local) {
+    if (!h) return ALB_ERR_INVALID;
+    if (nx) *nx = h->nx;
+    if (ny_global) *ny_global = h->ny_global;
+    if (y0) *y0 = h->y0;
+    if (ny_local) *ny_local = h->nyl;
+    return ALB_OK;
+}
+
+int alb_set_params(alb_handle *h, double u0, double tau) {
+    NEED(h);
+    ARG(isfinite(u0) && isfinite(tau) && (float)tau != 0.0f, "alb_set_params: u0 and tau must be finite, tau != 0");
+    int r = ensure_macro(h);
+    if (r) return r;
+    h->u0 = u0;
+    h->tau = tau;
+    refresh_params(h);
+    return ALB_OK;
+}
+
+int alb_get_params(const alb_handle *h, double *u0, double *tau) {
+    if (!h) return ALB_ERR_INVALID;
+    if (u0) *u0 = h->u0;
+    if (tau) *tau = h->tau;
+    return ALB_OK;
+}
+
+int alb_reset(alb_handle *h, double u0) {
+    NEED(h);
+    ARG(isfinite(u0), "alb_reset: u0 must be finite");
+    return do_reset(h, u0);
+}
+
+int alb_rasterize_panels(alb_handle *h, const double *xp, const double *yp, int n, uint8_t *mask_out) {
+    NEED(h);
+    ARG(xp && yp && n >= 2 && n <= 1024, "alb_rasterize_panels: need 2 <= n <= 1024 panel nodes");
+    int r = ensure_macro(h);
+    if (r) return r;
+    CK(cudaMemcpyAsync(h->d_xp, xp, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_yp, yp, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // xp/yp are caller memory
+    CK(launch_raster(h->d_xp, h->d_yp, n, h->mask, h->pitch, h->nx, h->ny_global, h->y0 - 1, h->nrows,
+                     h->stream));
+    r = rebuild_info(h);
+    if (r) return r;
+    if (mask_out) {
+        r = copy_out_rows(h, mask_out, h->mask + h->pitch, 1);
+        if (r) return r;
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return ALB_OK;
+}
+
+int alb_rasterize(alb_handle *h, const double *xy, int npts, double alpha_deg, uint8_t *mask_out) {
+    NEED(h);
+    ARG(xy && npts >= 2 && npts <= 100000, "alb_rasterize: need 2 <= npts <= 100000 coordinate pairs");
+    ARG(isfinite(alpha_deg), "alb_rasterize: alpha must be finite");
+    for (int i = 0; i < 2 * npts; i++) ARG(isfinite(xy[i]), "alb_rasterize: coordinates must be finite");
+    try {
+        host_rotate_panelise(xy, npts, alpha_deg, h->xp, h->yp);
+    } catch (const std::bad_alloc &) {
+        return h->fail(ALB_ERR_NOMEM, "alb_rasterize: host allocation failed");
+    }
+    h->have_panels = true;
+    return alb_rasterize_panels(h, h->xp, h->yp, ALB_NPANEL + 1, mask_out);
+}
+
+int alb_set_mask(alb_handle *h, const uint8_t *mask_global) {
+    NEED(h);
+    ARG(mask_global, "alb_set_mask: mask is NULL");
+    int r = ensure_macro(h);
+    if (r) return r;
+    CK(cudaMemsetAsync(h->mask, 0, h->plane, h->stream));
+    const int gy_lo = h->y0 - 1 < 0 ? 0 : h->y0 - 1;
+    const int gy_hi = h->y0 + h->nyl + 1 > h->ny_global ? h->ny_global : h->y0 + h->nyl + 1;
+    const int j_lo = gy_lo - (h->y0 - 1);
+    CK(cudaMemcpy2DAsync(h->mask + (size_t)j_lo * h->pitch, h->pitch, mask_global + (size_t)gy_lo * h->nx,
+                         h->nx, h->nx, gy_hi - gy_lo, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return rebuild_info(h);
+}
+
+int alb_get_mask(alb_handle *h, uint8_t *mask_out) {
+    NEED(h);
+    ARG(mask_out, "alb_get_mask: output is NULL");
+    int r = copy_out_rows(h, mask_out, h->mask + h->pitch, 1);
+    if (r) return r;
+    CK(cudaStreamSynchronize(h->stream));
+    return ALB_OK;
+}
+
+int alb_get_panels(const alb_handle *h, double *xp, double *yp) {
+    if (!h) return ALB_ERR_INVALID;
+    if (!h->have_panels) return const_cast<alb_handle *>(h)->fail(ALB_ERR_STATE, "alb_get_panels: no alb_rasterize() yet");
+    if (xp) memcpy(xp, h->xp, sizeof h->xp);
+    if (yp) memcpy(yp, h->yp, sizeof h->yp);
+    return ALB_OK;
+}
+
+int alb_step(alb_handle *h, int nsteps) {
+    NEED(h);
+    ARG(nsteps >= 0, "alb_step: nsteps must be >= 0");
+    if (nsteps == 0) return ALB_OK;
+    const bool halo = !h->external_halo && (h->lo.base || h->hi.base);
+    CK(cudaEventRecord(h->ev0, h->stream));
+    for (int s = 0; s < nsteps; s++) {
+        StepParams p = make_params(h, h->cur);
+        const long long slot = h->sync_steps % ME_RING;
+        p.me_slot = h->me_ring + 2 * slot;
+        p.me_next = h->me_ring + 2 * ((slot + 1) % ME_RING);
+        if (halo) {
+            // my step k needs the neighbours' k completed steps: their edge rows of state k are in
+            // my ghost rows, and they no longer read the ghost rows I am about to overwrite.
+            wait_kernel<<<1, 1, 0, h->stream>>>(h->lo.base ? h->flags + 0 : nullptr,
+                                                h->hi.base ? h->flags + 1 : nullptr,
+                                                (int)h->sync_steps, h->d_err, WAIT_TIMEOUT_NS);
+            const int dst_idx = 1 - h->cur;
+            if (h->lo.base) {
+                p.peer_lo_dst = h->lo.base + (size_t)dst_idx * 9 * h->lo.plane;
+                p.peer_lo_plane = h->lo.plane;
+                p.peer_lo_row = (size_t)(h->lo.nyl + 1) * h->pitch;
+            }
+            if (h->hi.base) {
+                p.peer_hi_dst = h->hi.base + (size_t)dst_idx * 9 * h->hi.plane;
+                p.peer_hi_plane = h->hi.plane;
+                p.peer_hi_row = 0;
+            }
+        }
+        CK(launch_step(p, h->stream));
+        h->cur = 1 - h->cur;
+        h->steps++;
+        h->sync_steps++;
+        if (halo) {
+            // I am the UPPER neighbour of lo (its flags[1]) and the LOWER neighbour of hi (its flags[0])
+            signal_kernel<<<1, 1, 0, h->stream>>>(h->lo.flags ? h->lo.flags + 1 : nullptr,
+                                                  h->hi.flags ? h->hi.flags + 0 : nullptr,
+                                                  (int)h->sync_steps);
+        }
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->macro_valid = false;
+    return ALB_OK;
+}
+
+int alb_sync(alb_handle *h) {
+    NEED(h);
+    CK(cudaStreamSynchronize(h->stream));
+    return check_wait_error(h);
+}
+
+int alb_step_count(const alb_handle *h, long long *steps) {
+    if (!h || !steps) return ALB_ERR_INVALID;
+    *steps = h->steps;
+    return ALB_OK;
+}
+
+int alb_last_step_ms(alb_handle *h, float *ms) {
+    NEED(h);
+    ARG(ms, "alb_last_step_ms: output is NULL");
+    if (!h->timed) return h->fail(ALB_ERR_STATE, "alb_last_step_ms: no alb_step() yet");
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return check_wait_error(h);
+}
+
+int alb_get_populations(alb_handle *h, float *f) {
+    NEED(h);
+    ARG(f, "alb_get_populations: output is NULL");
+    const size_t dense = (size_t)h->nx * h->nyl;
+    for (int i = 0; i < 9; i++) {
+        int r = copy_out_rows(h, f + i * dense, h->f[h->cur] + i * h->plane + h->pitch, sizeof(float));
+        if (r) return r;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return check_wait_error(h);
+}
+
+int alb_set_populations(alb_handle *h, const float *f) {
+    NEED(h);
+    ARG(f, "alb_set_populations: input is NULL");
+    int r = ensure_macro(h);
+    if (r) return r;
+    const size_t dense = (size_t)h->nx * h->nyl;
+    for (int i = 0; i < 9; i++)
+        CK(cudaMemcpy2DAsync(h->f[h->cur] + i * h->plane + h->pitch, sizeof(float) * h->pitch, f + i * dense,
+                             sizeof(float) * h->nx, sizeof(float) * h->nx, h->nyl, cudaMemcpyHostToDevice,
+                             h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return ALB_OK;
+}
+
+int alb_get_macro(alb_handle *h, float *rho, float *ux, float *uy) {
+    NEED(h);
+    int r = ensure_macro(h);
+    if (r) return r;
+    if (rho && (r = copy_out_rows(h, rho, h->rho + h->pitch, sizeof(float)))) return r;
+    if (ux && (r = copy_out_rows(h, ux, h->ux + h->pitch, sizeof(float)))) return r;
+    if (uy && (r = copy_out_rows(h, uy, h->uy + h->pitch, sizeof(float)))) return r;
+    CK(cudaStreamSynchronize(h->stream));
+    return check_wait_error(h);
+}
+
+int alb_set_macro(alb_handle *h, const float *rho, const float *ux, const float *uy) {
+    NEED(h);
+    const float *srcs[3] = {rho, ux, uy};
+    float *dsts[3] = {h->rho, h->ux, h->uy};
+    for (int k = 0; k < 3; k++)
+        if (srcs[k])
+            CK(cudaMemcpy2DAsync(dsts[k] + h->pitch, sizeof(float) * h->pitch, srcs[k], sizeof(float) * h->nx,
+                                 sizeof(float) * h->nx, h->nyl, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->macro_valid = true;
+    return ALB_OK;
+}
+
+int alb_total_mass(alb_handle *h, double *mass) {
+    NEED(h);
+    ARG(mass, "alb_total_mass: output is NULL");
+    CK(launch_mass(h->f[h->cur], h->plane, h->pitch, h->nx, h->nyl, h->d_part, DIAG_BLOCKS, h->stream));
+    CK(cudaMemcpyAsync(h->h_part, h->d_part, sizeof(double) * DIAG_BLOCKS, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    double m = 0;
+    for (int b = 0; b < DIAG_BLOCKS; b++) m += h->h_part[b];
+    *mass = m;
+    return ALB_OK;
+}
+
+int alb_stats_partial(alb_handle *h, double *out3, float *U, float *V, float *Cp) {
+    NEED(h);
+    int r = ensure_macro(h);
+    if (r) return r;
+    float *dU = nullptr, *dV = nullptr, *dC = nullptr;
+    if (U) { if ((r = ensure_tmp(h, 0))) return r; dU = h->d_tmp[0]; }
+    if (V) { if ((r = ensure_tmp(h, 1))) return r; dV = h->d_tmp[1]; }
+    if (Cp) { if ((r = ensure_tmp(h, 2))) return r; dC = h->d_tmp[2]; }
+    CK(launch_stats(h->mask, h->rho, h->ux, h->uy, h->pitch, h->nx, h->nyl, h->u0, dU, dV, dC, h->d_part,
+                    DIAG_BLOCKS, h->stream));
+    CK(cudaMemcpyAsync(h->h_part, h->d_part, sizeof(double) * 3 * DIAG_BLOCKS, cudaMemcpyDeviceToHost, h->stream));
+    const size_t bytes = sizeof(float) * (size_t)h->nx * h->nyl;
+    if (U) CK(cudaMemcpyAsync(U, dU, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (V) CK(cudaMemcpyAsync(V, dV, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (Cp) CK(cudaMemcpyAsync(Cp, dC, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    double mx = 0, cmin = INFINITY, cmax = -INFINITY;
+    for (int b = 0; b < DIAG_BLOCKS; b++) {
+        mx = fmax(mx, h->h_part[3 * b]);
+        cmin = fmin(cmin, h->h_part[3 * b + 1]);
+        cmax = fmax(cmax, h->h_part[3 * b + 2]);
+    }
+    if (out3) { out3[0] = mx; out3[1] = cmin; out3[2] = cmax; }
+    return check_wait_error(h);
+}
+
+int alb_update_stats(alb_handle *h, double *stats, float *U, float *V, float *Cp) {
+    double raw[3];
+    int r = alb_stats_partial(h, raw, U, V, Cp);
+    if (r) return r;
+    if (raw[0] > 0) h->maxS = raw[0];            // HTML:611-613
+    if (isfinite(raw[1])) h->cpMin = raw[1];
+    if (isfinite(raw[2])) h->cpMax = raw[2];
+    if (stats) { stats[0] = h->maxS; stats[1] = h->cpMin; stats[2] = h->cpMax; }
+    return ALB_OK;
+}
+
+int alb_set_stats(alb_handle *h, double maxS, double cpMin, double cpMax) {
+    if (!h) return ALB_ERR_INVALID;
+    h->maxS = maxS; h->cpMin = cpMin; h->cpMax = cpMax;
+    return ALB_OK;
+}
+
+int alb_get_stats(const alb_handle *h, double *stats3) {
+    if (!h || !stats3) return ALB_ERR_INVALID;
+    stats3[0] = h->maxS; stats3[1] = h->cpMin; stats3[2] = h->cpMax;
+    return ALB_OK;
+}
+
+static int render_common(alb_handle *h, int mode, float *t_out, uint8_t *rgba) {
+    NEED(h);
+    ARG(mode >= 0 && mode <= 2, "field mode must be 0 (speed), 1 (Cp) or 2 (vorticity)");
+    if (!h->whole()) return h->fail(ALB_ERR_STATE, "field rendering needs a whole-lattice handle");
+    int r = ensure_macro(h);
+    if (r) return r;
+    if ((r = ensure_tmp(h, 0))) return r;
+    if ((r = ensure_tmp(h, 1))) return r;
+    float *dt = h->d_tmp[0];
+    uint8_t *drgba = reinterpret_cast<uint8_t *>(h->d_tmp[1]);
+    CK(launch_render(h->mask, h->rho, h->ux, h->uy, h->pitch, h->nx, h->nyl, mode, h->u0f, (float)h->maxS,
+                     (float)h->cpMin, (float)h->cpMax, 0.06f, dt, rgba ? drgba : nullptr, h->stream));
+    const size_t n = (size_t)h->nx * h->nyl;
+    if (t_out) CK(cudaMemcpyAsync(t_out, dt, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (rgba) CK(cudaMemcpyAsync(rgba, drgba, 4 * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return check_wait_error(h);
+}
+
+int alb_get_field(alb_handle *h, int mode, float *t_out) {
+    if (h && !t_out) return h->fail(ALB_ERR_INVALID, "alb_get_field: output is NULL");
+    return render_common(h, mode, t_out, nullptr);
+}
+
+int alb_get_rgba(alb_handle *h, int mode, uint8_t *rgba) {
+    if (h && !rgba) return h->fail(ALB_ERR_INVALID, "alb_get_rgba: output is NULL");
+    return render_common(h, mode, nullptr, rgba);
+}
+
+int alb_forces_partial(alb_handle *h, double *out4) {
+    NEED(h);
+    ARG(out4, "alb_forces_partial: output is NULL");
+    int r = ensure_macro(h);
+    if (r) return r;
+    CK(launch_forces(h->mask, h->rho, h->ux, h->pitch, h->nx, h->ny_global, h->y0 - 1, h->nyl, h->d_part,
+                     DIAG_BLOCKS, h->stream));
+    CK(cudaMemcpyAsync(h->h_part, h->d_part, sizeof(double) * 4 * DIAG_BLOCKS, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    double s[4] = {0, 0, 0, 0};
+    for (int b = 0; b < DIAG_BLOCKS; b++)
+        for (int k = 0; k < 4; k++) s[k] += h->h_part[4 * b + k];
+    memcpy(out4, s, sizeof s);
+    return check_wait_error(h);
+}
+
+int alb_compute_forces(alb_handle *h, double *out10) {
+    NEED(h);
+    ARG(out10, "alb_compute_forces: output is NULL");
+    if (!h->whole()) return h->fail(ALB_ERR_STATE, "alb_compute_forces needs a whole-lattice handle; use alb_forces_partial");
+    double s[4];
+    int r = alb_forces_partial(h, s);
+    if (r) return r;
+    const bool any = s[2] > 0;
+    double cl_raw = 0, cd_raw = 0;
+    if (any) {                                   // HTML:672-679, 699
+        const double q = h->qdyn();
+        cl_raw = s[1] / q;
+        cd_raw = s[0] / q;
+        if (!h->ema_valid) {
+            h->cl_smooth = cl_raw;
+            h->cd_smooth = cd_raw;
+            h->ema_valid = true;
+        } else {
+            h->cl_smooth = h->cl_smooth * 0.9 + cl_raw * 0.1;
+            h->cd_smooth = h->cd_smooth * 0.9 + cd_raw * 0.1;
+        }
+        h->sep_frac = h->sep_frac * 0.85 + (s[3] / s[2]) * 0.15;
+    }
+    out10[0] = s[0]; out10[1] = s[1]; out10[2] = cl_raw; out10[3] = cd_raw;
+    out10[4] = h->ema_valid ? h->cl_smooth : NAN;
+    out10[5] = h->ema_valid ? h->cd_smooth : NAN;
+    out10[6] = h->sep_frac; out10[7] = s[2]; out10[8] = s[3]; out10[9] = any ? 1.0 : 0.0;
+    return ALB_OK;
+}
+
+int alb_reset_force_emas(alb_handle *h) {
+    if (!h) return ALB_ERR_INVALID;
+    h->ema_valid = false;
+    h->cl_smooth = h->cd_smooth = h->sep_frac = 0;
+    return ALB_OK;
+}
+
+int alb_get_me_history(alb_handle *h, int n, long long *fxfy) {
+    NEED(h);
+    ARG(fxfy && n >= 0 && n <= ALB_ME_HISTORY, "alb_get_me_history: need 0 <= n <= ALB_ME_HISTORY");
+    if (n > h->steps) return h->fail(ALB_ERR_STATE, "alb_get_me_history: fewer steps taken than requested");
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < n; k++) {
+        const long long step = h->sync_steps - n + k;
+        const long long slot = step % ME_RING;
+        CK(cudaMemcpy(fxfy + 2 * k, h->me_ring + 2 * slot, sizeof(long long) * 2, cudaMemcpyDeviceToHost));
+    }
+    return check_wait_error(h);
+}
+
+int alb_get_me_forces(alb_handle *h, double *out4) {
+    NEED(h);
+    ARG(out4, "alb_get_me_forces: output is NULL");
+    long long v[2];
+    int r = alb_get_me_history(h, 1, v);
+    if (r) return r;
+    const double fx = (double)v[0] / ALB_ME_SCALE, fy = (double)v[1] / ALB_ME_SCALE;
+    const double q = h->qdyn();
+    out4[0] = fx; out4[1] = fy; out4[2] = fy / q; out4[3] = fx / q;
+    return ALB_OK;
+}
+
+int alb_clamp_hits(alb_handle *h, long long *hits) {
+    NEED(h);
+    ARG(hits, "alb_clamp_hits: output is NULL");
+    unsigned long long v = 0;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(&v, h->clamp_hits, sizeof v, cudaMemcpyDeviceToHost));
+    *hits = (long long)v;
+    return ALB_OK;
+}
+
+int alb_reynolds(const alb_handle *h, double *re) {
+    if (!h || !re) return ALB_ERR_INVALID;
+    const double nu_l = (h->tau - 0.5) / 3;       // HTML:79
+    *re = h->u0 * h->chord_l() / nu_l;            // HTML:865
+    return ALB_OK;
+}
+
+int alb_stall_state(const alb_handle *h, int *state, int *sep_pct) {
+    if (!h) return ALB_ERR_INVALID;
+    const int pct = (int)floor(h->sep_frac * 100 + 0.5);   // Math.round, HTML:869
+    if (sep_pct) *sep_pct = pct;
+    if (state) *state = pct < 5 ? 0 : (pct < 25 ? 1 : 2);  // HTML:872-884
+    return ALB_OK;
+}
+
+/* ---- multi-GPU y-slabs ------------------------------------------------------ */
+
+int alb_connect_local(alb_handle *h, alb_handle *lo, alb_handle *hi) {
+    NEED(h);
+    alb_handle *peers[2] = {lo, hi};
+    for (alb_handle *p : peers) {
+        if (!p) continue;
+        ARG(p->nx == h->nx && p->ny_global == h->ny_global, "alb_connect_local: neighbour has a different lattice");
+        if (p->device != h->device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, h->device, p->device));
+            if (!can) return h->fail(ALB_ERR_CUDA, "alb_connect_local: no peer access between the two devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(p->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return h->fail(ALB_ERR_CUDA, "cudaDeviceEnablePeerAccess", e);
+            cudaGetLastError();
+        }
+    }
+    if (lo) ARG(lo->y0 + lo->nyl == h->y0, "alb_connect_local: lower neighbour does not end where this slab starts");
+    if (hi) ARG(h->y0 + h->nyl == hi->y0, "alb_connect_local: upper neighbour does not start where this slab ends");
+    h->lo = Peer();
+    h->hi = Peer();
+    if (lo) { h->lo.base = lo->f[0]; h->lo.flags = lo->flags; h->lo.plane = lo->plane; h->lo.nyl = lo->nyl; }
+    if (hi) { h->hi.base = hi->f[0]; h->hi.flags = hi->flags; h->hi.plane = hi->plane; h->hi.nyl = hi->nyl; }
+    return ALB_OK;
+}
+
+int alb_ipc_export(alb_handle *h, void *blob) {
+    NEED(h);
+    ARG(blob, "alb_ipc_export: blob is NULL");
+    IpcBlob b;
+    memset(&b, 0, sizeof b);
+    CK(cudaIpcGetMemHandle(&b.mem, h->block));
+    b.nx = h->nx; b.nyl = h->nyl; b.pitch = h->pitch; b.device = h->device;
+    b.plane = h->plane;
+    b.flags_offset_bytes = sizeof(float) * 18 * h->plane;
+    b.magic = 0x414c4231;
+    memset(blob, 0, ALB_IPC_BYTES);
+    memcpy(blob, &b, sizeof b);
+    return ALB_OK;
+}
+
+static int open_peer(alb_handle *h, const void *blob, Peer *out) {
+    IpcBlob b;
+    memcpy(&b, blob, sizeof b);
+    ARG(b.magic == 0x414c4231, "alb_ipc_connect: not an alb_ipc_export() blob");
+    ARG(b.nx == h->nx && b.pitch == h->pitch, "alb_ipc_connect: neighbour has a different lattice width");
+    void *base = nullptr;
+    CK(cudaIpcOpenMemHandle(&base, b.mem, cudaIpcMemLazyEnablePeerAccess));
+    out->ipc_base = base;
+    out->base = reinterpret_cast<float *>(base);
+    out->flags = reinterpret_cast<int *>(reinterpret_cast<char *>(base) + b.flags_offset_bytes);
+    out->plane = b.plane;
+    out->nyl = b.nyl;
+    return ALB_OK;
+}
+
+int alb_ipc_connect(alb_handle *h, const void *lo_blob, const void *hi_blob) {
+    NEED(h);
+    if (h->lo.ipc_base) { cudaIpcCloseMemHandle(h->lo.ipc_base); }
+    if (h->hi.ipc_base) { cudaIpcCloseMemHandle(h->hi.ipc_base); }
+    h->lo = Peer();
+    h->hi = Peer();
+    int r;
+    if (lo_blob && (r = open_peer(h, lo_blob, &h->lo))) return r;
+    if (hi_blob && (r = open_peer(h, hi_blob, &h->hi))) return r;
+    return ALB_OK;
+}
+
+int alb_halo_prime(alb_handle *h) {
+    NEED(h);
+    // push my edge rows of the CURRENT state into the neighbours' ghost rows, then publish my step count
+    const size_t rowb = sizeof(float) * h->pitch;
+    const int lo_pops[3] = {4, 7, 8}, hi_pops[3] = {2, 5, 6};
+    if (h->lo.base)
+        for (int k = 0; k < 3; k++) {
+            const int i = lo_pops[k];
+            CK(cudaMemcpyAsync(h->lo.base + (size_t)h->cur * 9 * h->lo.plane + i * h->lo.plane +
+                                   (size_t)(h->lo.nyl + 1) * h->pitch,
+                               h->f[h->cur] + i * h->plane + (size_t)1 * h->pitch, rowb, cudaMemcpyDefault,
+                               h->stream));
+        }
+    if (h->hi.base)
+        for (int k = 0; k < 3; k++) {
+            const int i = hi_pops[k];
+            CK(cudaMemcpyAsync(h->hi.base + (size_t)h->cur * 9 * h->hi.plane + i * h->hi.plane,
+                               h->f[h->cur] + i * h->plane + (size_t)h->nyl * h->pitch, rowb, cudaMemcpyDefault,
+                               h->stream));
+        }
+    signal_kernel<<<1, 1, 0, h->stream>>>(h->lo.flags ? h->lo.flags + 1 : nullptr,
+                                          h->hi.flags ? h->hi.flags + 0 : nullptr, (int)h->sync_steps);
+    CK(cudaGetLastError());
+    return ALB_OK;
+}
+
+int alb_halo_ptrs(alb_handle *h, void **send_lo3, void **send_hi3, void **recv_lo3, void **recv_hi3) {
+    NEED(h);
+    float *cur = h->f[h->cur];
+    const int lo_pops[3] = {4, 7, 8}, hi_pops[3] = {2, 5, 6};
+    for (int k = 0; k < 3; k++) {
+        if (send_lo3) send_lo3[k] = cur + lo_pops[k] * h->plane + (size_t)1 * h->pitch;
+        if (send_hi3) send_hi3[k] = cur + hi_pops[k] * h->plane + (size_t)h->nyl * h->pitch;
+        if (recv_lo3) recv_lo3[k] = cur + hi_pops[k] * h->plane;   // ghost row 0 receives the lower slab's f2,f5,f6
+        if (recv_hi3) recv_hi3[k] = cur + lo_pops[k] * h->plane + (size_t)(h->nyl + 1) * h->pitch;
+    }
+    return ALB_OK;
+}
+
+int alb_set_external_halo(alb_handle *h, int on) {
+    if (!h) return ALB_ERR_INVALID;
+    h->external_halo = on != 0;
+    return ALB_OK;
+}
+
+}  // extern "C"

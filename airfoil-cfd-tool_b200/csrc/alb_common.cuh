@@ -1,0 +1,100 @@
+// Shared definitions of libaerolab_lbm.so (B200 / sm_100a).
+//
+// Data layout in HBM:
+//   populations  f[2][9][nrows][pitch] fp32, SoA, ping-pong pair
+//   nrows = ny_local + 2 (one ghost row below and above: the slab halo; on a
+//   whole-lattice handle the ghost rows are never read), pitch = nx rounded up
+//   to 128 cells so that a warp task (128 consecutive cells of one row, four
+//   per lane, one 128-bit access per lane and population) never straddles rows.
+//   mask   u8  [nrows][pitch]   0 / 255, ghost rows included
+//   info   u16 [nrows][pitch]   per-cell type + "pull source is solid" bits
+//   tclass u8  [nrows][pitch/128] per-warp-task class (all fluid / general /
+//                               all solid / all equilibrium)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/aerolab_lbm.h"
+
+namespace alb {
+
+constexpr int TASK_CELLS = 128;          // cells per warp task
+constexpr int BLOCK_THREADS = 256;       // 8 warp tasks per CTA
+constexpr int TASKS_PER_BLOCK = BLOCK_THREADS / 32;
+
+// world window, HTML:73
+constexpr double DX0 = -0.42, DX1 = 1.42, DY0 = -0.46, DY1 = 0.46;
+
+// cell types (info >> 8); priority solid > outlet > equilibrium > interior
+// (HTML:287, 301, 314, 324)
+enum : int { CT_FLUID = 0, CT_SOLID = 1, CT_OUTLET = 2, CT_EQUIL = 3 };
+// warp-task classes
+enum : int { TC_FLUID = 0, TC_GENERAL = 1, TC_SOLID = 2, TC_EQUIL = 3 };
+
+struct StepParams {
+    const float *__restrict__ src;
+    float *__restrict__ dst;
+    const uint16_t *__restrict__ info;
+    const uint8_t *__restrict__ tclass;
+    size_t plane;            // floats per population plane = nrows * pitch
+    int pitch;               // cells per row (multiple of 128)
+    int tpr;                 // warp tasks per row = pitch / 128
+    int ntasks;              // ny_local * tpr
+    int nyl;                 // rows owned by this slab
+    int nx;
+    float tau, inv_tau;      // inv_tau = RN(1/tau)
+    float u0;
+    float feq0[9];           // feq_i(1, U0, 0) in fp32, source order (HTML:315-317)
+    // macro output (macro mode only)
+    float *rho, *ux, *uy;
+    // momentum exchange: slot of this step, slot to clear for the next one
+    long long *me_slot;
+    long long *me_next;
+    unsigned long long *clamp_hits;
+    // halo push into the neighbours' ghost rows (nullable)
+    float *peer_lo_dst;      // base of the lower neighbour's DESTINATION buffer
+    size_t peer_lo_plane;
+    size_t peer_lo_row;      // float offset of its upper ghost row
+    float *peer_hi_dst;
+    size_t peer_hi_plane;
+    size_t peer_hi_row;      // float offset of its lower ghost row (row 0)
+};
+
+struct Handle;
+
+// alb_step.cu
+cudaError_t launch_step(const StepParams &p, cudaStream_t s);
+cudaError_t launch_macro(const StepParams &p, cudaStream_t s);
+void host_feq0(float u0, float *out9);
+
+// alb_geometry.cu
+void host_rotate_panelise(const double *xy, int npts, double alpha_deg, double *xp, double *yp);
+cudaError_t launch_raster(const double *d_xp, const double *d_yp, int n, uint8_t *mask, int pitch,
+                          int nx, int ny_global, int gy_first, int nrows, cudaStream_t s);
+cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tclass, int pitch,
+                              int nx, int ny_global, int gy_first, int nrows, cudaStream_t s);
+
+// alb_diag.cu
+struct DiagScratch {
+    double *d_part = nullptr;     // device partials
+    double *h_part = nullptr;     // pinned host mirror
+    int nblocks = 0;
+};
+cudaError_t launch_stats(const uint8_t *mask, const float *rho, const float *ux, const float *uy,
+                         int pitch, int nx, int nyl, double u0, float *U, float *V, float *Cp,
+                         double *d_part, int nblocks, cudaStream_t s);
+cudaError_t launch_forces(const uint8_t *mask, const float *rho, const float *ux, int pitch, int nx,
+                          int ny_global, int gy_first, int nyl, double *d_part, int nblocks,
+                          cudaStream_t s);
+cudaError_t launch_render(const uint8_t *mask, const float *rho, const float *ux, const float *uy,
+                          int pitch, int nx, int ny, int mode, float u0, float maxS, float cpMin,
+                          float cpMax, float vortScale, float *t_out, uint8_t *rgba, cudaStream_t s);
+cudaError_t launch_mass(const float *f, size_t plane, int pitch, int nx, int nyl, double *d_part,
+                        int nblocks, cudaStream_t s);
+cudaError_t launch_fill_init(float *f0, float *f1, size_t plane, const float *feq9, float *rho,
+                             float *ux, float *uy, float u0, cudaStream_t s);
+
+}  // namespace alb

@@ -1,0 +1,294 @@
+// Subsystem (c): diagnostics on the macroscopic fields.
+//
+//   stats_kernel   updateFieldsFromMacro()        HTML:596-614
+//   forces_kernel  computeForces(): pressure faces + separation counts  HTML:649-700
+//   render_kernel  RENDER_FS_SRC.main (+palettes) HTML:371-422
+//   mass_kernel    total population sum (float64)
+//   fill_kernel    equilibriumInitData()/initSim  HTML:474-500
+//
+// "HTML:n" = pages/airfoil_flow_lbm_aerolab.html.  Reductions are made
+// deterministic by construction: a fixed grid of CTAs, each reducing a fixed
+// set of cells in a fixed order (warp shuffle tree, then one thread sums the
+// warps), one partial per CTA, summed on the host in CTA order.
+#include <math.h>
+
+#include "alb_common.cuh"
+
+namespace alb {
+
+namespace {
+
+constexpr int DIAG_THREADS = 256;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, d));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, d));
+    return v;
+}
+
+// HTML:596-614.  part[3*b + {0,1,2}] = {mx, cMin, cMax} of CTA b.
+__global__ void __launch_bounds__(DIAG_THREADS)
+stats_kernel(const uint8_t *__restrict__ mask, const float *__restrict__ rho,
+             const float *__restrict__ ux, const float *__restrict__ uy, int pitch, int nx, int nyl,
+             double U0, float *U, float *V, float *Cp, double *part) {
+    __shared__ double sm[3][DIAG_THREADS / 32];
+    double mx = 0.0, cmin = INFINITY, cmax = -INFINITY;
+    const double cden = __dmul_rn(__dmul_rn(1.5, U0), U0);   // 1.5*U0*U0
+    const size_t ncell = (size_t)nx * nyl;
+    for (size_t t = (size_t)blockIdx.x * DIAG_THREADS + threadIdx.x; t < ncell;
+         t += (size_t)gridDim.x * DIAG_THREADS) {
+        const int y = (int)(t / nx), x = (int)(t - (size_t)y * nx);
+        const size_t c = (size_t)(y + 1) * pitch + x;   // padded storage, ghost row below
+        const size_t o = t;                             // dense output index
+        if (mask[c]) {
+            if (U) U[o] = NAN;
+            if (V) V[o] = NAN;
+            if (Cp) Cp[o] = NAN;
+            continue;
+        }
+        const double u = __ddiv_rn((double)ux[c], U0), v = __ddiv_rn((double)uy[c], U0);
+        const double cp = __ddiv_rn(__dsub_rn((double)rho[c], 1.0), cden);
+        if (U) U[o] = (float)u;
+        if (V) V[o] = (float)v;
+        if (Cp) Cp[o] = (float)cp;
+        const double s = hypot(u, v);
+        if (s > mx && s < 4.0) mx = s;
+        if (cp > -4.0 && cp < 1.2) {
+            if (cp < cmin) cmin = cp;
+            if (cp > cmax) cmax = cp;
+        }
+    }
+    mx = warp_max(mx);
+    cmin = warp_min(cmin);
+    cmax = warp_max(cmax);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sm[0][w] = mx; sm[1][w] = cmin; sm[2][w] = cmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < DIAG_THREADS / 32; k++) {
+            mx = fmax(mx, sm[0][k]);
+            cmin = fmin(cmin, sm[1][k]);
+            cmax = fmax(cmax, sm[2][k]);
+        }
+        part[3 * blockIdx.x + 0] = mx;
+        part[3 * blockIdx.x + 1] = cmin;
+        part[3 * blockIdx.x + 2] = cmax;
+    }
+}
+
+// HTML:649-700, enumerated from the fluid side so that a slab only needs its
+// own rho/ux rows plus the (static) mask ghost rows: for every non-solid cell
+// and each of its four neighbours that is in the lattice and solid, the face
+// contributes p = rho/3 along (solid - fluid).  part[4*b + {0,1,2,3}] =
+// {fx, fy, surf, rev}.
+__global__ void __launch_bounds__(DIAG_THREADS)
+forces_kernel(const uint8_t *__restrict__ mask, const float *__restrict__ rho,
+              const float *__restrict__ ux, int pitch, int nx, int ny_global, int gy_first, int nyl,
+              double *part) {
+    __shared__ double sm[4][DIAG_THREADS / 32];
+    double fx = 0, fy = 0, surf = 0, rev = 0;
+    const size_t ncell = (size_t)nx * nyl;
+    for (size_t t = (size_t)blockIdx.x * DIAG_THREADS + threadIdx.x; t < ncell;
+         t += (size_t)gridDim.x * DIAG_THREADS) {
+        const int y = (int)(t / nx), x = (int)(t - (size_t)y * nx);
+        const int j = y + 1, gy = gy_first + j;
+        const size_t c = (size_t)j * pitch + x;
+        if (mask[c]) continue;
+        // neighbour offsets from the fluid cell to the candidate solid cell
+        const int dx[4] = {-1, 0, 1, 0}, dy[4] = {0, -1, 0, 1};
+        double p = 0;
+        bool have = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int xs = x + dx[k], gys = gy + dy[k];
+            if (xs < 0 || xs >= nx || gys < 0 || gys >= ny_global) continue;
+            if (!mask[(size_t)(j + dy[k]) * pitch + xs]) continue;
+            if (!have) { p = __ddiv_rn((double)rho[c], 3.0); have = true; }
+            // JS: face (FACE_DX,FACE_DY) = fluid - solid = (-dx,-dy); f += p*(-FACE)
+            fx += p * (double)dx[k];
+            fy += p * (double)dy[k];
+            surf += 1.0;
+            if (ux[c] < 0.0f) rev += 1.0;
+        }
+    }
+    fx = warp_sum(fx); fy = warp_sum(fy); surf = warp_sum(surf); rev = warp_sum(rev);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sm[0][w] = fx; sm[1][w] = fy; sm[2][w] = surf; sm[3][w] = rev; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < DIAG_THREADS / 32; k++) {
+            fx += sm[0][k]; fy += sm[1][k]; surf += sm[2][k]; rev += sm[3][k];
+        }
+        part[4 * blockIdx.x + 0] = fx;
+        part[4 * blockIdx.x + 1] = fy;
+        part[4 * blockIdx.x + 2] = surf;
+        part[4 * blockIdx.x + 3] = rev;
+    }
+}
+
+__global__ void __launch_bounds__(DIAG_THREADS)
+mass_kernel(const float *__restrict__ f, size_t plane, int pitch, int nx, int nyl, double *part) {
+    __shared__ double sm[DIAG_THREADS / 32];
+    double m = 0;
+    const size_t ncell = (size_t)nx * nyl;
+    for (size_t t = (size_t)blockIdx.x * DIAG_THREADS + threadIdx.x; t < ncell;
+         t += (size_t)gridDim.x * DIAG_THREADS) {
+        const int y = (int)(t / nx), x = (int)(t - (size_t)y * nx);
+        const size_t c = (size_t)(y + 1) * pitch + x;
+#pragma unroll
+        for (int i = 0; i < 9; i++) m += (double)f[i * plane + c];
+    }
+    m = warp_sum(m);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sm[w] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < DIAG_THREADS / 32; k++) m += sm[k];
+        part[blockIdx.x] = m;
+    }
+}
+
+__device__ __forceinline__ float mixf(float a, float b, float u) { return a * (1.0f - u) + b * u; }
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ uint8_t unorm8(float v) {
+    return (uint8_t)(int)floorf(clampf(v, 0.0f, 1.0f) * 255.0f + 0.5f);
+}
+
+__constant__ float SPEED_PAL[10][3] = {{5, 5, 20}, {0, 20, 120}, {0, 60, 200}, {0, 140, 220}, {0, 220, 220},
+                                       {0, 210, 140}, {80, 200, 0}, {220, 210, 0}, {255, 120, 0}, {220, 20, 0}};
+__constant__ float CP_PAL[8][3] = {{20, 50, 160}, {40, 110, 210}, {100, 175, 235}, {190, 220, 245},
+                                   {248, 248, 248}, {248, 214, 140}, {240, 150, 60}, {205, 50, 25}};
+
+__device__ __forceinline__ void palette(const float (*C)[3], int nseg, float t, float *rgb) {
+    t = clampf(t, 0.0f, 1.0f);
+    const float f = t * (float)nseg;
+    int i = (int)floorf(f);
+    if (i > nseg - 1) i = nseg - 1;
+    if (i < 0) i = 0;
+    const float u = f - (float)i;
+#pragma unroll
+    for (int k = 0; k < 3; k++) rgb[k] = mixf(C[i][k] / 255.0f, C[i + 1][k] / 255.0f, u);
+}
+
+// HTML:395-422.  Whole lattice only (ghost rows are not valid macro data).
+__global__ void render_kernel(const uint8_t *__restrict__ mask, const float *__restrict__ rho,
+                              const float *__restrict__ ux, const float *__restrict__ uy, int pitch,
+                              int nx, int ny, int mode, float U0, float maxS, float cpMin, float cpMax,
+                              float vortScale, float *t_out, uint8_t *rgba) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const size_t c = (size_t)(y + 1) * pitch + x;
+    const size_t o = (size_t)y * nx + x;
+    float t = NAN;
+    const bool solid = mask[c] != 0;
+    if (!solid) {
+        if (mode == ALB_FIELD_SPEED) {
+            const float s = sqrtf(ux[c] * ux[c] + uy[c] * uy[c]) / U0;
+            t = s / fmaxf(maxS * 0.92f, 1e-6f);
+        } else if (mode == ALB_FIELD_CP) {
+            const float cp = (rho[c] - 1.0f) / (1.5f * U0 * U0);
+            const float range = fmaxf(cpMax - cpMin, 1e-6f);
+            t = (cp - cpMin) / range;
+        } else {
+            // CLAMP_TO_EDGE neighbour taps (HTML:443-444, 411-414)
+            const int xr = min(x + 1, nx - 1), xl = max(x - 1, 0);
+            const int yu = min(y + 1, ny - 1), yd = max(y - 1, 0);
+            const float dvydx = (uy[(size_t)(y + 1) * pitch + xr] - uy[(size_t)(y + 1) * pitch + xl]) * 0.5f;
+            const float duxdy = (ux[(size_t)(yu + 1) * pitch + x] - ux[(size_t)(yd + 1) * pitch + x]) * 0.5f;
+            const float vort = dvydx - duxdy;
+            t = vort / fmaxf(U0 * vortScale, 1e-6f);
+        }
+    }
+    if (t_out) t_out[o] = t;
+    if (rgba) {
+        float col[3];
+        if (solid) {
+            col[0] = 0.039f; col[1] = 0.043f; col[2] = 0.078f;
+        } else if (mode == ALB_FIELD_SPEED) {
+            palette(SPEED_PAL, 9, t, col);
+        } else if (mode == ALB_FIELD_CP) {
+            palette(CP_PAL, 7, t, col);
+        } else {
+            const float tc = clampf(t, -1.0f, 1.0f);
+            const float base[3] = {0.06f, 0.07f, 0.11f};
+            const float neg[3] = {0.15f, 0.5f, 0.98f}, pos[3] = {0.98f, 0.28f, 0.18f};
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                col[k] = tc < 0.0f ? mixf(base[k], neg[k], -tc) : mixf(base[k], pos[k], tc);
+        }
+        rgba[4 * o + 0] = unorm8(col[0]);
+        rgba[4 * o + 1] = unorm8(col[1]);
+        rgba[4 * o + 2] = unorm8(col[2]);
+        rgba[4 * o + 3] = 255;
+    }
+}
+
+// HTML:474-500: every cell of both ping-pong sets := the same nine fp32 values.
+__global__ void fill_kernel(float *f0, float *f1, size_t plane, float e0, float e1, float e2, float e3,
+                            float e4, float e5, float e6, float e7, float e8, float *rho, float *ux,
+                            float *uy, float u0) {
+    const float e[9] = {e0, e1, e2, e3, e4, e5, e6, e7, e8};
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < plane;
+         t += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            f0[i * plane + t] = e[i];
+            f1[i * plane + t] = e[i];
+        }
+        rho[t] = 1.0f;
+        ux[t] = u0;
+        uy[t] = 0.0f;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_stats(const uint8_t *mask, const float *rho, const float *ux, const float *uy,
+                         int pitch, int nx, int nyl, double u0, float *U, float *V, float *Cp,
+                         double *d_part, int nblocks, cudaStream_t s) {
+    stats_kernel<<<nblocks, DIAG_THREADS, 0, s>>>(mask, rho, ux, uy, pitch, nx, nyl, u0, U, V, Cp, d_part);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_forces(const uint8_t *mask, const float *rho, const float *ux, int pitch, int nx,
+                          int ny_global, int gy_first, int nyl, double *d_part, int nblocks,
+                          cudaStream_t s) {
+    forces_kernel<<<nblocks, DIAG_THREADS, 0, s>>>(mask, rho, ux, pitch, nx, ny_global, gy_first, nyl, d_part);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render(const uint8_t *mask, const float *rho, const float *ux, const float *uy,
+                          int pitch, int nx, int ny, int mode, float u0, float maxS, float cpMin,
+                          float cpMax, float vortScale, float *t_out, uint8_t *rgba, cudaStream_t s) {
+    dim3 grid((nx + 255) / 256, ny);
+    render_kernel<<<grid, 256, 0, s>>>(mask, rho, ux, uy, pitch, nx, ny, mode, u0, maxS, cpMin, cpMax,
+                                       vortScale, t_out, rgba);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mass(const float *f, size_t plane, int pitch, int nx, int nyl, double *d_part,
+                        int nblocks, cudaStream_t s) {
+    mass_kernel<<<nblocks, DIAG_THREADS, 0, s>>>(f, plane, pitch, nx, nyl, d_part);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_init(float *f0, float *f1, size_t plane, const float *e, float *rho, float *ux,
+                             float *uy, float u0, cudaStream_t s) {
+    fill_kernel<<<148 * 8, 256, 0, s>>>(f0, f1, plane, e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], e[8],
+                                        rho, ux, uy, u0);
+    return cudaGetLastError();
+}
+
+}  // namespace alb

@@ -1,0 +1,204 @@
+// Subsystem (a): airfoil coordinates -> solid mask on the lattice.
+//
+//   host_rotate_panelise : rotate() + panelise()       HTML:133-157 (float64, libm)
+//   raster_kernel        : rasterMask()                HTML:160-182 (float64 on the GPU)
+//   build_info_kernel    : per-cell type + link bits   (derived; HTML:287-334 branch tests)
+//   build_tclass_kernel  : per-warp-task class
+//
+// "HTML:n" = pages/airfoil_flow_lbm_aerolab.html of the reference.  The mask
+// must be bit-exact: the scan conversion reproduces the reference's quirks --
+// y sampled at cell centres but x at integer node positions, the polygon is
+// not closed, crossings are sorted numerically and an unpaired last crossing
+// is dropped.  All float64 operations are individually rounded (-fmad=false
+// plus explicit _rn intrinsics), in the reference's operand order.
+#include <math.h>
+
+#include "alb_common.cuh"
+
+namespace alb {
+
+// HTML:133-157.  xy: npts (x, y) pairs.  xp/yp: ALB_NPANEL + 1 nodes.
+void host_rotate_panelise(const double *xy, int npts, double alpha_deg, double *xp, double *yp) {
+    const int NP = ALB_NPANEL;
+    // rotate(): a = -aDeg*PI/180 about (0.25, 0)
+    volatile double a = -alpha_deg * M_PI / 180;
+    const double ca = cos(a), sa = sin(a);
+    const double px = 0.25, py = 0;
+    std::vector<double> xs(npts), ys(npts), arc(npts);
+    for (int i = 0; i < npts; i++) {
+        const double dx = xy[2 * i] - px, dy = xy[2 * i + 1] - py;
+        volatile double t1 = dx * ca, t2 = dy * sa, t3 = dx * sa, t4 = dy * ca;
+        volatile double rx = px + t1;
+        volatile double ry = py + t3;
+        xs[i] = rx - t2;
+        ys[i] = ry + t4;
+    }
+    // panelise(): cumulative arc length, cosine spacing, linear search
+    arc[0] = 0;
+    for (int i = 1; i < npts; i++) arc[i] = arc[i - 1] + hypot(xs[i] - xs[i - 1], ys[i] - ys[i - 1]);
+    const double L = arc[npts - 1];
+    for (int i = 0; i <= NP; i++) {
+        volatile double ang = M_PI * i / NP;
+        volatile double half = L * 0.5;
+        volatile double om = 1 - cos(ang);
+        const double s = half * om;
+        int j = 0;
+        while (j < npts - 2 && arc[j + 1] < s) j++;
+        volatile double den = arc[j + 1] - arc[j];
+        den = den + 1e-12;
+        const double t = (s - arc[j]) / den;
+        volatile double mx = (xs[j + 1] - xs[j]) * t;
+        volatile double my = (ys[j + 1] - ys[j]) * t;
+        xp[i] = xs[j] + mx;
+        yp[i] = ys[j] + my;
+    }
+}
+
+namespace {
+
+constexpr int RASTER_THREADS = 128;
+constexpr int MAX_CROSS = 1024;   // crossings kept per row (a 161-node outline has <= 160)
+
+// One CTA per lattice row.  HTML:163-179.
+__global__ void __launch_bounds__(RASTER_THREADS)
+raster_kernel(const double *__restrict__ xp, const double *__restrict__ yp, int n, uint8_t *mask,
+              int pitch, int nx, int ny_global, int gy_first, int nrows) {
+    __shared__ double xs_raw[MAX_CROSS];
+    __shared__ double xs[MAX_CROSS];
+    __shared__ int span0[MAX_CROSS / 2], span1[MAX_CROSS / 2];
+    __shared__ int count;
+    const int j = blockIdx.x;
+    if (j >= nrows) return;
+    const int iy = gy_first + j;
+    uint8_t *row = mask + (size_t)j * pitch;
+    if (iy < 0 || iy >= ny_global) {   // ghost row outside the lattice: fluid, never read
+        for (int x = threadIdx.x; x < pitch; x += RASTER_THREADS) row[x] = 0;
+        return;
+    }
+    if (threadIdx.x == 0) count = 0;
+    __syncthreads();
+    // wy = DY0 + (iy+0.5)/NY*(DY1-DY0)
+    const double wy = __dadd_rn(DY0, __dmul_rn(__ddiv_rn((double)iy + 0.5, (double)ny_global), DY1 - DY0));
+    for (int i = threadIdx.x; i < n - 1; i += RASTER_THREADS) {
+        const double y1 = yp[i], y2 = yp[i + 1];
+        if ((y1 > wy) != (y2 > wy)) {
+            const double x1 = xp[i], x2 = xp[i + 1];
+            // x1 + (x2-x1)*(wy-y1)/(y2-y1)
+            const double num = __dmul_rn(__dsub_rn(x2, x1), __dsub_rn(wy, y1));
+            const double xc = __dadd_rn(x1, __ddiv_rn(num, __dsub_rn(y2, y1)));
+            const int k = atomicAdd(&count, 1);
+            if (k < MAX_CROSS) xs_raw[k] = xc;
+        }
+    }
+    __syncthreads();
+    const int m = min(count, MAX_CROSS);
+    // numeric ascending sort by ranking (equal values are interchangeable)
+    for (int k = threadIdx.x; k < m; k += RASTER_THREADS) {
+        const double v = xs_raw[k];
+        int rank = 0;
+        for (int q = 0; q < m; q++) {
+            const double w = xs_raw[q];
+            rank += (w < v) || (w == v && q < k);
+        }
+        xs[rank] = v;
+    }
+    __syncthreads();
+    const int npairs = m / 2;   // unpaired last crossing dropped (HTML:174)
+    for (int k = threadIdx.x; k < npairs; k += RASTER_THREADS) {
+        // ix0 = ceil((xs[k]-DX0)/(DX1-DX0)*NX), ix1 = floor(...), clamped
+        const double a = ceil(__dmul_rn(__ddiv_rn(__dsub_rn(xs[2 * k], DX0), DX1 - DX0), (double)nx));
+        const double b = floor(__dmul_rn(__ddiv_rn(__dsub_rn(xs[2 * k + 1], DX0), DX1 - DX0), (double)nx));
+        const double a2 = fmax(0.0, a);
+        const double b2 = fmin((double)(nx - 1), b);
+        // empty span when b2 < a2; values are within [0, nx-1] or the span is empty
+        span0[k] = (a2 <= (double)(nx - 1)) ? (int)a2 : nx;
+        span1[k] = (b2 >= 0.0) ? (int)b2 : -1;
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < pitch; x += RASTER_THREADS) {
+        uint8_t v = 0;
+        if (x < nx)
+            for (int k = 0; k < npairs; k++)
+                if (x >= span0[k] && x <= span1[k]) { v = 255; break; }
+        row[x] = v;
+    }
+}
+
+// Per-cell info word: bits 0..7 = "pull source x - e_i is solid" for i = 1..8
+// (interior fluid cells only), bits 8..9 = cell type.  Padding cells (x >= nx)
+// are typed equilibrium so that they only ever receive constants.
+__global__ void build_info_kernel(const uint8_t *__restrict__ mask, uint16_t *__restrict__ info,
+                                  int pitch, int nx, int ny_global, int gy_first, int nrows) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (x >= pitch || j >= nrows) return;
+    const int gy = gy_first + j;
+    const size_t c = (size_t)j * pitch + x;
+    unsigned type, links = 0;
+    if (x >= nx || gy < 0 || gy >= ny_global) {
+        type = CT_EQUIL;
+    } else if (mask[c]) {
+        type = CT_SOLID;
+    } else if (x == nx - 1) {
+        type = CT_OUTLET;
+    } else if (x == 0 || gy == ny_global - 1 || gy == 0) {
+        type = CT_EQUIL;
+    } else {
+        type = CT_FLUID;
+        const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+        const int ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+        // interior: 1 <= x <= nx-2 and 1 <= gy <= ny-2, so j-ey is a stored row
+        if (j >= 1 && j <= nrows - 2) {
+#pragma unroll
+            for (int i = 1; i < 9; i++) {
+                const size_t sidx = (size_t)(j - ey[i]) * pitch + (x - ex[i]);
+                if (mask[sidx]) links |= 1u << (i - 1);
+            }
+        }
+    }
+    info[c] = (uint16_t)((type << 8) | links);
+}
+
+__global__ void build_tclass_kernel(const uint16_t *__restrict__ info, uint8_t *__restrict__ tclass,
+                                    int pitch, int nrows) {
+    const int lane = threadIdx.x & 31;
+    const int tpr = pitch / TASK_CELLS;
+    const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (task >= tpr * nrows) return;
+    const int j = task / tpr, s = task - j * tpr;
+    const uint16_t *p = info + (size_t)j * pitch + s * TASK_CELLS + lane * 4;
+    bool all_fluid = true, all_solid = true, all_equil = true;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned v = p[k];
+        all_fluid &= (v == (CT_FLUID << 8));
+        all_solid &= ((v >> 8) == CT_SOLID);
+        all_equil &= ((v >> 8) == CT_EQUIL);
+    }
+    all_fluid = __all_sync(0xffffffffu, all_fluid);
+    all_solid = __all_sync(0xffffffffu, all_solid);
+    all_equil = __all_sync(0xffffffffu, all_equil);
+    if (lane == 0)
+        tclass[task] = all_fluid ? TC_FLUID : (all_solid ? TC_SOLID : (all_equil ? TC_EQUIL : TC_GENERAL));
+}
+
+}  // namespace
+
+cudaError_t launch_raster(const double *d_xp, const double *d_yp, int n, uint8_t *mask, int pitch,
+                          int nx, int ny_global, int gy_first, int nrows, cudaStream_t s) {
+    raster_kernel<<<nrows, RASTER_THREADS, 0, s>>>(d_xp, d_yp, n, mask, pitch, nx, ny_global, gy_first, nrows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tclass, int pitch,
+                              int nx, int ny_global, int gy_first, int nrows, cudaStream_t s) {
+    dim3 grid((pitch + 255) / 256, nrows);
+    build_info_kernel<<<grid, 256, 0, s>>>(mask, info, pitch, nx, ny_global, gy_first, nrows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int ntask = (pitch / TASK_CELLS) * nrows;
+    build_tclass_kernel<<<(ntask + 7) / 8, 256, 0, s>>>(info, tclass, pitch, nrows);
+    return cudaGetLastError();
+}
+
+}  // namespace alb

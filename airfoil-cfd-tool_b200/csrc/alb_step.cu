@@ -1,0 +1,400 @@
+// The hot path: one fused D2Q9 step = pull-stream + half-way bounce-back on the
+// mask + inlet/outlet/equilibrium borders + clamp + BGK collision, i.e.
+// STEP_FS_SRC.main of the reference (pages/airfoil_flow_lbm_aerolab.html:283-360,
+// "HTML:n" below), written for sm_100a.
+//
+// Arithmetic contract: every fp32 operation is a separately rounded IEEE
+// operation in the reference's source order (the file is compiled with
+// -fmad=false; divisions and the square root are the IEEE ones), so the result
+// is bit-identical to the strict-fp32 CPU oracle.  The only FMAs are inside
+// div_by_tau(), which computes the correctly rounded quotient (see there).
+//
+// Mapping: one warp = one "task" = 128 consecutive cells of one row, four cells
+// per lane, so every population is moved with one 128-bit load and one 128-bit
+// store per lane.  Populations that stream along x are loaded at the aligned
+// own position and shifted by one cell through the neighbouring lane's
+// register (shfl); only lane 0 / lane 31 issue one extra scalar load for the
+// cell beyond the task.  A per-task class byte selects a branch-free path for
+// tasks that are pure interior fluid (the vast majority), pure solid or pure
+// equilibrium border; everything else takes the general path that patches the
+// pulled populations per cell from a 16-bit info word.
+#include "alb_common.cuh"
+
+namespace alb {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float4 ld4(const float *p) {
+    return __ldg(reinterpret_cast<const float4 *>(p));
+}
+__device__ __forceinline__ void st4(float *p, const float4 &v) {
+    *reinterpret_cast<float4 *>(p) = v;
+}
+
+// x / tau, correctly rounded (== IEEE division), for the uniform divisor tau.
+// rcp = RN(1/tau) is computed once on the host.  q0 = RN(x*rcp) is within a
+// few ulp; one residual correction makes it faithful; by Markstein's theorem a
+// second correction with an exact residual (FMA) and a correctly rounded
+// reciprocal yields RN(x/tau).  5 instructions instead of the ~10 + slow path
+// of the generic division.  (Operands here are differences of populations: 0
+// or >= 2^-30 in magnitude, far from underflow.)  Checked exhaustively against
+// true division in tests/test_div_by_tau.py.
+__device__ __forceinline__ float div_by_tau(float x, float tau, float rcp) {
+    float q = __fmul_rn(x, rcp);
+    float r = __fmaf_rn(-tau, q, x);
+    q = __fmaf_rn(r, rcp, q);
+    r = __fmaf_rn(-tau, q, x);
+    q = __fmaf_rn(r, rcp, q);
+    return q;
+}
+
+struct Moments {
+    float rho, ux, uy;
+    bool hit;
+};
+
+// HTML:335-350: moments of the streamed populations, then the stability clamps.
+__device__ __forceinline__ Moments moments_clamped(const float (&f)[9]) {
+    Moments m;
+    float rho = f[0];
+    rho = rho + f[1];
+    rho = rho + f[2];
+    rho = rho + f[3];
+    rho = rho + f[4];
+    rho = rho + f[5];
+    rho = rho + f[6];
+    rho = rho + f[7];
+    rho = rho + f[8];
+    float ux = (f[1] + f[5] + f[8] - f[3] - f[6] - f[7]) / rho;
+    float uy = (f[2] + f[5] + f[6] - f[4] - f[7] - f[8]) / rho;
+    const float uMax = 0.35f, rhoMin = 0.5f, rhoMax = 2.0f;
+    float rc = fminf(fmaxf(rho, rhoMin), rhoMax);
+    m.hit = (rc != rho);
+    float spd2 = ux * ux + uy * uy;
+    if (spd2 > uMax * uMax) {
+        float k = uMax / sqrtf(spd2);
+        ux *= k;
+        uy *= k;
+        m.hit = true;
+    }
+    m.rho = rc;
+    m.ux = ux;
+    m.uy = uy;
+    return m;
+}
+
+// plain moments of the outlet rule (HTML:305-307): no clamp
+__device__ __forceinline__ void moments_plain(const float (&f)[9], float &rho, float &ux, float &uy) {
+    rho = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8];
+    ux = (f[1] + f[5] + f[8] - f[3] - f[6] - f[7]) / rho;
+    uy = (f[2] + f[5] + f[6] - f[4] - f[7] - f[8]) / rho;
+}
+
+// HTML:276-281 and 352-356.  feq_i = wt(i)*rho*(1+3eu+4.5eu*eu-1.5uu), left to
+// right; opposite directions share 3*eu and 4.5*eu*eu (negating eu negates the
+// first exactly and leaves the second unchanged, so sharing is bit-neutral).
+__device__ __forceinline__ void collide(float (&f)[9], const Moments &m, float tau, float rcp) {
+    const float w0 = 4.0f / 9.0f, ws = 1.0f / 9.0f, wd = 1.0f / 36.0f;
+    const float rho = m.rho, ux = m.ux, uy = m.uy;
+    const float uu = ux * ux + uy * uy;
+    const float c15 = 1.5f * uu;
+    const float wr0 = w0 * rho, wrs = ws * rho, wrd = wd * rho;
+    {
+        float eq = wr0 * (1.0f - c15);
+        f[0] = f[0] - div_by_tau(f[0] - eq, tau, rcp);
+    }
+#define ALB_PAIR(A, B, EU, WR)                                      \
+    {                                                               \
+        const float eu = (EU);                                      \
+        const float t1 = 3.0f * eu;                                 \
+        const float t2 = (4.5f * eu) * eu;                          \
+        const float ea = (WR) * (((1.0f + t1) + t2) - c15);         \
+        const float eb = (WR) * (((1.0f - t1) + t2) - c15);         \
+        f[A] = f[A] - div_by_tau(f[A] - ea, tau, rcp);              \
+        f[B] = f[B] - div_by_tau(f[B] - eb, tau, rcp);              \
+    }
+    ALB_PAIR(1, 3, ux, wrs)
+    ALB_PAIR(2, 4, uy, wrs)
+    ALB_PAIR(5, 7, ux + uy, wrd)
+    ALB_PAIR(6, 8, uy - ux, wrd)
+#undef ALB_PAIR
+}
+
+__device__ __forceinline__ float comp(const float4 &v, int k) {
+    return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
+}
+__device__ __forceinline__ void setc(float4 &v, int k, float a) {
+    if (k == 0) v.x = a;
+    else if (k == 1) v.y = a;
+    else if (k == 2) v.z = a;
+    else v.w = a;
+}
+
+// populations arriving from x-1: own aligned vector shifted right by one cell
+__device__ __forceinline__ float4 from_left(const float4 &v, float edge, int lane) {
+    float t = __shfl_up_sync(FULL, v.w, 1);
+    if (lane == 0) t = edge;
+    return make_float4(t, v.x, v.y, v.z);
+}
+// populations arriving from x+1
+__device__ __forceinline__ float4 from_right(const float4 &v, float edge, int lane) {
+    float t = __shfl_down_sync(FULL, v.x, 1);
+    if (lane == 31) t = edge;
+    return make_float4(v.y, v.z, v.w, t);
+}
+
+constexpr int MODE_STEP = 0, MODE_MACRO = 1;
+
+template <int MODE>
+__global__ void __launch_bounds__(BLOCK_THREADS)
+step_kernel(const __grid_constant__ StepParams p) {
+    const int lane = threadIdx.x & 31;
+    const int task = blockIdx.x * TASKS_PER_BLOCK + (threadIdx.x >> 5);
+    if (MODE == MODE_STEP && blockIdx.x == 0 && threadIdx.x == 0 && p.me_next) {
+        p.me_next[0] = 0;   // next step's accumulator; kernels of one handle run in stream order
+        p.me_next[1] = 0;
+    }
+    if (task >= p.ntasks) return;
+    const int j = task / p.tpr + 1;          // local row (0 is the lower ghost row)
+    const int s = task - (j - 1) * p.tpr;
+    const int x0 = s * TASK_CELLS + lane * 4;
+    const size_t c = (size_t)j * p.pitch + x0;
+    const size_t plane = p.plane;
+    const int cls = p.tclass[(size_t)j * p.tpr + s];   // warp-uniform
+    const float *__restrict__ src = p.src;
+
+    float4 o[9];
+
+    if (cls == TC_EQUIL) {
+        // HTML:314-322: whole task is inlet/top/bottom equilibrium at (1, U0, 0)
+        if (MODE == MODE_STEP) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                const float v = p.feq0[i];
+                st4(p.dst + i * plane + c, make_float4(v, v, v, v));
+            }
+        } else {
+            st4(p.rho + c, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
+            st4(p.ux + c, make_float4(p.u0, p.u0, p.u0, p.u0));
+            st4(p.uy + c, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        }
+        return;
+    }
+    if (cls == TC_SOLID) {
+        // HTML:287-294: solid cells swap every population with its opposite
+        if (MODE == MODE_STEP) {
+            const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+#pragma unroll
+            for (int i = 0; i < 9; i++) o[i] = ld4(src + opp[i] * plane + c);
+#pragma unroll
+            for (int i = 0; i < 9; i++) st4(p.dst + i * plane + c, o[i]);
+        } else {
+            st4(p.rho + c, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
+            st4(p.ux + c, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+            st4(p.uy + c, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        }
+        return;
+    }
+
+    // ---- pull (HTML:325-334), all loads issued before first use ------------
+    const size_t cm = c - p.pitch;   // row j-1
+    const size_t cp = c + p.pitch;   // row j+1
+    const float4 v0 = ld4(src + 0 * plane + c);
+    const float4 v1 = ld4(src + 1 * plane + c);
+    const float4 v2 = ld4(src + 2 * plane + cm);
+    const float4 v3 = ld4(src + 3 * plane + c);
+    const float4 v4 = ld4(src + 4 * plane + cp);
+    const float4 v5 = ld4(src + 5 * plane + cm);
+    const float4 v6 = ld4(src + 6 * plane + cm);
+    const float4 v7 = ld4(src + 7 * plane + cp);
+    const float4 v8 = ld4(src + 8 * plane + cp);
+    float l1 = 0.f, l5 = 0.f, l8 = 0.f, r3 = 0.f, r6 = 0.f, r7 = 0.f;
+    if (lane == 0 && x0 > 0) {
+        l1 = __ldg(src + 1 * plane + c - 1);
+        l5 = __ldg(src + 5 * plane + cm - 1);
+        l8 = __ldg(src + 8 * plane + cp - 1);
+    }
+    if (lane == 31 && x0 + 4 < p.pitch) {
+        r3 = __ldg(src + 3 * plane + c + 4);
+        r6 = __ldg(src + 6 * plane + cm + 4);
+        r7 = __ldg(src + 7 * plane + cp + 4);
+    }
+
+    float4 own[9];
+    uint2 iv = make_uint2(0u, 0u);
+    if (cls == TC_GENERAL) {
+        // own-cell populations for bounce-back / solid swap (v0, v1, v3 are own already)
+        iv = __ldg(reinterpret_cast<const uint2 *>(p.info + c));
+        own[0] = v0;
+        own[1] = v1;
+        own[3] = v3;
+        own[2] = ld4(src + 2 * plane + c);
+        own[4] = ld4(src + 4 * plane + c);
+        own[5] = ld4(src + 5 * plane + c);
+        own[6] = ld4(src + 6 * plane + c);
+        own[7] = ld4(src + 7 * plane + c);
+        own[8] = ld4(src + 8 * plane + c);
+    }
+
+    o[0] = v0;
+    o[1] = from_left(v1, l1, lane);
+    o[2] = v2;
+    o[3] = from_right(v3, r3, lane);
+    o[4] = v4;
+    o[5] = from_left(v5, l5, lane);
+    o[6] = from_right(v6, r6, lane);
+    o[7] = from_right(v7, r7, lane);
+    o[8] = from_left(v8, l8, lane);
+
+    float4 mr, mx, my;   // macro outputs (macro mode)
+    long long me_fx = 0, me_fy = 0;
+    unsigned hits = 0;
+
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float f[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) f[i] = comp(o[i], k);
+
+        unsigned info = 0;
+        if (cls == TC_GENERAL) {
+            info = (k < 2 ? iv.x : iv.y) >> ((k & 1) * 16) & 0xffffu;
+            const unsigned links = info & 0xffu;
+            if (links && (info >> 8) == CT_FLUID) {
+                // HTML:329-330: source cell is solid -> take my own opposite population
+                const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+                const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+                const int ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+#pragma unroll
+                for (int i = 1; i < 9; i++) {
+                    if (links & (1u << (i - 1))) {
+                        const float b = comp(own[opp[i]], k);
+                        f[i] = b;
+                        if (MODE == MODE_STEP) {
+                            // momentum handed to the body, 2*b*e_opp(i), in 2^-40 fixed point
+                            const long long q = __double2ll_rn((double)b * 0x1p41);
+                            me_fx += -ex[i] * q;
+                            me_fy += -ey[i] * q;
+                        }
+                    }
+                }
+            }
+        }
+
+        const Moments m = moments_clamped(f);
+        float rho = m.rho, ux = m.ux, uy = m.uy;
+        if (MODE == MODE_STEP) collide(f, m, p.tau, p.inv_tau);
+        bool hit = m.hit;
+
+        if (cls == TC_GENERAL) {
+            const int type = info >> 8;
+            if (type != CT_FLUID) hit = false;
+            if (type == CT_SOLID) {
+                const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+#pragma unroll
+                for (int i = 0; i < 9; i++) f[i] = comp(own[opp[i]], k);
+                rho = 1.0f; ux = 0.0f; uy = 0.0f;
+            } else if (type == CT_EQUIL) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) f[i] = p.feq0[i];
+                rho = 1.0f; ux = p.u0; uy = 0.0f;
+            } else if (type == CT_OUTLET) {
+                // HTML:301-312: copy all nine populations of (x-1, y), previous state
+#pragma unroll
+                for (int i = 0; i < 9; i++) f[i] = __ldg(src + i * plane + c + k - 1);
+                moments_plain(f, rho, ux, uy);
+            }
+        }
+        if (hit) hits++;
+
+        if (MODE == MODE_STEP) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) setc(o[i], k, f[i]);
+        } else {
+            setc(mr, k, rho);
+            setc(mx, k, ux);
+            setc(my, k, uy);
+        }
+    }
+
+    if (MODE == MODE_STEP) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) st4(p.dst + i * plane + c, o[i]);
+
+        // halo push: my edge rows go straight into the neighbours' ghost rows
+        // (peer memory over NVLink, or the same GPU for in-process slabs)
+        if (j == p.nyl && p.peer_hi_dst) {
+            st4(p.peer_hi_dst + 2 * p.peer_hi_plane + p.peer_hi_row + x0, o[2]);
+            st4(p.peer_hi_dst + 5 * p.peer_hi_plane + p.peer_hi_row + x0, o[5]);
+            st4(p.peer_hi_dst + 6 * p.peer_hi_plane + p.peer_hi_row + x0, o[6]);
+        }
+        if (j == 1 && p.peer_lo_dst) {
+            st4(p.peer_lo_dst + 4 * p.peer_lo_plane + p.peer_lo_row + x0, o[4]);
+            st4(p.peer_lo_dst + 7 * p.peer_lo_plane + p.peer_lo_row + x0, o[7]);
+            st4(p.peer_lo_dst + 8 * p.peer_lo_plane + p.peer_lo_row + x0, o[8]);
+        }
+
+        if (cls == TC_GENERAL && p.me_slot) {
+            // integer sums are exact and order independent: shuffle tree, one atomic per warp
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                me_fx += __shfl_xor_sync(FULL, me_fx, d);
+                me_fy += __shfl_xor_sync(FULL, me_fy, d);
+            }
+            if (lane == 0) {
+                if (me_fx) atomicAdd(reinterpret_cast<unsigned long long *>(p.me_slot), (unsigned long long)me_fx);
+                if (me_fy) atomicAdd(reinterpret_cast<unsigned long long *>(p.me_slot + 1), (unsigned long long)me_fy);
+            }
+        }
+        if (hits && p.clamp_hits) atomicAdd(p.clamp_hits, (unsigned long long)hits);
+    } else {
+        st4(p.rho + c, mr);
+        st4(p.ux + c, mx);
+        st4(p.uy + c, my);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_step(const StepParams &p, cudaStream_t s) {
+    const int nblocks = (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
+    step_kernel<MODE_STEP><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_macro(const StepParams &p, cudaStream_t s) {
+    const int nblocks = (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
+    step_kernel<MODE_MACRO><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// feq_i(rho = 1, ux = U0, uy = 0) exactly as the shader evaluates it
+// (HTML:276-281, 315-317).  Host code; built with -ffp-contract=off.
+void host_feq0(float u0, float *out9) {
+    const float w0 = 4.0f / 9.0f, ws = 1.0f / 9.0f, wd = 1.0f / 36.0f;
+    const float W[9] = {w0, ws, ws, ws, ws, wd, wd, wd, wd};
+    const float EXf[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+    const float EYf[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+    volatile float rho = 1.0f, ux = u0, uy = 0.0f;   // volatile: keep the operations separate
+    for (int i = 0; i < 9; i++) {
+        volatile float a = EXf[i] * ux;
+        volatile float b = EYf[i] * uy;
+        volatile float eu = a + b;
+        volatile float uxx = ux * ux;
+        volatile float uyy = uy * uy;
+        volatile float uu = uxx + uyy;
+        volatile float wr = W[i] * rho;
+        volatile float t1 = 3.0f * eu;
+        volatile float s1 = 1.0f + t1;
+        volatile float t2 = 4.5f * eu;
+        volatile float t3 = t2 * eu;
+        volatile float s2 = s1 + t3;
+        volatile float t4 = 1.5f * uu;
+        volatile float s3 = s2 - t4;
+        out9[i] = wr * s3;
+    }
+}
+
+}  // namespace alb

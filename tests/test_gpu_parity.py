@@ -1,0 +1,381 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): mask bit-exact; populations and macroscopic
+fields bit-identical to the strict-fp32 oracle (which implies the stated
+relative L-inf <= 1e-5 after 1,000 steps); total mass equal to the oracle's to
+1e-6 relative; closed-box mass conserved to 1e-6.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_bitwise, rel_linf
+
+pytestmark = pytest.mark.gpu
+
+from oracle import geometry as ogeo  # noqa: E402
+from oracle import lbm as olbm  # noqa: E402
+
+FIELD_TOL = 1e-5      # north_star: relative L-inf after 1,000 steps
+MASS_TOL = 1e-6       # north_star: mass parity / conservation
+
+
+@pytest.fixture(scope="module")
+def al(built_lib):
+    import aerolab_lbm
+    return aerolab_lbm
+
+
+def make_pair(al, nx, ny, shape, alpha, u0=0.06, tau=0.58):
+    t = al.WindTunnel(nx, ny, 0, u0=u0, tau=tau)
+    t.load_shape(shape, alpha=alpha)
+    o = olbm.OracleTunnel(nx, ny, u0, tau)
+    o.apply_geometry(ogeo.SHAPES[shape](), alpha)
+    return t, o
+
+
+def compare_state(t, o, what):
+    assert_bitwise(t.populations(), o.F, what + " populations")
+    rho, ux, uy = t.macro()
+    assert_bitwise(rho, o.rho, what + " rho")
+    assert_bitwise(ux, o.ux, what + " ux")
+    assert_bitwise(uy, o.uy, what + " uy")
+
+
+# ---- (a) mask rasterisation: bit-exact ---------------------------------------
+
+@pytest.mark.parametrize("shape,alpha,nx,ny", [
+    ("naca0012", 5.0, 320, 160), ("naca2412", 6.0, 320, 160), ("naca4412", 10.0, 320, 160),
+    ("naca6409", -7.5, 320, 160), ("clark_y", 6.0, 320, 160), ("clark_y", 6.0, 2048, 1024),
+    ("naca0012", 0.0, 2048, 1024), ("naca0012", 20.0, 2048, 1024), ("naca4412", 10.0, 4096, 2048),
+    ("naca2412", 5.0, 333, 171), ("naca2412", 25.0, 100, 37), ("naca0012", -20.0, 640, 320),
+])
+def test_mask_bit_exact(al, shape, alpha, nx, ny):
+    with al.WindTunnel(nx, ny, 0) as t:
+        t.load_shape(shape)
+        got = t.set_alpha(alpha, want_mask=True)
+        xp, yp, want = ogeo.build_geometry(ogeo.SHAPES[shape](), alpha, nx, ny)
+        gxp, gyp = t.panels()
+        assert_bitwise(gxp, np.array(xp), "panel x")
+        assert_bitwise(gyp, np.array(yp), "panel y")
+        assert np.array_equal(got, want), f"{int((got != want).sum())} mask cells differ"
+        assert np.array_equal(t.mask(), want)
+
+
+def test_mask_open_te_user_coords(al):
+    """Injected 6-decimal coordinates with an open trailing edge (test_main.py:33-50 fixture):
+    odd crossing counts drop the last crossing, leaving slit rows."""
+    pts = [(1.0, 0.00126), (0.933013, 0.00574), (0.75, 0.01597), (0.5, 0.03023), (0.25, 0.04121),
+           (0.066987, 0.03153), (0.0, 0.0), (0.066987, -0.03153), (0.25, -0.04121), (0.5, -0.03023),
+           (0.75, -0.01597), (0.933013, -0.00574), (1.0, -0.00126)]
+    for alpha, nx, ny in ((0.0, 2048, 1024), (5.0, 2048, 1024), (6.0, 320, 160)):
+        with al.WindTunnel(nx, ny, 0) as t:
+            got = t.load_coords(al.round_coords(pts)).set_alpha(alpha, want_mask=True)
+            _, _, want = ogeo.build_geometry(ogeo.round_coords(pts), alpha, nx, ny)
+            assert np.array_equal(got, want)
+    # the documented quirk: rows 511-512 are empty at alpha = 0 on 2048x1024
+    _, _, m0 = ogeo.build_geometry(ogeo.round_coords(pts), 0.0, 2048, 1024)
+    assert m0[511].sum() == 0 and m0[512].sum() == 0 and m0[510].sum() > 0
+
+
+def test_set_mask_roundtrip(al):
+    rng = np.random.default_rng(1)
+    m = (rng.random((48, 200)) < 0.2).astype(np.uint8) * 255
+    with al.WindTunnel(200, 48, 0) as t:
+        t.set_mask(m)
+        assert np.array_equal(t.mask(), m)
+
+
+# ---- (b) the step: bitwise against the strict-fp32 oracle ---------------------
+
+def test_init_state_bitwise(al):
+    t, o = make_pair(al, 320, 160, "naca0012", 5.0)
+    compare_state(t, o, "init")
+    t.reset(0.083)
+    o.reset(0.083)
+    compare_state(t, o, "reset(0.083)")
+
+
+def test_steps_bitwise_first_10(al):
+    t, o = make_pair(al, 320, 160, "naca0012", 5.0)
+    for s in range(1, 11):
+        t.step(1)
+        o.step(1)
+        compare_state(t, o, f"step {s}")
+
+
+def test_default_case_1000_steps(al):
+    """configs[1]: NACA 0012, alpha 5, 320x160, U0 0.06, tau 0.58, 1,000 steps."""
+    t, o = make_pair(al, 320, 160, "naca0012", 5.0)
+    t.step(1000)
+    o.step(1000)
+    fluid = o.mask == 0
+    F = t.populations()
+    rho, ux, uy = t.macro()
+    for name, got, want in (("rho", rho, o.rho), ("ux", ux, o.ux), ("uy", uy, o.uy)):
+        assert rel_linf(got, want, fluid) <= FIELD_TOL, name
+    assert abs(t.total_mass() / olbm.total_mass(o.F) - 1) <= MASS_TOL
+    # and the stronger, intended property
+    assert_bitwise(F, o.F, "populations after 1000 steps")
+    assert_bitwise(rho, o.rho, "rho after 1000 steps")
+    assert_bitwise(ux, o.ux, "ux after 1000 steps")
+    assert_bitwise(uy, o.uy, "uy after 1000 steps")
+    assert t.clamp_hits() == o.clamp_hits == 0
+
+
+@pytest.mark.parametrize("nx,ny,shape,alpha,u0,tau,n", [
+    (333, 171, "naca2412", 12.0, 0.06, 0.58, 60),      # odd sizes: padded pitch, ragged tasks
+    (128, 64, "clark_y", 6.0, 0.1, 0.52, 300),         # open TE, high speed, low tau
+    (1024, 512, "naca4412", 10.0, 0.06, 0.58, 40),
+    (100, 37, "naca2412", 25.0, 0.03, 0.9, 80),
+    (640, 320, "naca6409", -10.0, 0.08, 0.6, 50),
+])
+def test_steps_bitwise_various(al, nx, ny, shape, alpha, u0, tau, n):
+    t, o = make_pair(al, nx, ny, shape, alpha, u0, tau)
+    t.step(n)
+    o.step(n)
+    compare_state(t, o, f"{nx}x{ny} {shape}")
+
+
+def test_clamps_fire_and_match(al):
+    """Broadside plate + fast inlet + low tau drives the rho/u clamps (HTML:340-350)."""
+    nx, ny = 160, 80
+    m = np.zeros((ny, nx), np.uint8)
+    m[10:70, 60:64] = 255
+    t = al.WindTunnel(nx, ny, 0, u0=0.25, tau=0.505)
+    t.set_mask(m)
+    o = olbm.OracleTunnel(nx, ny, 0.25, 0.505)
+    o.set_mask(m)
+    t.step(400)
+    o.step(400)
+    assert o.clamp_hits > 0
+    assert t.clamp_hits() == o.clamp_hits
+    compare_state(t, o, "clamped")
+
+
+def test_mask_touching_borders(al):
+    """Solid wins over outlet/inlet/top/bottom (branch priority, HTML:287-322)."""
+    nx, ny = 96, 40
+    rng = np.random.default_rng(7)
+    m = (rng.random((ny, nx)) < 0.08).astype(np.uint8) * 255
+    m[0, 5:20] = 255
+    m[ny - 1, 30:50] = 255
+    m[3:9, 0] = 255
+    m[12:30, nx - 1] = 255
+    m[20:25, nx - 2] = 255
+    t = al.WindTunnel(nx, ny, 0)
+    t.set_mask(m)
+    o = olbm.OracleTunnel(nx, ny)
+    o.set_mask(m)
+    for s in range(30):
+        t.step(1)
+        o.step(1)
+        compare_state(t, o, f"random mask step {s}")
+
+
+def test_alpha_and_u0_change_mid_run(al):
+    """applyGeometry / U0 slider do not reset the flow (HTML:579-586, 956-959)."""
+    t, o = make_pair(al, 320, 160, "naca2412", 6.0)
+    t.step(50); o.step(50)
+    t.set_alpha(14.0); o.apply_geometry(ogeo.SHAPES["naca2412"](), 14.0)
+    t.step(30); o.step(30)
+    compare_state(t, o, "after alpha change")
+    t.set_u0(0.09); o.u0 = 0.09
+    t.set_tau(0.62); o.tau = 0.62
+    t.step(30); o.step(30)
+    compare_state(t, o, "after u0/tau change")
+    # macro read just before a mask change must still be that step's macro
+    t.step(5); o.step(5)
+    t.set_alpha(-3.0)
+    rho, ux, uy = t.macro()
+    assert_bitwise(rho, o.rho, "rho kept across mask change")
+    assert_bitwise(ux, o.ux, "ux kept across mask change")
+
+
+def test_set_get_populations_roundtrip(al):
+    t, o = make_pair(al, 200, 90, "naca0012", 3.0)
+    t.step(20); o.step(20)
+    F = t.populations()
+    t2 = al.WindTunnel(200, 90, 0)
+    t2.load_shape("naca0012", alpha=3.0)
+    t2.set_populations(F)
+    t2.step(10); o.step(10)
+    assert_bitwise(t2.populations(), o.F, "restart from dumped populations")
+
+
+def test_closed_box_mass_conservation(al):
+    """No inlet/outlet influence: a sealed solid box around quiescent-but-perturbed fluid.
+    Stream + collide + half-way bounce-back must conserve mass to 1e-6 relative."""
+    nx, ny = 128, 96
+    m = np.zeros((ny, nx), np.uint8)
+    m[:3, :] = 255; m[-3:, :] = 255; m[:, :3] = 255; m[:, -3:] = 255
+    m[40:50, 50:70] = 255
+    inside = np.zeros_like(m, bool)
+    inside[3:-3, 3:-3] = True
+    inside &= m == 0
+    t = al.WindTunnel(nx, ny, 0, u0=0.0)
+    t.set_mask(m)
+    F = t.populations()
+    rng = np.random.default_rng(3)
+    F *= (1 + 0.05 * rng.standard_normal(F.shape)).astype(np.float32)
+    t.set_populations(F)
+    m0 = float(F[:, inside].astype(np.float64).sum())
+    t.step(500)
+    m1 = float(t.populations()[:, inside].astype(np.float64).sum())
+    assert abs(m1 / m0 - 1) <= MASS_TOL
+    assert t.clamp_hits() == 0
+
+
+# ---- (c) diagnostics ----------------------------------------------------------
+
+def test_forces_stats_render_match_oracle(al):
+    t, o = make_pair(al, 320, 160, "naca4412", 10.0)
+    for frame in range(1, 31):
+        t.step(4); o.step(4)
+        # render uses the PREVIOUS frame's autoscale (HTML:909-911)
+        if frame in (10, 20, 30):
+            for mode in (0, 1, 2):
+                got = t.field(mode)
+                want = o.render(mode)
+                assert np.array_equal(np.isnan(got), np.isnan(want))
+                ok = ~np.isnan(want)
+                assert_bitwise(got[ok], want[ok], f"render mode {mode} frame {frame}")
+                assert np.array_equal(t.rgba(mode), olbm.rgba(o.mask, want, mode))
+        st = t.update_stats(want_fields=(frame == 30))
+        U, V, Cp = o.update_fields(want_fields=(frame == 30))
+        assert st["maxS"] == pytest.approx(o.max_s, rel=1e-14)   # hypot may differ in the last ulp
+        assert st["cpMin"] == o.cp_min and st["cpMax"] == o.cp_max
+        if frame == 30:
+            for got, want, name in ((st["U"], U, "U"), (st["V"], V, "V"), (st["Cp"], Cp, "Cp")):
+                assert np.array_equal(np.isnan(got), np.isnan(want)), name
+                ok = ~np.isnan(want)
+                assert_bitwise(got[ok], want[ok], name)
+        if frame % 3 == 0:
+            f = t.forces()
+            w = o.compute_forces()
+            assert f["surf"] == w["surf"] and f["rev"] == w["rev"]
+            assert f["CL_raw"] == pytest.approx(w["CL_raw"], rel=1e-12)
+            assert f["CD_raw"] == pytest.approx(w["CD_raw"], rel=1e-12)
+            assert f["CL"] == pytest.approx(o.cl_smooth, rel=1e-12)
+            assert f["CD"] == pytest.approx(o.cd_smooth, rel=1e-12)
+            assert f["sep_frac"] == pytest.approx(o.sep_frac, rel=1e-12, abs=1e-300)
+            cl_me, cd_me = o.me_coeffs()
+            assert f["CL_me"] == pytest.approx(cl_me, rel=1e-13)
+            assert f["CD_me"] == pytest.approx(cd_me, rel=1e-13)
+    assert t.stall_state() == o.stall_state()[0]
+    assert t.reynolds() == pytest.approx(o.reynolds(), rel=1e-15)
+    # momentum-exchange history: exact integers
+    hist = t.me_history(40)
+    assert np.array_equal(hist, np.array(o.me_hist[-40:], dtype=np.int64))
+
+
+def test_forces_none_without_body(al):
+    with al.WindTunnel(64, 32, 0) as t:
+        t.step(3)
+        f = t.forces()
+        assert not f["any"] and f["surf"] == 0 and np.isnan(f["CL"])
+
+
+def test_stall_indicator_large_alpha(al):
+    """At alpha = 25 deg the separation fraction grows and the card leaves 'Attached'."""
+    t, o = make_pair(al, 320, 160, "naca0012", 25.0)
+    for frame in range(1, 301):
+        t.step(4); o.step(4)
+        if frame % 3 == 0:
+            t.forces(); o.compute_forces()
+    assert t.stall_state() == o.stall_state()[0]
+    assert t.stall_state() != "Attached"
+
+
+def test_frame_loop_and_component(al):
+    pts = al.SHAPES["naca2412"]()
+    t = al.build_lbm_component(pts, "My Foil")
+    assert (t.nx, t.ny, t.alpha) == (320, 160, 6.0)
+    assert t.png_name() == "My_Foil_alpha6.0deg_lbm.png"
+    o = olbm.OracleTunnel(320, 160)
+    o.apply_geometry(ogeo.round_coords(ogeo.SHAPES["naca2412"]()), 6.0)
+    out = None
+    for k in range(1, 7):
+        out = t.frame()
+        o.step(4); o.update_fields()
+        if k % 3 == 0:
+            o.compute_forces()
+    assert "forces" in out
+    assert out["forces"]["CL"] == pytest.approx(o.cl_smooth, rel=1e-12)
+    assert out["stats"]["cpMin"] == o.cp_min
+
+
+# ---- error behaviour ------------------------------------------------------------
+
+def test_errors(al):
+    with pytest.raises(al.AerolabLbmError):
+        al.WindTunnel(2, 2, 0)
+    with pytest.raises(al.AerolabLbmError):
+        al.WindTunnel(64, 32, 99)
+    t = al.WindTunnel(64, 32, 0)
+    with pytest.raises(al.AerolabLbmError):
+        t.set_alpha(3.0)            # no geometry yet
+    with pytest.raises(al.AerolabLbmError):
+        t.load_coords([[0.0, float("nan")], [1.0, 0.0], [0.5, 0.1]])
+    with pytest.raises(al.AerolabLbmError):
+        t.set_mask(np.zeros((3, 3), np.uint8))
+    with pytest.raises(al.AerolabLbmError):
+        t.me_history(5)             # no steps yet
+    t.close()
+
+
+# ---- (e) y-slabs: in-process slabs on one GPU must equal the whole lattice bitwise --------------
+
+@pytest.mark.parametrize("splits", [[(0, 80), (80, 80)], [(0, 50), (50, 70), (120, 40)], [(0, 1), (1, 158), (159, 1)]])
+def test_local_slabs_bitwise(al, splits):
+    nx, ny = 320, 160
+    whole = al.WindTunnel(nx, ny, 0)
+    whole.load_shape("naca4412", alpha=10.0)
+    slabs = [al.WindTunnel(nx, ny, 0, y0=y0, ny_local=n) for y0, n in splits]
+    for s in slabs:
+        s.load_shape("naca4412", alpha=10.0)
+    for k, s in enumerate(slabs):
+        s.connect_local(slabs[k - 1] if k > 0 else None, slabs[k + 1] if k + 1 < len(slabs) else None)
+    assert np.array_equal(np.concatenate([s.mask() for s in slabs], 0), whole.mask())
+    nsteps = 60
+    whole.step(nsteps)
+    for _ in range(nsteps):
+        for s in slabs:
+            s.step(1)
+    for s in slabs:
+        s.sync()
+    assert_bitwise(np.concatenate([s.populations() for s in slabs], 1), whole.populations(), "slab populations")
+    wm = whole.macro()
+    for k in range(3):
+        assert_bitwise(np.concatenate([s.macro()[k] for s in slabs], 0), wm[k], f"slab macro {k}")
+    # forces: partial sums add up; momentum exchange adds up exactly
+    part = sum(s.forces_partial() for s in slabs)
+    wf = whole.forces()
+    assert part[2] == wf["surf"] and part[3] == wf["rev"]
+    assert part[0] == pytest.approx(wf["fx"], rel=1e-12)
+    assert part[1] == pytest.approx(wf["fy"], rel=1e-12)
+    me = sum(s.me_history(1)[0] for s in slabs)
+    assert np.array_equal(me, whole.me_history(1)[0])
+    assert sum(s.total_mass() for s in slabs) == pytest.approx(whole.total_mass(), rel=1e-13)
+
+
+def test_slab_restart_needs_prime(al):
+    """set_populations on slabs + alb_halo_prime reproduces the whole-lattice run."""
+    nx, ny = 256, 96
+    whole = al.WindTunnel(nx, ny, 0)
+    whole.load_shape("naca0012", alpha=8.0)
+    whole.step(25)
+    F = whole.populations()
+    slabs = [al.WindTunnel(nx, ny, 0, y0=0, ny_local=40), al.WindTunnel(nx, ny, 0, y0=40, ny_local=56)]
+    for s in slabs:
+        s.load_shape("naca0012", alpha=8.0)
+    slabs[0].connect_local(None, slabs[1])
+    slabs[1].connect_local(slabs[0], None)
+    slabs[0].set_populations(F[:, :40])
+    slabs[1].set_populations(F[:, 40:])
+    for s in slabs:
+        s.halo_prime()
+    whole.step(20)
+    for _ in range(20):
+        for s in slabs:
+            s.step(1)
+    assert_bitwise(np.concatenate([s.populations() for s in slabs], 1), whole.populations(), "restarted slabs")
