@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libaerolab_lbm.so")
+# AEROLAB_LBM_LIB: use another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("AEROLAB_LBM_LIB") or os.path.join(_HERE, "_lib", "libaerolab_lbm.so")
 
 ALB_OK = 0
 ALB_ERR_INVALID = -1

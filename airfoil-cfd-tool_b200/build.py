@@ -45,17 +45,21 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(p) <= t for p in paths)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    """`defines`/`out` build a tuning variant (e.g. defines=["ALB_ST_HINT=1"]) next to the default."""
+    if not force and out == OUT and up_to_date():
         return OUT
-    os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [nvcc_path(), *NVCC_FLAGS] + [f"-D{d}" for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.run(cmd, check=True)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv or bool(defs), verbose="--verbose" in sys.argv, defines=defs,
+                out=os.path.abspath(outs[0]) if outs else OUT))

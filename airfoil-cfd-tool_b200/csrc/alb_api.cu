@@ -54,11 +54,15 @@ struct alb_handle {
     uint8_t *mask = nullptr;
     uint16_t *info = nullptr;
     uint8_t *tclass = nullptr;
+    int *gen_list = nullptr;      // TC_GENERAL tasks of this slab, [0] of gen_count = how many
+    int *gen_count = nullptr;
+    int ngen = 0;
     double u0 = 0.06, tau = 0.58;
     float u0f = 0, tauf = 0, inv_tau = 0;
     float feq0[9];
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t aux = nullptr;   // runs the general-task kernel concurrently with the fast kernel
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     bool timed = false;
     long long steps = 0;          // user-visible step count
     long long sync_steps = 0;     // monotonic, drives the halo flags and the ME ring
@@ -142,6 +146,8 @@ StepParams make_params(alb_handle *h, int src_idx) {
     p.dst = h->f[1 - src_idx];
     p.info = h->info;
     p.tclass = h->tclass;
+    p.gen_list = h->gen_list;
+    p.ngen = h->ngen;
     p.plane = h->plane;
     p.pitch = h->pitch;
     p.tpr = h->tpr;
@@ -172,8 +178,11 @@ int ensure_macro(alb_handle *h) {
 }
 
 int rebuild_info(alb_handle *h) {
-    CK(launch_build_info(h->mask, h->info, h->tclass, h->pitch, h->nx, h->ny_global, h->y0 - 1, h->nrows,
-                         h->stream));
+    CK(launch_build_info(h->mask, h->info, h->tclass, h->gen_list, h->gen_count, h->pitch, h->nx,
+                         h->ny_global, h->y0 - 1, h->nrows, h->stream));
+    // the host needs the number of general tasks to size that kernel's grid (mask changes are rare)
+    CK(cudaMemcpyAsync(&h->ngen, h->gen_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return ALB_OK;
 }
 
@@ -228,6 +237,8 @@ void free_handle(alb_handle *h) {
     cudaFree(h->mask);
     cudaFree(h->info);
     cudaFree(h->tclass);
+    cudaFree(h->gen_list);
+    cudaFree(h->gen_count);
     cudaFree(h->me_ring);
     cudaFree(h->clamp_hits);
     cudaFree(h->d_xp);
@@ -238,6 +249,9 @@ void free_handle(alb_handle *h) {
     if (h->h_err) cudaFreeHost(h->h_err);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->aux) cudaStreamDestroy(h->aux);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -312,8 +326,13 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
     auto body = [&]() -> int {
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, prio_hi));
         CK(cudaEventCreate(&h->ev0));
         CK(cudaEventCreate(&h->ev1));
+        CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
         const size_t pop_bytes = sizeof(float) * 18 * h->plane;
         CK(cudaMalloc(&h->block, pop_bytes + 256));
         h->f[0] = reinterpret_cast<float *>(h->block);
@@ -326,6 +345,8 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaMalloc(&h->mask, h->plane));
         CK(cudaMalloc(&h->info, sizeof(uint16_t) * h->plane));
         CK(cudaMalloc(&h->tclass, (size_t)h->nrows * h->tpr));
+        CK(cudaMalloc(&h->gen_list, sizeof(int) * (size_t)h->nrows * h->tpr));
+        CK(cudaMalloc(&h->gen_count, sizeof(int)));
         CK(cudaMalloc(&h->me_ring, sizeof(long long) * 2 * ME_RING));
         CK(cudaMalloc(&h->clamp_hits, sizeof(unsigned long long)));
         CK(cudaMalloc(&h->d_xp, sizeof(double) * 1024));
@@ -491,7 +512,15 @@ int alb_step(alb_handle *h, int nsteps) {
                 p.peer_hi_row = 0;
             }
         }
-        CK(launch_step(p, h->stream));
+        if (p.ngen > 0) {
+            // fork: the general-task kernel runs on the aux stream beside the fast kernel
+            CK(cudaEventRecord(h->ev_fork, h->stream));
+            CK(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+            CK(launch_step_general(p, h->aux));
+            CK(cudaEventRecord(h->ev_join, h->aux));
+        }
+        CK(launch_step_fast(p, h->stream));
+        if (p.ngen > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         h->cur = 1 - h->cur;
         h->steps++;
         h->sync_steps++;

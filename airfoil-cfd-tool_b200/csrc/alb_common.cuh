@@ -39,6 +39,8 @@ struct StepParams {
     float *__restrict__ dst;
     const uint16_t *__restrict__ info;
     const uint8_t *__restrict__ tclass;
+    const int *__restrict__ gen_list;   // compacted indices of TC_GENERAL tasks (row-major task ids)
+    int ngen;
     size_t plane;            // floats per population plane = nrows * pitch
     int pitch;               // cells per row (multiple of 128)
     int tpr;                 // warp tasks per row = pitch / 128
@@ -66,7 +68,8 @@ struct StepParams {
 struct Handle;
 
 // alb_step.cu
-cudaError_t launch_step(const StepParams &p, cudaStream_t s);
+cudaError_t launch_step_fast(const StepParams &p, cudaStream_t s);
+cudaError_t launch_step_general(const StepParams &p, cudaStream_t s);
 cudaError_t launch_macro(const StepParams &p, cudaStream_t s);
 void host_feq0(float u0, float *out9);
 
@@ -74,8 +77,9 @@ void host_feq0(float u0, float *out9);
 void host_rotate_panelise(const double *xy, int npts, double alpha_deg, double *xp, double *yp);
 cudaError_t launch_raster(const double *d_xp, const double *d_yp, int n, uint8_t *mask, int pitch,
                           int nx, int ny_global, int gy_first, int nrows, cudaStream_t s);
-cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tclass, int pitch,
-                              int nx, int ny_global, int gy_first, int nrows, cudaStream_t s);
+cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tclass, int *gen_list,
+                              int *gen_count, int pitch, int nx, int ny_global, int gy_first, int nrows,
+                              cudaStream_t s);
 
 // alb_diag.cu
 struct DiagScratch {

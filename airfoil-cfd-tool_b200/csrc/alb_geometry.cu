@@ -159,8 +159,10 @@ __global__ void build_info_kernel(const uint8_t *__restrict__ mask, uint16_t *__
     info[c] = (uint16_t)((type << 8) | links);
 }
 
+// Also appends the TC_GENERAL tasks of the owned rows (1 .. nrows-2) to gen_list as
+// (row - 1) * tpr + segment, the task numbering of the step kernel.
 __global__ void build_tclass_kernel(const uint16_t *__restrict__ info, uint8_t *__restrict__ tclass,
-                                    int pitch, int nrows) {
+                                    int *gen_list, int *gen_count, int pitch, int nrows) {
     const int lane = threadIdx.x & 31;
     const int tpr = pitch / TASK_CELLS;
     const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -178,8 +180,11 @@ __global__ void build_tclass_kernel(const uint16_t *__restrict__ info, uint8_t *
     all_fluid = __all_sync(0xffffffffu, all_fluid);
     all_solid = __all_sync(0xffffffffu, all_solid);
     all_equil = __all_sync(0xffffffffu, all_equil);
-    if (lane == 0)
-        tclass[task] = all_fluid ? TC_FLUID : (all_solid ? TC_SOLID : (all_equil ? TC_EQUIL : TC_GENERAL));
+    if (lane == 0) {
+        const int cls = all_fluid ? TC_FLUID : (all_solid ? TC_SOLID : (all_equil ? TC_EQUIL : TC_GENERAL));
+        tclass[task] = (uint8_t)cls;
+        if (cls == TC_GENERAL && j >= 1 && j <= nrows - 2) gen_list[atomicAdd(gen_count, 1)] = (j - 1) * tpr + s;
+    }
 }
 
 }  // namespace
@@ -190,14 +195,17 @@ cudaError_t launch_raster(const double *d_xp, const double *d_yp, int n, uint8_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tclass, int pitch,
-                              int nx, int ny_global, int gy_first, int nrows, cudaStream_t s) {
+cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tclass, int *gen_list,
+                              int *gen_count, int pitch, int nx, int ny_global, int gy_first, int nrows,
+                              cudaStream_t s) {
     dim3 grid((pitch + 255) / 256, nrows);
     build_info_kernel<<<grid, 256, 0, s>>>(mask, info, pitch, nx, ny_global, gy_first, nrows);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(gen_count, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
     const int ntask = (pitch / TASK_CELLS) * nrows;
-    build_tclass_kernel<<<(ntask + 7) / 8, 256, 0, s>>>(info, tclass, pitch, nrows);
+    build_tclass_kernel<<<(ntask + 7) / 8, 256, 0, s>>>(info, tclass, gen_list, gen_count, pitch, nrows);
     return cudaGetLastError();
 }
 

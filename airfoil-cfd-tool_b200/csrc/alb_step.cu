@@ -26,11 +26,38 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// Tuning knobs (defaults chosen from B200 measurements, see DESIGN.md / profiles/):
+//   ALB_LD_HINT  0 ld.global.nc   1 ld.global.cs (evict first)   2 ld.global.nc.L1::no_allocate
+//   ALB_ST_HINT  0 st.global      1 st.global.cs (evict first)
+//   ALB_FAST_MINBLOCKS  resident CTAs per SM the fast kernel is compiled for
+#ifndef ALB_LD_HINT
+#define ALB_LD_HINT 0
+#endif
+#ifndef ALB_ST_HINT
+#define ALB_ST_HINT 0
+#endif
+#ifndef ALB_FAST_MINBLOCKS
+#define ALB_FAST_MINBLOCKS 4
+#endif
+
 __device__ __forceinline__ float4 ld4(const float *p) {
+#if ALB_LD_HINT == 1
+    return __ldcs(reinterpret_cast<const float4 *>(p));
+#elif ALB_LD_HINT == 2
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#else
     return __ldg(reinterpret_cast<const float4 *>(p));
+#endif
 }
 __device__ __forceinline__ void st4(float *p, const float4 &v) {
+#if ALB_ST_HINT == 1
+    __stcs(reinterpret_cast<float4 *>(p), v);
+#else
     *reinterpret_cast<float4 *>(p) = v;
+#endif
 }
 
 // x / tau, correctly rounded (== IEEE division), for the uniform divisor tau.
@@ -147,27 +174,36 @@ __device__ __forceinline__ float4 from_right(const float4 &v, float edge, int la
 
 constexpr int MODE_STEP = 0, MODE_MACRO = 1;
 
-template <int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+// GENERAL = false: every task of the slab, but tasks of class TC_GENERAL are skipped -- 64
+// registers, 4 CTAs per SM.  GENERAL = true: only the compacted list of TC_GENERAL tasks
+// (tasks that mix cell types or touch the body), with the per-cell patching code.
+template <int MODE, bool GENERAL>
+__global__ void __launch_bounds__(BLOCK_THREADS, GENERAL ? 2 : ALB_FAST_MINBLOCKS)
 step_kernel(const __grid_constant__ StepParams p) {
     const int lane = threadIdx.x & 31;
-    const int task = blockIdx.x * TASKS_PER_BLOCK + (threadIdx.x >> 5);
-    if (MODE == MODE_STEP && blockIdx.x == 0 && threadIdx.x == 0 && p.me_next) {
+    int task = blockIdx.x * TASKS_PER_BLOCK + (threadIdx.x >> 5);
+    if (!GENERAL && MODE == MODE_STEP && blockIdx.x == 0 && threadIdx.x == 0 && p.me_next) {
         p.me_next[0] = 0;   // next step's accumulator; kernels of one handle run in stream order
         p.me_next[1] = 0;
     }
-    if (task >= p.ntasks) return;
+    if (GENERAL) {
+        if (task >= p.ngen) return;
+        task = p.gen_list[task];
+    } else if (task >= p.ntasks) {
+        return;
+    }
     const int j = task / p.tpr + 1;          // local row (0 is the lower ghost row)
     const int s = task - (j - 1) * p.tpr;
     const int x0 = s * TASK_CELLS + lane * 4;
     const size_t c = (size_t)j * p.pitch + x0;
     const size_t plane = p.plane;
-    const int cls = p.tclass[(size_t)j * p.tpr + s];   // warp-uniform
+    const int cls = GENERAL ? (int)TC_GENERAL : (int)p.tclass[(size_t)j * p.tpr + s];   // warp-uniform
+    if (!GENERAL && cls == TC_GENERAL) return;
     const float *__restrict__ src = p.src;
 
     float4 o[9];
 
-    if (cls == TC_EQUIL) {
+    if (!GENERAL && cls == TC_EQUIL) {
         // HTML:314-322: whole task is inlet/top/bottom equilibrium at (1, U0, 0)
         if (MODE == MODE_STEP) {
 #pragma unroll
@@ -182,7 +218,7 @@ step_kernel(const __grid_constant__ StepParams p) {
         }
         return;
     }
-    if (cls == TC_SOLID) {
+    if (!GENERAL && cls == TC_SOLID) {
         // HTML:287-294: solid cells swap every population with its opposite
         if (MODE == MODE_STEP) {
             const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
@@ -224,7 +260,7 @@ step_kernel(const __grid_constant__ StepParams p) {
 
     float4 own[9];
     uint2 iv = make_uint2(0u, 0u);
-    if (cls == TC_GENERAL) {
+    if (GENERAL) {
         // own-cell populations for bounce-back / solid swap (v0, v1, v3 are own already)
         iv = __ldg(reinterpret_cast<const uint2 *>(p.info + c));
         own[0] = v0;
@@ -259,7 +295,7 @@ step_kernel(const __grid_constant__ StepParams p) {
         for (int i = 0; i < 9; i++) f[i] = comp(o[i], k);
 
         unsigned info = 0;
-        if (cls == TC_GENERAL) {
+        if (GENERAL) {
             info = (k < 2 ? iv.x : iv.y) >> ((k & 1) * 16) & 0xffffu;
             const unsigned links = info & 0xffu;
             if (links && (info >> 8) == CT_FLUID) {
@@ -288,7 +324,7 @@ step_kernel(const __grid_constant__ StepParams p) {
         if (MODE == MODE_STEP) collide(f, m, p.tau, p.inv_tau);
         bool hit = m.hit;
 
-        if (cls == TC_GENERAL) {
+        if (GENERAL) {
             const int type = info >> 8;
             if (type != CT_FLUID) hit = false;
             if (type == CT_SOLID) {
@@ -336,7 +372,7 @@ step_kernel(const __grid_constant__ StepParams p) {
             st4(p.peer_lo_dst + 8 * p.peer_lo_plane + p.peer_lo_row + x0, o[8]);
         }
 
-        if (cls == TC_GENERAL && p.me_slot) {
+        if (GENERAL && p.me_slot) {
             // integer sums are exact and order independent: shuffle tree, one atomic per warp
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
@@ -358,15 +394,28 @@ step_kernel(const __grid_constant__ StepParams p) {
 
 }  // namespace
 
-cudaError_t launch_step(const StepParams &p, cudaStream_t s) {
+// The fast kernel and the general kernel of one step read the same source state and write
+// disjoint cells, so the caller may run them concurrently on two streams.
+cudaError_t launch_step_fast(const StepParams &p, cudaStream_t s) {
     const int nblocks = (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
-    step_kernel<MODE_STEP><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    step_kernel<MODE_STEP, false><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step_general(const StepParams &p, cudaStream_t s) {
+    if (p.ngen == 0) return cudaSuccess;
+    const int gblocks = (p.ngen + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
+    step_kernel<MODE_STEP, true><<<gblocks, BLOCK_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_macro(const StepParams &p, cudaStream_t s) {
     const int nblocks = (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
-    step_kernel<MODE_MACRO><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    step_kernel<MODE_MACRO, false><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || p.ngen == 0) return e;
+    const int gblocks = (p.ngen + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
+    step_kernel<MODE_MACRO, true><<<gblocks, BLOCK_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -306,7 +306,7 @@ def main():
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": args.steps * (1 if world == 1 else 3),
+            "gpu_launches": args.steps * (2 if world == 1 else 4),
             "clocks": clocks,
             "check": {"CL_me": forces.get("CL_me"), "CD_me": forces.get("CD_me"),
                       "CL_pressure_raw": forces.get("CL_raw"), "CD_pressure_raw": forces.get("CD_raw"),

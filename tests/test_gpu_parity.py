@@ -203,8 +203,12 @@ def test_set_get_populations_roundtrip(al):
 
 
 def test_closed_box_mass_conservation(al):
-    """No inlet/outlet influence: a sealed solid box around quiescent-but-perturbed fluid.
-    Stream + collide + half-way bounce-back must conserve mass to 1e-6 relative."""
+    """No inlet/outlet influence: a sealed solid box around perturbed fluid.
+
+    Stream + collide + half-way bounce-back conserve mass up to fp32 rounding.  The reference's
+    arithmetic has a systematic rounding bias of about 1.2e-8 per step (the oracle shows exactly
+    the same drift), so 1e-6 relative holds for ~80 steps: checked over 50 steps, and after 500
+    steps the populations must still equal the oracle's bit for bit (mass parity = exact)."""
     nx, ny = 128, 96
     m = np.zeros((ny, nx), np.uint8)
     m[:3, :] = 255; m[-3:, :] = 255; m[:, :3] = 255; m[:, -3:] = 255
@@ -214,15 +218,24 @@ def test_closed_box_mass_conservation(al):
     inside &= m == 0
     t = al.WindTunnel(nx, ny, 0, u0=0.0)
     t.set_mask(m)
+    o = olbm.OracleTunnel(nx, ny, 0.0)
+    o.set_mask(m)
     F = t.populations()
+    assert_bitwise(F, o.F, "closed box init")
     rng = np.random.default_rng(3)
     F *= (1 + 0.05 * rng.standard_normal(F.shape)).astype(np.float32)
     t.set_populations(F)
+    o.F[...] = F
     m0 = float(F[:, inside].astype(np.float64).sum())
-    t.step(500)
+    t.step(50); o.step(50)
     m1 = float(t.populations()[:, inside].astype(np.float64).sum())
     assert abs(m1 / m0 - 1) <= MASS_TOL
-    assert t.clamp_hits() == 0
+    t.step(450); o.step(450)
+    Fg = t.populations()
+    assert_bitwise(Fg, o.F, "closed box after 500 steps")
+    drift = float(Fg[:, inside].astype(np.float64).sum()) / m0 - 1
+    assert abs(drift) / 500 < 2e-8          # per-step fp32 rounding bias, same as the oracle's
+    assert t.clamp_hits() == 0 == o.clamp_hits
 
 
 # ---- (c) diagnostics ----------------------------------------------------------
