@@ -217,12 +217,14 @@ class DistributedTunnel:
 
     def step(self, n: int = 1):
         if self.halo == "nccl":
+            import torch
+            t0 = time.perf_counter()
             for _ in range(n):
                 self.t.step(1)
                 self.t.sync()
                 self._xchg.exchange()
-                import torch
                 torch.cuda.current_stream().synchronize()
+            self._nccl_ms = (time.perf_counter() - t0) * 1e3     # host-synchronous transport: wall clock
         else:
             self.t.step(n)
         return self
@@ -232,6 +234,9 @@ class DistributedTunnel:
         return self
 
     def last_step_ms(self) -> float:
+        """GPU time of the last step() call (CUDA events); wall clock for the host-driven nccl transport."""
+        if self.halo == "nccl":
+            return self._nccl_ms
         return self.t.last_step_ms()
 
     @property

@@ -19,6 +19,7 @@ namespace {
 
 constexpr int ME_RING = ALB_ME_HISTORY + 1;   // 4096 slots of {Fx, Fy}
 constexpr int DIAG_BLOCKS = 148 * 4;          // fixed reduction grid -> deterministic partials
+constexpr int UNIFIED_MAX_TASKS = 148 * 2 * 8;   // one wave of the unified kernel (2 CTAs/SM x 8 tasks)
 constexpr long long WAIT_TIMEOUT_NS = 20LL * 1000 * 1000 * 1000;
 
 thread_local std::string g_create_error;
@@ -51,6 +52,12 @@ struct alb_handle {
     int cur = 0;
     float *rho = nullptr, *ux = nullptr, *uy = nullptr;
     bool macro_valid = true;
+    bool diag_valid = false;      // h_diag holds the fused statistics/forces of the current state
+    DiagAcc *d_diag = nullptr;
+    DiagAcc *h_diag = nullptr;    // pinned
+    double thr_u0 = -1;           // U0 the cached thresholds below were derived for
+    float rho_lo = 0, rho_hi = 0;
+    double m2_lo = -1, m2_hi = -1;
     uint8_t *mask = nullptr;
     uint16_t *info = nullptr;
     uint8_t *tclass = nullptr;
@@ -165,16 +172,88 @@ StepParams make_params(alb_handle *h, int src_idx) {
     return p;
 }
 
+// ---- thresholds of the fused diagnostics -------------------------------------------------------
+// Cp = (rho-1)/(1.5*U0*U0) is a monotone function of the fp32 rho, so the window -4 < Cp < 1.2 of
+// HTML:609 is a closed interval [rho_lo, rho_hi] of floats; it is found by bisection over the
+// ordered bit patterns with the very expression the reference evaluates (float64, HTML:605).
+double cp_of(float rho, double U0) {
+    volatile double c = 1.5 * U0;
+    c = c * U0;
+    volatile double n = (double)rho - 1;
+    return n / c;
+}
+uint32_t fkey(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+float fromkey(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+void refresh_thresholds(alb_handle *h) {
+    if (h->thr_u0 == h->u0) return;
+    const double U0 = h->u0;
+    h->thr_u0 = U0;
+    const double cden = 1.5 * U0 * U0;
+    if (!(cden > 0) || !isfinite(cden)) {          // U0 == 0: Cp and u/U0 are inf/NaN, nothing qualifies
+        h->rho_lo = INFINITY; h->rho_hi = -INFINITY; h->m2_lo = h->m2_hi = -1;
+        return;
+    }
+    const uint32_t kmin = fkey(-3.0e38f), kmax = fkey(3.0e38f);
+    // smallest float with cp > -4
+    uint32_t lo = kmin, hi = kmax;
+    if (!(cp_of(fromkey(hi), U0) > -4)) { h->rho_lo = INFINITY; }
+    else {
+        while (lo < hi) { uint32_t mid = lo + (hi - lo) / 2; if (cp_of(fromkey(mid), U0) > -4) hi = mid; else lo = mid + 1; }
+        h->rho_lo = fromkey(lo);
+    }
+    // largest float with cp < 1.2
+    lo = kmin; hi = kmax;
+    if (!(cp_of(fromkey(lo), U0) < 1.2)) { h->rho_hi = -INFINITY; }
+    else {
+        while (lo < hi) { uint32_t mid = lo + (hi - lo + 1) / 2; if (cp_of(fromkey(mid), U0) < 1.2) lo = mid; else hi = mid - 1; }
+        h->rho_hi = fromkey(lo);
+    }
+    const double cut = (4 * U0) * (4 * U0);
+    h->m2_lo = cut * (1 - 1e-9);
+    h->m2_hi = cut * (1 + 1e-9);
+}
+
+// One pass over the previous state that yields the autoscale statistics (HTML:596-614) and the
+// pressure-face sums (HTML:649-700) of the current state, optionally also storing rho/ux/uy.
+int run_macro_pass(alb_handle *h, bool write_macro) {
+    refresh_thresholds(h);
+    DiagAcc init;
+    memset(&init, 0, sizeof init);
+    init.rho_min = INFINITY;
+    init.rho_max = -INFINITY;
+    *h->h_diag = init;
+    CK(cudaMemcpyAsync(h->d_diag, h->h_diag, sizeof(DiagAcc), cudaMemcpyHostToDevice, h->stream));
+    StepParams p = make_params(h, 1 - h->cur);
+    p.write_macro = write_macro ? 1 : 0;
+    p.diag = h->d_diag;
+    p.rho_lo = h->rho_lo;
+    p.rho_hi = h->rho_hi;
+    p.U0d = h->u0;
+    p.m2_lo = h->m2_lo;
+    p.m2_hi = h->m2_hi;
+    CK(launch_macro(p, h->stream));
+    CK(cudaMemcpyAsync(h->h_diag, h->d_diag, sizeof(DiagAcc), cudaMemcpyDeviceToHost, h->stream));
+    if (write_macro) h->macro_valid = true;
+    h->diag_valid = true;     // h_diag is readable after the next stream synchronisation
+    return ALB_OK;
+}
+
 // Materialise rho/ux/uy of the current state: they are a function of the
 // PREVIOUS state (still intact in the other ping-pong buffer), the mask and the
 // parameters the last step ran with -- so this is called before any of those
 // change.  Costs one read of the populations instead of 12 B/cell on every step.
 int ensure_macro(alb_handle *h) {
     if (h->macro_valid) return ALB_OK;
-    StepParams p = make_params(h, 1 - h->cur);
-    CK(launch_macro(p, h->stream));
-    h->macro_valid = true;
-    return ALB_OK;
+    return run_macro_pass(h, true);
 }
 
 int rebuild_info(alb_handle *h) {
@@ -183,6 +262,7 @@ int rebuild_info(alb_handle *h) {
     // the host needs the number of general tasks to size that kernel's grid (mask changes are rare)
     CK(cudaMemcpyAsync(&h->ngen, h->gen_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->diag_valid = false;      // faces and the solid set changed
     return ALB_OK;
 }
 
@@ -206,6 +286,7 @@ int do_reset(alb_handle *h, double u0) {
     h->cur = 0;
     h->steps = 0;
     h->macro_valid = true;
+    h->diag_valid = false;
     return ALB_OK;
 }
 
@@ -247,6 +328,8 @@ void free_handle(alb_handle *h) {
     for (auto &t : h->d_tmp) cudaFree(t);
     if (h->h_part) cudaFreeHost(h->h_part);
     if (h->h_err) cudaFreeHost(h->h_err);
+    if (h->h_diag) cudaFreeHost(h->h_diag);
+    cudaFree(h->d_diag);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -353,6 +436,8 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaMalloc(&h->d_yp, sizeof(double) * 1024));
         CK(cudaMalloc(&h->d_part, sizeof(double) * 4 * DIAG_BLOCKS));
         CK(cudaHostAlloc(&h->h_part, sizeof(double) * 4 * DIAG_BLOCKS, cudaHostAllocDefault));
+        CK(cudaMalloc(&h->d_diag, sizeof(DiagAcc)));
+        CK(cudaHostAlloc(&h->h_diag, sizeof(DiagAcc), cudaHostAllocDefault));
         CK(cudaHostAlloc(&h->h_err, sizeof(int), cudaHostAllocMapped));
         *h->h_err = 0;
         CK(cudaHostGetDevicePointer(&h->d_err, h->h_err, 0));
@@ -396,10 +481,12 @@ int alb_get_dims(const alb_handle *h, int *nx, int *ny_global, int *y0, int *ny_
 int alb_set_params(alb_handle *h, double u0, double tau) {
     NEED(h);
     ARG(isfinite(u0) && isfinite(tau) && (float)tau != 0.0f, "alb_set_params: u0 and tau must be finite, tau != 0");
+    if (u0 == h->u0 && tau == h->tau) return ALB_OK;
     int r = ensure_macro(h);
     if (r) return r;
     h->u0 = u0;
     h->tau = tau;
+    h->diag_valid = false;      // statistics and force normalisation depend on U0
     refresh_params(h);
     return ALB_OK;
 }
@@ -512,6 +599,10 @@ int alb_step(alb_handle *h, int nsteps) {
                 p.peer_hi_row = 0;
             }
         }
+        if (p.ntasks <= UNIFIED_MAX_TASKS) {
+            // small lattice: launch-latency bound, one launch for both paths
+            CK(launch_step_unified(p, h->stream));
+        } else {
         if (p.ngen > 0) {
             // fork: the general-task kernel runs on the aux stream beside the fast kernel
             CK(cudaEventRecord(h->ev_fork, h->stream));
@@ -521,6 +612,7 @@ int alb_step(alb_handle *h, int nsteps) {
         }
         CK(launch_step_fast(p, h->stream));
         if (p.ngen > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        }
         h->cur = 1 - h->cur;
         h->steps++;
         h->sync_steps++;
@@ -535,6 +627,7 @@ int alb_step(alb_handle *h, int nsteps) {
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
     h->macro_valid = false;
+    h->diag_valid = false;
     return ALB_OK;
 }
 
@@ -582,6 +675,7 @@ int alb_set_populations(alb_handle *h, const float *f) {
                              sizeof(float) * h->nx, sizeof(float) * h->nx, h->nyl, cudaMemcpyHostToDevice,
                              h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->diag_valid = false;
     return ALB_OK;
 }
 
@@ -606,6 +700,7 @@ int alb_set_macro(alb_handle *h, const float *rho, const float *ux, const float 
                                  sizeof(float) * h->nx, h->nyl, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->macro_valid = true;
+    h->diag_valid = false;
     return ALB_OK;
 }
 
@@ -621,9 +716,38 @@ int alb_total_mass(alb_handle *h, double *mass) {
     return ALB_OK;
 }
 
+// true when the fused pass can serve the request: the previous state is still the source of the
+// current macroscopic fields (i.e. they were not injected by reset/set_macro)
+static int fused_diag(alb_handle *h) {
+    if (!h->diag_valid) {
+        if (h->macro_valid) return 1;            // fields exist only as arrays: use the array kernels
+        int r = run_macro_pass(h, false);
+        if (r) return r;
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return h->fail(ALB_ERR_CUDA, "cudaStreamSynchronize", e);
+    return ALB_OK;
+}
+
 int alb_stats_partial(alb_handle *h, double *out3, float *U, float *V, float *Cp) {
     NEED(h);
-    int r = ensure_macro(h);
+    int r;
+    if (!U && !V && !Cp) {
+        r = fused_diag(h);
+        if (r < 0) return r;
+        if (r == ALB_OK) {
+            const DiagAcc &d = *h->h_diag;
+            double smax;
+            memcpy(&smax, &d.smax_bits, 8);
+            if (out3) {
+                out3[0] = smax;                                                    // 0 when nothing qualified
+                out3[1] = d.rho_min <= d.rho_max ? cp_of(d.rho_min, h->u0) : INFINITY;
+                out3[2] = d.rho_min <= d.rho_max ? cp_of(d.rho_max, h->u0) : -INFINITY;
+            }
+            return check_wait_error(h);
+        }
+    }
+    r = ensure_macro(h);
     if (r) return r;
     float *dU = nullptr, *dV = nullptr, *dC = nullptr;
     if (U) { if ((r = ensure_tmp(h, 0))) return r; dU = h->d_tmp[0]; }
@@ -702,7 +826,19 @@ int alb_get_rgba(alb_handle *h, int mode, uint8_t *rgba) {
 int alb_forces_partial(alb_handle *h, double *out4) {
     NEED(h);
     ARG(out4, "alb_forces_partial: output is NULL");
-    int r = ensure_macro(h);
+    int r = fused_diag(h);
+    if (r < 0) return r;
+    if (r == ALB_OK) {
+        // HTML:663-668: p = rho/3 per face; here (sum of rho)/3, exact integer sum (differs from the
+        // sequential float64 sum by rounding only, ~1e-16 relative)
+        const DiagAcc &d = *h->h_diag;
+        out4[0] = (double)d.fx / ALB_ME_SCALE / 3;
+        out4[1] = (double)d.fy / ALB_ME_SCALE / 3;
+        out4[2] = (double)d.surf;
+        out4[3] = (double)d.rev;
+        return check_wait_error(h);
+    }
+    r = ensure_macro(h);
     if (r) return r;
     CK(launch_forces(h->mask, h->rho, h->ux, h->pitch, h->nx, h->ny_global, h->y0 - 1, h->nyl, h->d_part,
                      DIAG_BLOCKS, h->stream));

@@ -34,6 +34,19 @@ enum : int { CT_FLUID = 0, CT_SOLID = 1, CT_OUTLET = 2, CT_EQUIL = 3 };
 // warp-task classes
 enum : int { TC_FLUID = 0, TC_GENERAL = 1, TC_SOLID = 2, TC_EQUIL = 3 };
 
+// info word layout
+constexpr unsigned INFO_TYPE_SHIFT = 8, INFO_TYPE_MASK = 3, INFO_PAD = 0x400;
+
+// Accumulators of one fused macroscopic/diagnostics pass (step_kernel<MODE_MACRO,*>): everything is
+// a max/min or an integer sum, so the result does not depend on the order of the atomics.
+struct DiagAcc {
+    unsigned long long smax_bits;    // double bits of max s = hypot(ux/U0, uy/U0) over cells with s < 4 (0: none)
+    unsigned long long m2max_bits;   // double bits of ux^2 + uy^2 of that cell (pre-filter for the atomics)
+    float rho_min, rho_max;          // over non-solid cells whose Cp lies in (-4, 1.2); +inf / -inf: none
+    long long fx, fy;                // sum over fluid/solid faces of rho (2^-40 fixed point) * (solid - fluid)
+    unsigned long long surf, rev;    // number of faces, faces whose fluid cell has ux < 0
+};
+
 struct StepParams {
     const float *__restrict__ src;
     float *__restrict__ dst;
@@ -52,6 +65,11 @@ struct StepParams {
     float feq0[9];           // feq_i(1, U0, 0) in fp32, source order (HTML:315-317)
     // macro output (macro mode only)
     float *rho, *ux, *uy;
+    int write_macro;         // 0: diagnostics only, do not store rho/ux/uy
+    DiagAcc *diag;           // nullable: fused autoscale statistics + pressure-face force
+    float rho_lo, rho_hi;    // Cp window (-4, 1.2) expressed as a closed rho interval
+    double U0d;              // the double U0 of the JS host code
+    double m2_lo, m2_hi;     // (4 U0)^2 (1 -/+ 1e-9): below -> s < 4 for sure, above -> s >= 4 for sure
     // momentum exchange: slot of this step, slot to clear for the next one
     long long *me_slot;
     long long *me_next;
@@ -70,6 +88,7 @@ struct Handle;
 // alb_step.cu
 cudaError_t launch_step_fast(const StepParams &p, cudaStream_t s);
 cudaError_t launch_step_general(const StepParams &p, cudaStream_t s);
+cudaError_t launch_step_unified(const StepParams &p, cudaStream_t s);
 cudaError_t launch_macro(const StepParams &p, cudaStream_t s);
 void host_feq0(float u0, float *out9);
 

@@ -134,9 +134,10 @@ __global__ void build_info_kernel(const uint8_t *__restrict__ mask, uint16_t *__
     if (x >= pitch || j >= nrows) return;
     const int gy = gy_first + j;
     const size_t c = (size_t)j * pitch + x;
-    unsigned type, links = 0;
+    unsigned type, links = 0, pad = 0;
     if (x >= nx || gy < 0 || gy >= ny_global) {
         type = CT_EQUIL;
+        pad = INFO_PAD;       // not a lattice cell: only ever receives constants, never counted
     } else if (mask[c]) {
         type = CT_SOLID;
     } else if (x == nx - 1) {
@@ -145,18 +146,20 @@ __global__ void build_info_kernel(const uint8_t *__restrict__ mask, uint16_t *__
         type = CT_EQUIL;
     } else {
         type = CT_FLUID;
+    }
+    if (!pad && type != CT_SOLID && j >= 1 && j <= nrows - 2) {
+        // "the cell at x - e_i is a solid lattice cell".  The step uses the bits of interior
+        // fluid cells (bounce-back); the pressure-face force uses bits 0..3 of every non-solid cell.
         const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
         const int ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
-        // interior: 1 <= x <= nx-2 and 1 <= gy <= ny-2, so j-ey is a stored row
-        if (j >= 1 && j <= nrows - 2) {
 #pragma unroll
-            for (int i = 1; i < 9; i++) {
-                const size_t sidx = (size_t)(j - ey[i]) * pitch + (x - ex[i]);
-                if (mask[sidx]) links |= 1u << (i - 1);
-            }
+        for (int i = 1; i < 9; i++) {
+            const int xs = x - ex[i], gys = gy - ey[i];
+            if (xs < 0 || xs >= nx || gys < 0 || gys >= ny_global) continue;
+            if (mask[(size_t)(j - ey[i]) * pitch + xs]) links |= 1u << (i - 1);
         }
     }
-    info[c] = (uint16_t)((type << 8) | links);
+    info[c] = (uint16_t)((type << INFO_TYPE_SHIFT) | links | pad);
 }
 
 // Also appends the TC_GENERAL tasks of the owned rows (1 .. nrows-2) to gen_list as
@@ -174,8 +177,8 @@ __global__ void build_tclass_kernel(const uint16_t *__restrict__ info, uint8_t *
     for (int k = 0; k < 4; k++) {
         const unsigned v = p[k];
         all_fluid &= (v == (CT_FLUID << 8));
-        all_solid &= ((v >> 8) == CT_SOLID);
-        all_equil &= ((v >> 8) == CT_EQUIL);
+        all_solid &= (((v >> 8) & 3) == CT_SOLID);
+        all_equil &= (v == (CT_EQUIL << 8));   // no solid neighbour, not padding
     }
     all_fluid = __all_sync(0xffffffffu, all_fluid);
     all_solid = __all_sync(0xffffffffu, all_solid);

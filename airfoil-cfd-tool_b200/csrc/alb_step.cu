@@ -174,19 +174,122 @@ __device__ __forceinline__ float4 from_right(const float4 &v, float edge, int la
 
 constexpr int MODE_STEP = 0, MODE_MACRO = 1;
 
-// GENERAL = false: every task of the slab, but tasks of class TC_GENERAL are skipped -- 64
-// registers, 4 CTAs per SM.  GENERAL = true: only the compacted list of TC_GENERAL tasks
-// (tasks that mix cell types or touch the body), with the per-cell patching code.
-template <int MODE, bool GENERAL>
-__global__ void __launch_bounds__(BLOCK_THREADS, GENERAL ? 2 : ALB_FAST_MINBLOCKS)
+// ---- fused diagnostics of the macro pass (HTML:596-614 statistics, HTML:649-700 faces) ----------
+struct DiagLocal {
+    float rmin = INFINITY, rmax = -INFINITY;
+    double m2 = -1.0;        // largest ux^2+uy^2 among cells with s < 4
+    float bux = 0.f, buy = 0.f;
+    long long fx = 0, fy = 0;
+    unsigned surf = 0, rev = 0;
+};
+
+__device__ __forceinline__ double speed_ratio(float ux, float uy, double U0) {
+    return hypot(__ddiv_rn((double)ux, U0), __ddiv_rn((double)uy, U0));   // Math.hypot(ux/U0, uy/U0)
+}
+
+// One non-solid lattice cell.  s is monotone in ux^2+uy^2 (exact in double), so only the arg-max
+// candidate ever needs the hypot; cells within 1e-9 of the s < 4 cut are decided exactly.
+__device__ __forceinline__ void diag_cell(const StepParams &p, DiagLocal &d, float rho, float ux, float uy) {
+    if (rho >= p.rho_lo && rho <= p.rho_hi) {
+        d.rmin = fminf(d.rmin, rho);
+        d.rmax = fmaxf(d.rmax, rho);
+    }
+    const double m2 = __dadd_rn(__dmul_rn((double)ux, (double)ux), __dmul_rn((double)uy, (double)uy));
+    if (m2 > d.m2 && m2 < p.m2_hi) {
+        if (m2 >= p.m2_lo && !(speed_ratio(ux, uy, p.U0d) < 4.0)) return;
+        d.m2 = m2;
+        d.bux = ux;
+        d.buy = uy;
+    }
+}
+
+// faces of a non-solid cell: bit i-1 of `links` (i = 1..4) says the cell at x - e_i is solid
+__device__ __forceinline__ void diag_faces(DiagLocal &d, unsigned links, float rho, float ux) {
+    const unsigned faces = links & 0xfu;
+    if (!faces) return;
+    const long long q = __double2ll_rn((double)rho * 0x1p40);
+    const int n = __popc(faces);
+    if (faces & 1u) d.fx -= q;   // solid at x-1: force on the body points to -x
+    if (faces & 4u) d.fx += q;   // solid at x+1
+    if (faces & 2u) d.fy -= q;   // solid at y-1
+    if (faces & 8u) d.fy += q;   // solid at y+1
+    d.surf += n;
+    if (ux < 0.0f) d.rev += n;
+}
+
+__device__ __forceinline__ void atomic_min_float(float *a, float v) {
+    int *ai = reinterpret_cast<int *>(a);
+    int old = *ai;
+    while (v < __int_as_float(old)) {
+        const int assumed = old;
+        old = atomicCAS(ai, assumed, __float_as_int(v));
+        if (old == assumed) break;
+    }
+}
+__device__ __forceinline__ void atomic_max_float(float *a, float v) {
+    int *ai = reinterpret_cast<int *>(a);
+    int old = *ai;
+    while (v > __int_as_float(old)) {
+        const int assumed = old;
+        old = atomicCAS(ai, assumed, __float_as_int(v));
+        if (old == assumed) break;
+    }
+}
+
+// warp tree, then at most a handful of atomics per warp -- and none at all once the global
+// extrema have settled (plain-load pre-check)
+__device__ __forceinline__ void diag_flush(const StepParams &p, DiagLocal &d, int lane) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        d.rmin = fminf(d.rmin, __shfl_xor_sync(FULL, d.rmin, s));
+        d.rmax = fmaxf(d.rmax, __shfl_xor_sync(FULL, d.rmax, s));
+        const double om = __shfl_xor_sync(FULL, d.m2, s);
+        const float ox = __shfl_xor_sync(FULL, d.bux, s), oy = __shfl_xor_sync(FULL, d.buy, s);
+        if (om > d.m2) { d.m2 = om; d.bux = ox; d.buy = oy; }
+        d.fx += __shfl_xor_sync(FULL, d.fx, s);
+        d.fy += __shfl_xor_sync(FULL, d.fy, s);
+        d.surf += __shfl_xor_sync(FULL, d.surf, s);
+        d.rev += __shfl_xor_sync(FULL, d.rev, s);
+    }
+    if (lane != 0) return;
+    DiagAcc *g = p.diag;
+    if (d.rmin < *(volatile float *)&g->rho_min) atomic_min_float(&g->rho_min, d.rmin);
+    if (d.rmax > *(volatile float *)&g->rho_max) atomic_max_float(&g->rho_max, d.rmax);
+    if (d.m2 >= 0.0) {
+        const double cur = __longlong_as_double((long long)*(volatile unsigned long long *)&g->m2max_bits);
+        if (d.m2 >= cur * (1.0 - 1e-12)) {
+            const double sr = speed_ratio(d.bux, d.buy, p.U0d);
+            if (sr < 4.0) {
+                atomicMax(&g->smax_bits, (unsigned long long)__double_as_longlong(sr));
+                atomicMax(&g->m2max_bits, (unsigned long long)__double_as_longlong(d.m2));
+            }
+        }
+    }
+    if (d.surf) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(&g->fx), (unsigned long long)d.fx);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&g->fy), (unsigned long long)d.fy);
+        atomicAdd(&g->surf, (unsigned long long)d.surf);
+        atomicAdd(&g->rev, (unsigned long long)d.rev);
+    }
+}
+
+// KIND_FAST: every task of the slab, but tasks of class TC_GENERAL are skipped -- 64 registers,
+// 4 CTAs per SM.  KIND_GENERAL: only the compacted list of TC_GENERAL tasks (tasks that mix cell
+// types or touch the body), with the per-cell patching code.  KIND_UNIFIED: every task, both
+// paths in one launch -- for lattices so small that the step is launch-latency bound and
+// occupancy is irrelevant.
+constexpr int KIND_FAST = 0, KIND_GENERAL = 1, KIND_UNIFIED = 2;
+
+template <int MODE, int KIND>
+__global__ void __launch_bounds__(BLOCK_THREADS, KIND == KIND_FAST ? ALB_FAST_MINBLOCKS : 2)
 step_kernel(const __grid_constant__ StepParams p) {
     const int lane = threadIdx.x & 31;
     int task = blockIdx.x * TASKS_PER_BLOCK + (threadIdx.x >> 5);
-    if (!GENERAL && MODE == MODE_STEP && blockIdx.x == 0 && threadIdx.x == 0 && p.me_next) {
+    if (KIND != KIND_GENERAL && MODE == MODE_STEP && blockIdx.x == 0 && threadIdx.x == 0 && p.me_next) {
         p.me_next[0] = 0;   // next step's accumulator; kernels of one handle run in stream order
         p.me_next[1] = 0;
     }
-    if (GENERAL) {
+    if (KIND == KIND_GENERAL) {
         if (task >= p.ngen) return;
         task = p.gen_list[task];
     } else if (task >= p.ntasks) {
@@ -197,13 +300,14 @@ step_kernel(const __grid_constant__ StepParams p) {
     const int x0 = s * TASK_CELLS + lane * 4;
     const size_t c = (size_t)j * p.pitch + x0;
     const size_t plane = p.plane;
-    const int cls = GENERAL ? (int)TC_GENERAL : (int)p.tclass[(size_t)j * p.tpr + s];   // warp-uniform
-    if (!GENERAL && cls == TC_GENERAL) return;
+    const int cls = KIND == KIND_GENERAL ? (int)TC_GENERAL : (int)p.tclass[(size_t)j * p.tpr + s];   // warp-uniform
+    if (KIND == KIND_FAST && cls == TC_GENERAL) return;
+    const bool GENERAL = KIND != KIND_FAST && cls == TC_GENERAL;   // warp-uniform; compile-time false for KIND_FAST
     const float *__restrict__ src = p.src;
 
     float4 o[9];
 
-    if (!GENERAL && cls == TC_EQUIL) {
+    if (KIND != KIND_GENERAL && cls == TC_EQUIL) {
         // HTML:314-322: whole task is inlet/top/bottom equilibrium at (1, U0, 0)
         if (MODE == MODE_STEP) {
 #pragma unroll
@@ -212,13 +316,20 @@ step_kernel(const __grid_constant__ StepParams p) {
                 st4(p.dst + i * plane + c, make_float4(v, v, v, v));
             }
         } else {
-            st4(p.rho + c, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
-            st4(p.ux + c, make_float4(p.u0, p.u0, p.u0, p.u0));
-            st4(p.uy + c, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+            if (p.write_macro) {
+                st4(p.rho + c, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
+                st4(p.ux + c, make_float4(p.u0, p.u0, p.u0, p.u0));
+                st4(p.uy + c, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+            }
+            if (p.diag) {   // 128 identical border cells (1, U0, 0), none of them next to a solid
+                DiagLocal d;
+                if (lane == 0) diag_cell(p, d, 1.0f, p.u0, 0.0f);
+                diag_flush(p, d, lane);
+            }
         }
         return;
     }
-    if (!GENERAL && cls == TC_SOLID) {
+    if (KIND != KIND_GENERAL && cls == TC_SOLID) {
         // HTML:287-294: solid cells swap every population with its opposite
         if (MODE == MODE_STEP) {
             const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
@@ -226,7 +337,7 @@ step_kernel(const __grid_constant__ StepParams p) {
             for (int i = 0; i < 9; i++) o[i] = ld4(src + opp[i] * plane + c);
 #pragma unroll
             for (int i = 0; i < 9; i++) st4(p.dst + i * plane + c, o[i]);
-        } else {
+        } else if (p.write_macro) {
             st4(p.rho + c, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
             st4(p.ux + c, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
             st4(p.uy + c, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
@@ -287,6 +398,8 @@ step_kernel(const __grid_constant__ StepParams p) {
     float4 mr, mx, my;   // macro outputs (macro mode)
     long long me_fx = 0, me_fy = 0;
     unsigned hits = 0;
+    DiagLocal dl;
+    const bool want_diag = MODE == MODE_MACRO && p.diag != nullptr;
 
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -298,7 +411,7 @@ step_kernel(const __grid_constant__ StepParams p) {
         if (GENERAL) {
             info = (k < 2 ? iv.x : iv.y) >> ((k & 1) * 16) & 0xffffu;
             const unsigned links = info & 0xffu;
-            if (links && (info >> 8) == CT_FLUID) {
+            if (links && (info >> INFO_TYPE_SHIFT) == CT_FLUID) {
                 // HTML:329-330: source cell is solid -> take my own opposite population
                 const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
                 const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
@@ -325,7 +438,7 @@ step_kernel(const __grid_constant__ StepParams p) {
         bool hit = m.hit;
 
         if (GENERAL) {
-            const int type = info >> 8;
+            const int type = (info >> INFO_TYPE_SHIFT) & INFO_TYPE_MASK;
             if (type != CT_FLUID) hit = false;
             if (type == CT_SOLID) {
                 const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
@@ -344,6 +457,14 @@ step_kernel(const __grid_constant__ StepParams p) {
             }
         }
         if (hit) hits++;
+        if (want_diag) {
+            if (!GENERAL) {
+                diag_cell(p, dl, rho, ux, uy);
+            } else if (((info >> INFO_TYPE_SHIFT) & INFO_TYPE_MASK) != CT_SOLID && !(info & INFO_PAD)) {
+                diag_cell(p, dl, rho, ux, uy);
+                diag_faces(dl, info & 0xffu, rho, ux);
+            }
+        }
 
         if (MODE == MODE_STEP) {
 #pragma unroll
@@ -386,9 +507,12 @@ step_kernel(const __grid_constant__ StepParams p) {
         }
         if (hits && p.clamp_hits) atomicAdd(p.clamp_hits, (unsigned long long)hits);
     } else {
-        st4(p.rho + c, mr);
-        st4(p.ux + c, mx);
-        st4(p.uy + c, my);
+        if (p.write_macro) {
+            st4(p.rho + c, mr);
+            st4(p.ux + c, mx);
+            st4(p.uy + c, my);
+        }
+        if (want_diag) diag_flush(p, dl, lane);
     }
 }
 
@@ -398,24 +522,30 @@ step_kernel(const __grid_constant__ StepParams p) {
 // disjoint cells, so the caller may run them concurrently on two streams.
 cudaError_t launch_step_fast(const StepParams &p, cudaStream_t s) {
     const int nblocks = (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
-    step_kernel<MODE_STEP, false><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    step_kernel<MODE_STEP, KIND_FAST><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_step_general(const StepParams &p, cudaStream_t s) {
     if (p.ngen == 0) return cudaSuccess;
     const int gblocks = (p.ngen + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
-    step_kernel<MODE_STEP, true><<<gblocks, BLOCK_THREADS, 0, s>>>(p);
+    step_kernel<MODE_STEP, KIND_GENERAL><<<gblocks, BLOCK_THREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step_unified(const StepParams &p, cudaStream_t s) {
+    const int nblocks = (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
+    step_kernel<MODE_STEP, KIND_UNIFIED><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_macro(const StepParams &p, cudaStream_t s) {
     const int nblocks = (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
-    step_kernel<MODE_MACRO, false><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    step_kernel<MODE_MACRO, KIND_FAST><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || p.ngen == 0) return e;
     const int gblocks = (p.ngen + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
-    step_kernel<MODE_MACRO, true><<<gblocks, BLOCK_THREADS, 0, s>>>(p);
+    step_kernel<MODE_MACRO, KIND_GENERAL><<<gblocks, BLOCK_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 

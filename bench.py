@@ -306,7 +306,10 @@ def main():
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": args.steps * (2 if world == 1 else 4),
+            # per step: fast + general-task kernel (one unified kernel for lattices of <= 2368 tasks),
+            # plus the wait/signal flag kernels when slabs exchange halos
+            "gpu_launches": args.steps * ((1 if (tun.ny_local * ((nx + 127) // 128)) <= 2368 else 2)
+                                          + (2 if world > 1 else 0)),
             "clocks": clocks,
             "check": {"CL_me": forces.get("CL_me"), "CD_me": forces.get("CD_me"),
                       "CL_pressure_raw": forces.get("CL_raw"), "CD_pressure_raw": forces.get("CD_raw"),

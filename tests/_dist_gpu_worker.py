@@ -1,0 +1,50 @@
+"""One rank of the multi-GPU DistributedTunnel test (launched with torchrun by test_gpu_multi.py)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "airfoil-cfd-tool_b200"))
+
+import aerolab_lbm as al  # noqa: E402
+from aerolab_lbm import distributed as dm  # noqa: E402
+
+
+def main():
+    halo = sys.argv[1]
+    nx, ny, nsteps = 512, 250, 48
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    comm = dm.init_comm(world, rank, local)
+    tun = dm.DistributedTunnel(nx, ny, comm, device=local, halo=halo)
+    tun.load_shape("naca4412", alpha=9.0)
+    tun.step(nsteps // 2)
+    tun.step(nsteps - nsteps // 2)
+    tun.sync()
+    F = tun.gather("populations")
+    macro = tun.gather("macro")
+    forces = tun.forces()
+    stats = tun.update_stats()
+    ok = True
+    if rank == 0:
+        ref = al.WindTunnel(nx, ny, local)
+        ref.load_shape("naca4412", alpha=9.0)
+        ref.step(nsteps)
+        rf = ref.forces()
+        rs = ref.update_stats()
+        ok &= np.array_equal(F.view(np.uint32), ref.populations().view(np.uint32))
+        for a, b in zip(macro, ref.macro()):
+            ok &= np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        ok &= forces["surf"] == rf["surf"] and forces["rev"] == rf["rev"]
+        ok &= abs(forces["CL_raw"] - rf["CL_raw"]) <= 1e-12 * abs(rf["CL_raw"])
+        ok &= forces["CL_me"] == rf["CL_me"] and forces["CD_me"] == rf["CD_me"]
+        ok &= stats["cpMin"] == rs["cpMin"] and stats["cpMax"] == rs["cpMax"]
+        ok &= abs(stats["maxS"] - rs["maxS"]) <= 1e-14 * rs["maxS"]
+        print(f"[{halo}] world={world} bitwise_ok={bool(ok)} CL_me={forces['CL_me']!r}", flush=True)
+    tun.close()
+    comm.shutdown()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,3 +39,20 @@ def test_two_device_slabs_bitwise(al):
         assert_bitwise(np.concatenate([am[k], bm[k]], 0), wm[k], f"2-GPU macro {k}")
     me = a.me_history(1)[0] + b.me_history(1)[0]
     assert np.array_equal(me, whole.me_history(1)[0])
+
+
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
+def test_distributed_tunnel_torchrun(al, halo):
+    """One process per GPU (torchrun, NCCL plumbing): IPC/NVLink halo push and the NCCL fallback
+    must both reproduce the single-GPU run bit for bit."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    n = min(al.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29577" if halo == "p2p" else "29578",
+           os.path.join(ROOT, "tests", "_dist_gpu_worker.py"), halo]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "bitwise_ok=True" in r.stdout

@@ -169,7 +169,30 @@ def test_mask_touching_borders(al):
     for s in range(30):
         t.step(1)
         o.step(1)
+        if s % 7 == 3:
+            # fused diagnostics pass (no macro arrays yet): faces that involve border cells
+            f, w = t.forces(), o.compute_forces()
+            assert (f["surf"], f["rev"]) == (w["surf"], w["rev"])
+            assert f["CL_raw"] == pytest.approx(w["CL_raw"], rel=1e-12, abs=1e-12)
+            assert f["CD_raw"] == pytest.approx(w["CD_raw"], rel=1e-12, abs=1e-12)
+            st = t.update_stats()
+            o.update_fields()
+            assert st["cpMin"] == o.cp_min and st["cpMax"] == o.cp_max
+            assert st["maxS"] == pytest.approx(o.max_s, rel=1e-14)
         compare_state(t, o, f"random mask step {s}")
+    # array-based kernels (macro already materialised) must agree with the fused pass
+    t.step(1)
+    f1 = t.forces_partial()
+    s1 = t.stats_partial()
+    t.macro()
+    t2 = al.WindTunnel(nx, ny, 0)
+    t2.set_mask(m)
+    t2.set_populations(t.populations())
+    t2.set_macro(*t.macro())
+    f2, s2 = t2.forces_partial(), t2.stats_partial()
+    assert f1[2] == f2[2] and f1[3] == f2[3]
+    assert f1[0] == pytest.approx(f2[0], rel=1e-12, abs=1e-12) and f1[1] == pytest.approx(f2[1], rel=1e-12, abs=1e-12)
+    assert s1[1] == s2[1] and s1[2] == s2[2] and s1[0] == pytest.approx(s2[0], rel=1e-14)
 
 
 def test_alpha_and_u0_change_mid_run(al):
