@@ -64,6 +64,7 @@ struct alb_handle {
     int *gen_list = nullptr;      // TC_GENERAL tasks of this slab, [0] of gen_count = how many
     int *gen_count = nullptr;
     int ngen = 0;
+    int small_capacity = 0;       // cells the persistent small-lattice kernel can hold on this GPU
     double u0 = 0.06, tau = 0.58;
     float u0f = 0, tauf = 0, inv_tau = 0;
     float feq0[9];
@@ -447,6 +448,7 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         r = do_reset(h, 0.06);   // HTML:472, 503
         if (r) return r;
         CK(cudaStreamSynchronize(h->stream));
+        h->small_capacity = small_lattice_capacity(device);
         return ALB_OK;
     };
     rc = body();
@@ -576,7 +578,18 @@ int alb_step(alb_handle *h, int nsteps) {
     if (nsteps == 0) return ALB_OK;
     const bool halo = !h->external_halo && (h->lo.base || h->hi.base);
     CK(cudaEventRecord(h->ev0, h->stream));
-    for (int s = 0; s < nsteps; s++) {
+    const bool persistent = h->whole() && !halo && !h->external_halo && nsteps >= 2 &&
+                            (long long)h->nx * h->nyl <= h->small_capacity;
+    if (persistent) {
+        // small lattice: the whole batch of steps in ONE cooperative launch (grid barrier per step)
+        StepParams p = make_params(h, h->cur);
+        CK(launch_small_lattice(p, h->f[0], h->f[1], h->cur, nsteps, h->me_ring, h->sync_steps % ME_RING,
+                                ME_RING, h->stream));
+        h->cur = (h->cur + nsteps) & 1;
+        h->steps += nsteps;
+        h->sync_steps += nsteps;
+    }
+    for (int s = 0; s < (persistent ? 0 : nsteps); s++) {
         StepParams p = make_params(h, h->cur);
         const long long slot = h->sync_steps % ME_RING;
         p.me_slot = h->me_ring + 2 * slot;

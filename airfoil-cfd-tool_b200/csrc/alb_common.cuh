@@ -19,6 +19,14 @@
 
 #include "../../include/aerolab_lbm.h"
 
+// Tuning knob shared by the classifier (alb_geometry.cu) and the step kernel (alb_step.cu):
+// 1 = tasks that are all-fluid except the inlet cell x = 0 / the outlet cell x = nx-1 stay in the
+// fast kernel.  Measured on B200: +0.5 % at 2048x1024 but -4 % at 32768x16384 (the extra live
+// state spills in the hot path) -> off.
+#ifndef ALB_EDGE_IN_FAST
+#define ALB_EDGE_IN_FAST 0
+#endif
+
 namespace alb {
 
 constexpr int TASK_CELLS = 128;          // cells per warp task
@@ -32,7 +40,9 @@ constexpr double DX0 = -0.42, DX1 = 1.42, DY0 = -0.46, DY1 = 0.46;
 // (HTML:287, 301, 314, 324)
 enum : int { CT_FLUID = 0, CT_SOLID = 1, CT_OUTLET = 2, CT_EQUIL = 3 };
 // warp-task classes
-enum : int { TC_FLUID = 0, TC_GENERAL = 1, TC_SOLID = 2, TC_EQUIL = 3 };
+// TC_FLUID_L / TC_FLUID_R: all-fluid except the inlet cell x = 0 (first cell) / the outlet cell
+// x = nx-1 (last cell, nx a multiple of 128) -- still handled by the fast kernel
+enum : int { TC_FLUID = 0, TC_GENERAL = 1, TC_SOLID = 2, TC_EQUIL = 3, TC_FLUID_L = 4, TC_FLUID_R = 5 };
 
 // info word layout
 constexpr unsigned INFO_TYPE_SHIFT = 8, INFO_TYPE_MASK = 3, INFO_PAD = 0x400;
@@ -90,6 +100,9 @@ cudaError_t launch_step_fast(const StepParams &p, cudaStream_t s);
 cudaError_t launch_step_general(const StepParams &p, cudaStream_t s);
 cudaError_t launch_step_unified(const StepParams &p, cudaStream_t s);
 cudaError_t launch_macro(const StepParams &p, cudaStream_t s);
+int small_lattice_capacity(int device);
+cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps,
+                                 long long *me_ring, long long me_base, int me_ring_size, cudaStream_t s);
 void host_feq0(float u0, float *out9);
 
 // alb_geometry.cu

@@ -173,18 +173,26 @@ __global__ void build_tclass_kernel(const uint16_t *__restrict__ info, uint8_t *
     const int j = task / tpr, s = task - j * tpr;
     const uint16_t *p = info + (size_t)j * pitch + s * TASK_CELLS + lane * 4;
     bool all_fluid = true, all_solid = true, all_equil = true;
+    bool fluid_l = ALB_EDGE_IN_FAST && (s == 0), fluid_r = ALB_EDGE_IN_FAST && (s == tpr - 1);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const unsigned v = p[k];
-        all_fluid &= (v == (CT_FLUID << 8));
+        const bool is_fluid = (v == (CT_FLUID << 8));
+        all_fluid &= is_fluid;
         all_solid &= (((v >> 8) & 3) == CT_SOLID);
         all_equil &= (v == (CT_EQUIL << 8));   // no solid neighbour, not padding
+        // inlet cell = first cell of the row, outlet cell = last cell of the row (no padding)
+        fluid_l &= (lane == 0 && k == 0) ? (v == (CT_EQUIL << 8)) : is_fluid;
+        fluid_r &= (lane == 31 && k == 3) ? (v == (CT_OUTLET << 8)) : is_fluid;
     }
     all_fluid = __all_sync(0xffffffffu, all_fluid);
     all_solid = __all_sync(0xffffffffu, all_solid);
     all_equil = __all_sync(0xffffffffu, all_equil);
+    fluid_l = __all_sync(0xffffffffu, fluid_l);
+    fluid_r = __all_sync(0xffffffffu, fluid_r);
     if (lane == 0) {
-        const int cls = all_fluid ? TC_FLUID : (all_solid ? TC_SOLID : (all_equil ? TC_EQUIL : TC_GENERAL));
+        const int cls = all_fluid ? TC_FLUID : all_solid ? TC_SOLID : all_equil ? TC_EQUIL
+                        : fluid_l ? TC_FLUID_L : fluid_r ? TC_FLUID_R : TC_GENERAL;
         tclass[task] = (uint8_t)cls;
         if (cls == TC_GENERAL && j >= 1 && j <= nrows - 2) gen_list[atomicAdd(gen_count, 1)] = (j - 1) * tpr + s;
     }

@@ -18,7 +18,11 @@
 // tasks that are pure interior fluid (the vast majority), pure solid or pure
 // equilibrium border; everything else takes the general path that patches the
 // pulled populations per cell from a 16-bit info word.
+#include <cooperative_groups.h>
+
 #include "alb_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace alb {
 
@@ -36,6 +40,7 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef ALB_ST_HINT
 #define ALB_ST_HINT 0
 #endif
+//   ALB_EDGE_IN_FAST  (alb_common.cuh) inlet/outlet cells of otherwise all-fluid tasks patched in the fast kernel
 #ifndef ALB_FAST_MINBLOCKS
 #define ALB_FAST_MINBLOCKS 4
 #endif
@@ -289,7 +294,8 @@ step_kernel(const __grid_constant__ StepParams p) {
         p.me_next[0] = 0;   // next step's accumulator; kernels of one handle run in stream order
         p.me_next[1] = 0;
     }
-    if (KIND == KIND_GENERAL) {
+    constexpr bool from_list = KIND == KIND_GENERAL;
+    if (from_list) {
         if (task >= p.ngen) return;
         task = p.gen_list[task];
     } else if (task >= p.ntasks) {
@@ -300,14 +306,14 @@ step_kernel(const __grid_constant__ StepParams p) {
     const int x0 = s * TASK_CELLS + lane * 4;
     const size_t c = (size_t)j * p.pitch + x0;
     const size_t plane = p.plane;
-    const int cls = KIND == KIND_GENERAL ? (int)TC_GENERAL : (int)p.tclass[(size_t)j * p.tpr + s];   // warp-uniform
+    const int cls = from_list ? (int)TC_GENERAL : (int)p.tclass[(size_t)j * p.tpr + s];   // warp-uniform
     if (KIND == KIND_FAST && cls == TC_GENERAL) return;
     const bool GENERAL = KIND != KIND_FAST && cls == TC_GENERAL;   // warp-uniform; compile-time false for KIND_FAST
     const float *__restrict__ src = p.src;
 
     float4 o[9];
 
-    if (KIND != KIND_GENERAL && cls == TC_EQUIL) {
+    if (!from_list && cls == TC_EQUIL) {
         // HTML:314-322: whole task is inlet/top/bottom equilibrium at (1, U0, 0)
         if (MODE == MODE_STEP) {
 #pragma unroll
@@ -329,7 +335,7 @@ step_kernel(const __grid_constant__ StepParams p) {
         }
         return;
     }
-    if (KIND != KIND_GENERAL && cls == TC_SOLID) {
+    if (!from_list && cls == TC_SOLID) {
         // HTML:287-294: solid cells swap every population with its opposite
         if (MODE == MODE_STEP) {
             const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
@@ -456,6 +462,21 @@ step_kernel(const __grid_constant__ StepParams p) {
                 moments_plain(f, rho, ux, uy);
             }
         }
+        // inlet / outlet cell of an otherwise all-fluid task (fast kernel): lane 0 cell 0 is the
+        // equilibrium inlet (HTML:314-322), lane 31 cell 3 copies x-1 of the previous state
+        // (HTML:301-312; nine late scalar loads by that one lane)
+        if (ALB_EDGE_IN_FAST && KIND != KIND_GENERAL && cls == TC_FLUID_L && k == 0 && lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) f[i] = p.feq0[i];
+            rho = 1.0f; ux = p.u0; uy = 0.0f;
+            hit = false;
+        }
+        if (ALB_EDGE_IN_FAST && KIND != KIND_GENERAL && cls == TC_FLUID_R && k == 3 && lane == 31) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) f[i] = __ldg(src + i * plane + c + 2);   // late loads, one lane per row
+            moments_plain(f, rho, ux, uy);
+            hit = false;
+        }
         if (hit) hits++;
         if (want_diag) {
             if (!GENERAL) {
@@ -516,6 +537,90 @@ step_kernel(const __grid_constant__ StepParams p) {
     }
 }
 
+
+// ---- small lattices: one persistent cooperative launch for a whole batch of steps -------------
+// A 320x160 lattice (the reference's default) moves 3.7 MB per step: it lives in L2 and a step
+// is bound by launch latency and by the length of one thread's dependent instruction chain, not
+// by HBM.  So: one thread per cell (shortest chain, most warps), all CTAs co-resident, the whole
+// batch of steps inside one launch with a grid-wide barrier between steps.  The arithmetic is the
+// same moments_clamped()/collide() as the streaming kernels -> bit-identical results.
+__global__ void __launch_bounds__(BLOCK_THREADS)
+small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, int cur, int nsteps,
+                     long long *me_ring, long long me_base, int me_ring_size) {
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31;
+    const int tid = blockIdx.x * BLOCK_THREADS + threadIdx.x;
+    const int ncell = p.nx * p.nyl;
+    const bool active = tid < ncell;
+    const int row = active ? tid / p.nx : 0;
+    const int x = active ? tid - row * p.nx : 0;
+    const size_t c = (size_t)(row + 1) * p.pitch + x;
+    const size_t plane = p.plane;
+    const unsigned info = active ? p.info[c] : (unsigned)(CT_EQUIL << INFO_TYPE_SHIFT);
+    const int type = (info >> INFO_TYPE_SHIFT) & INFO_TYPE_MASK;
+    const unsigned links = type == CT_FLUID ? (info & 0xffu) : 0u;
+    const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+    const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+    const int ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+
+    for (int s = 0; s < nsteps; s++) {
+        const float *src = ((cur + s) & 1) ? f1 : f0;
+        float *dst = ((cur + s) & 1) ? f0 : f1;
+        long long *slot = me_ring + 2 * ((me_base + s) % me_ring_size);
+        if (tid == 0) {
+            long long *next = me_ring + 2 * ((me_base + s + 1) % me_ring_size);
+            next[0] = 0;
+            next[1] = 0;
+        }
+        long long me_fx = 0, me_fy = 0;
+        bool hit = false;
+        if (active) {
+            float f[9];
+            if (type == CT_FLUID) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) {
+                    if (i > 0 && (links & (1u << (i - 1)))) {
+                        const float b = __ldcg(src + opp[i] * plane + c);   // HTML:329-330
+                        f[i] = b;
+                        const long long q = __double2ll_rn((double)b * 0x1p41);
+                        me_fx += -ex[i] * q;
+                        me_fy += -ey[i] * q;
+                    } else {
+                        f[i] = __ldcg(src + i * plane + c - (ptrdiff_t)ey[i] * p.pitch - ex[i]);
+                    }
+                }
+                const Moments m = moments_clamped(f);
+                collide(f, m, p.tau, p.inv_tau);
+                hit = m.hit;
+            } else if (type == CT_SOLID) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) f[i] = __ldcg(src + opp[i] * plane + c);
+            } else if (type == CT_OUTLET) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) f[i] = __ldcg(src + i * plane + c - 1);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 9; i++) f[i] = p.feq0[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 9; i++) dst[i * plane + c] = f[i];
+        }
+        if (__any_sync(FULL, links != 0)) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                me_fx += __shfl_xor_sync(FULL, me_fx, d);
+                me_fy += __shfl_xor_sync(FULL, me_fy, d);
+            }
+            if (lane == 0) {
+                if (me_fx) atomicAdd(reinterpret_cast<unsigned long long *>(slot), (unsigned long long)me_fx);
+                if (me_fy) atomicAdd(reinterpret_cast<unsigned long long *>(slot + 1), (unsigned long long)me_fy);
+            }
+        }
+        if (hit && p.clamp_hits) atomicAdd(p.clamp_hits, 1ull);
+        grid.sync();
+    }
+}
+
 }  // namespace
 
 // The fast kernel and the general kernel of one step read the same source state and write
@@ -537,6 +642,26 @@ cudaError_t launch_step_unified(const StepParams &p, cudaStream_t s) {
     const int nblocks = (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
     step_kernel<MODE_STEP, KIND_UNIFIED><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
     return cudaGetLastError();
+}
+
+// Largest number of cells the persistent small-lattice kernel can own on this device (all CTAs
+// must be co-resident for the grid barrier); 0 when cooperative launches are unsupported.
+int small_lattice_capacity(int device) {
+    int coop = 0, sms = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, small_lattice_kernel, BLOCK_THREADS, 0) != cudaSuccess)
+        return 0;
+    return sms * per_sm * BLOCK_THREADS;
+}
+
+cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps,
+                                 long long *me_ring, long long me_base, int me_ring_size, cudaStream_t s) {
+    const int ncell = p.nx * p.nyl;
+    const int nblocks = (ncell + BLOCK_THREADS - 1) / BLOCK_THREADS;
+    StepParams pp = p;
+    void *args[] = {&pp, &f0, &f1, &cur, &nsteps, &me_ring, &me_base, &me_ring_size};
+    return cudaLaunchCooperativeKernel((const void *)small_lattice_kernel, dim3(nblocks), dim3(BLOCK_THREADS), args, 0, s);
 }
 
 cudaError_t launch_macro(const StepParams &p, cudaStream_t s) {
