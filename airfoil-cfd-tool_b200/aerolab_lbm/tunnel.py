@@ -376,6 +376,26 @@ class WindTunnel:
             out["forces"] = self.forces()
         return out
 
+    def save_png(self, path: Optional[str] = None, mode="speed") -> str:
+        """Write the colour-mapped field (page palettes, HTML:371-393) as a PNG; row 0 of the
+        lattice is the bottom of the image.  Default file name as in the page's export
+        (HTML:990-992).  Pure-Python encoder (zlib), no imaging dependency."""
+        import struct
+        import zlib
+        rgba = self.rgba(mode)[::-1]                     # PNG rows run top to bottom
+        h, w = rgba.shape[:2]
+        raw = b"".join(b"\x00" + rgba[y].tobytes() for y in range(h))
+
+        def chunk(tag: bytes, data: bytes) -> bytes:
+            return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+
+        png = (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0))
+               + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+        path = path or self.png_name()
+        with open(path, "wb") as fh:
+            fh.write(png)
+        return path
+
     def png_name(self) -> str:
         """File name convention of the page's PNG export (HTML:990-992)."""
         base = (self.name or "airfoil").split()

@@ -19,6 +19,7 @@
 // equilibrium border; everything else takes the general path that patches the
 // pulled populations per cell from a 16-bit info word.
 #include <cooperative_groups.h>
+#include <stdio.h>
 
 #include "alb_common.cuh"
 
@@ -44,6 +45,32 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef ALB_FAST_MINBLOCKS
 #define ALB_FAST_MINBLOCKS 4
 #endif
+
+// ALB_DEBUG_BOUNDS=1 (compute-sanitizer is not available on the pool): every population load and
+// store of the step kernels is checked against the source / destination allocation; a violation
+// prints the address and traps, which the C ABI reports as a CUDA error.
+#ifndef ALB_DEBUG_BOUNDS
+#define ALB_DEBUG_BOUNDS 0
+#endif
+#if ALB_DEBUG_BOUNDS
+// the kernels keep the bases in locals named src / dst_base / plane
+#define ALB_CHECK_SRC(ptr, n) alb_check((ptr), (n), src, 9 * plane, "load")
+#define ALB_CHECK_DST(ptr, n) alb_check((ptr), (n), dst_base, 9 * plane, "store")
+__device__ __noinline__ void alb_check(const float *ptr, int n, const float *base, size_t len, const char *what) {
+    if (ptr < base || ptr + n > base + len || (n == 4 && (reinterpret_cast<uintptr_t>(ptr) & 15))) {
+        printf("alb bounds violation: %s of %d floats at offset %lld (allocation %llu floats)\n", what, n,
+               (long long)(ptr - base), (unsigned long long)len);
+        __trap();
+    }
+}
+#else
+#define ALB_CHECK_SRC(ptr, n) ((void)0)
+#define ALB_CHECK_DST(ptr, n) ((void)0)
+#endif
+#define LD4(ptr) (ALB_CHECK_SRC((ptr), 4), ld4(ptr))
+#define LD1(ptr) (ALB_CHECK_SRC((ptr), 1), __ldg(ptr))
+#define LD1CG(ptr) (ALB_CHECK_SRC((ptr), 1), __ldcg(ptr))
+#define ST4(ptr, v) (ALB_CHECK_DST((ptr), 4), st4((ptr), (v)))
 
 __device__ __forceinline__ float4 ld4(const float *p) {
 #if ALB_LD_HINT == 1
@@ -310,6 +337,7 @@ step_kernel(const __grid_constant__ StepParams p) {
     if (KIND == KIND_FAST && cls == TC_GENERAL) return;
     const bool GENERAL = KIND != KIND_FAST && cls == TC_GENERAL;   // warp-uniform; compile-time false for KIND_FAST
     const float *__restrict__ src = p.src;
+    [[maybe_unused]] float *const dst_base = p.dst;
 
     float4 o[9];
 
@@ -319,7 +347,7 @@ step_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
             for (int i = 0; i < 9; i++) {
                 const float v = p.feq0[i];
-                st4(p.dst + i * plane + c, make_float4(v, v, v, v));
+                ST4(p.dst + i * plane + c, make_float4(v, v, v, v));
             }
         } else {
             if (p.write_macro) {
@@ -340,9 +368,9 @@ step_kernel(const __grid_constant__ StepParams p) {
         if (MODE == MODE_STEP) {
             const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
 #pragma unroll
-            for (int i = 0; i < 9; i++) o[i] = ld4(src + opp[i] * plane + c);
+            for (int i = 0; i < 9; i++) o[i] = LD4(src + opp[i] * plane + c);
 #pragma unroll
-            for (int i = 0; i < 9; i++) st4(p.dst + i * plane + c, o[i]);
+            for (int i = 0; i < 9; i++) ST4(p.dst + i * plane + c, o[i]);
         } else if (p.write_macro) {
             st4(p.rho + c, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
             st4(p.ux + c, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
@@ -354,25 +382,25 @@ step_kernel(const __grid_constant__ StepParams p) {
     // ---- pull (HTML:325-334), all loads issued before first use ------------
     const size_t cm = c - p.pitch;   // row j-1
     const size_t cp = c + p.pitch;   // row j+1
-    const float4 v0 = ld4(src + 0 * plane + c);
-    const float4 v1 = ld4(src + 1 * plane + c);
-    const float4 v2 = ld4(src + 2 * plane + cm);
-    const float4 v3 = ld4(src + 3 * plane + c);
-    const float4 v4 = ld4(src + 4 * plane + cp);
-    const float4 v5 = ld4(src + 5 * plane + cm);
-    const float4 v6 = ld4(src + 6 * plane + cm);
-    const float4 v7 = ld4(src + 7 * plane + cp);
-    const float4 v8 = ld4(src + 8 * plane + cp);
+    const float4 v0 = LD4(src + 0 * plane + c);
+    const float4 v1 = LD4(src + 1 * plane + c);
+    const float4 v2 = LD4(src + 2 * plane + cm);
+    const float4 v3 = LD4(src + 3 * plane + c);
+    const float4 v4 = LD4(src + 4 * plane + cp);
+    const float4 v5 = LD4(src + 5 * plane + cm);
+    const float4 v6 = LD4(src + 6 * plane + cm);
+    const float4 v7 = LD4(src + 7 * plane + cp);
+    const float4 v8 = LD4(src + 8 * plane + cp);
     float l1 = 0.f, l5 = 0.f, l8 = 0.f, r3 = 0.f, r6 = 0.f, r7 = 0.f;
     if (lane == 0 && x0 > 0) {
-        l1 = __ldg(src + 1 * plane + c - 1);
-        l5 = __ldg(src + 5 * plane + cm - 1);
-        l8 = __ldg(src + 8 * plane + cp - 1);
+        l1 = LD1(src + 1 * plane + c - 1);
+        l5 = LD1(src + 5 * plane + cm - 1);
+        l8 = LD1(src + 8 * plane + cp - 1);
     }
     if (lane == 31 && x0 + 4 < p.pitch) {
-        r3 = __ldg(src + 3 * plane + c + 4);
-        r6 = __ldg(src + 6 * plane + cm + 4);
-        r7 = __ldg(src + 7 * plane + cp + 4);
+        r3 = LD1(src + 3 * plane + c + 4);
+        r6 = LD1(src + 6 * plane + cm + 4);
+        r7 = LD1(src + 7 * plane + cp + 4);
     }
 
     float4 own[9];
@@ -383,12 +411,12 @@ step_kernel(const __grid_constant__ StepParams p) {
         own[0] = v0;
         own[1] = v1;
         own[3] = v3;
-        own[2] = ld4(src + 2 * plane + c);
-        own[4] = ld4(src + 4 * plane + c);
-        own[5] = ld4(src + 5 * plane + c);
-        own[6] = ld4(src + 6 * plane + c);
-        own[7] = ld4(src + 7 * plane + c);
-        own[8] = ld4(src + 8 * plane + c);
+        own[2] = LD4(src + 2 * plane + c);
+        own[4] = LD4(src + 4 * plane + c);
+        own[5] = LD4(src + 5 * plane + c);
+        own[6] = LD4(src + 6 * plane + c);
+        own[7] = LD4(src + 7 * plane + c);
+        own[8] = LD4(src + 8 * plane + c);
     }
 
     o[0] = v0;
@@ -458,7 +486,7 @@ step_kernel(const __grid_constant__ StepParams p) {
             } else if (type == CT_OUTLET) {
                 // HTML:301-312: copy all nine populations of (x-1, y), previous state
 #pragma unroll
-                for (int i = 0; i < 9; i++) f[i] = __ldg(src + i * plane + c + k - 1);
+                for (int i = 0; i < 9; i++) f[i] = LD1(src + i * plane + c + k - 1);
                 moments_plain(f, rho, ux, uy);
             }
         }
@@ -473,7 +501,7 @@ step_kernel(const __grid_constant__ StepParams p) {
         }
         if (ALB_EDGE_IN_FAST && KIND != KIND_GENERAL && cls == TC_FLUID_R && k == 3 && lane == 31) {
 #pragma unroll
-            for (int i = 0; i < 9; i++) f[i] = __ldg(src + i * plane + c + 2);   // late loads, one lane per row
+            for (int i = 0; i < 9; i++) f[i] = LD1(src + i * plane + c + 2);   // late loads, one lane per row
             moments_plain(f, rho, ux, uy);
             hit = false;
         }
@@ -499,7 +527,7 @@ step_kernel(const __grid_constant__ StepParams p) {
 
     if (MODE == MODE_STEP) {
 #pragma unroll
-        for (int i = 0; i < 9; i++) st4(p.dst + i * plane + c, o[i]);
+        for (int i = 0; i < 9; i++) ST4(p.dst + i * plane + c, o[i]);
 
         // halo push: my edge rows go straight into the neighbours' ghost rows
         // (peer memory over NVLink, or the same GPU for in-process slabs)
@@ -566,6 +594,7 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
     for (int s = 0; s < nsteps; s++) {
         const float *src = ((cur + s) & 1) ? f1 : f0;
         float *dst = ((cur + s) & 1) ? f0 : f1;
+        [[maybe_unused]] float *const dst_base = dst;
         long long *slot = me_ring + 2 * ((me_base + s) % me_ring_size);
         if (tid == 0) {
             long long *next = me_ring + 2 * ((me_base + s + 1) % me_ring_size);
@@ -580,13 +609,13 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
 #pragma unroll
                 for (int i = 0; i < 9; i++) {
                     if (i > 0 && (links & (1u << (i - 1)))) {
-                        const float b = __ldcg(src + opp[i] * plane + c);   // HTML:329-330
+                        const float b = LD1CG(src + opp[i] * plane + c);   // HTML:329-330
                         f[i] = b;
                         const long long q = __double2ll_rn((double)b * 0x1p41);
                         me_fx += -ex[i] * q;
                         me_fy += -ey[i] * q;
                     } else {
-                        f[i] = __ldcg(src + i * plane + c - (ptrdiff_t)ey[i] * p.pitch - ex[i]);
+                        f[i] = LD1CG(src + i * plane + c - (ptrdiff_t)ey[i] * p.pitch - ex[i]);
                     }
                 }
                 const Moments m = moments_clamped(f);
@@ -594,16 +623,16 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
                 hit = m.hit;
             } else if (type == CT_SOLID) {
 #pragma unroll
-                for (int i = 0; i < 9; i++) f[i] = __ldcg(src + opp[i] * plane + c);
+                for (int i = 0; i < 9; i++) f[i] = LD1CG(src + opp[i] * plane + c);
             } else if (type == CT_OUTLET) {
 #pragma unroll
-                for (int i = 0; i < 9; i++) f[i] = __ldcg(src + i * plane + c - 1);
+                for (int i = 0; i < 9; i++) f[i] = LD1CG(src + i * plane + c - 1);
             } else {
 #pragma unroll
                 for (int i = 0; i < 9; i++) f[i] = p.feq0[i];
             }
 #pragma unroll
-            for (int i = 0; i < 9; i++) dst[i * plane + c] = f[i];
+            for (int i = 0; i < 9; i++) { ALB_CHECK_DST(dst + i * plane + c, 1); dst[i * plane + c] = f[i]; }
         }
         if (__any_sync(FULL, links != 0)) {
 #pragma unroll

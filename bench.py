@@ -219,6 +219,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="configs[3]", choices=list(WORKLOADS))
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="weak: configs[3] width, 2048 rows per GPU (32768 x 2048*N), fixed work per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -245,6 +247,8 @@ def main():
     comm = dist_mod.init_comm(world, rank, local_rank)
 
     nx, ny, shape, alpha = WORKLOADS[args.workload]
+    if args.scaling == "weak":
+        ny = 2048 * world
     tun = dist_mod.DistributedTunnel(nx, ny, comm, device=local_rank, halo=args.halo)
     tun.load_shape(shape, alpha=alpha)
     tun.sync()
@@ -298,7 +302,7 @@ def main():
         line = {
             "metric": METRIC, "value": glups, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {shape} alpha={alpha} on {nx}x{ny}, U0={U0}, tau={TAU}",
                        "decomposition": f"{world} y-slab(s), one-row population halo ({args.halo})",
                        "l2": "populations (2 x %.1f GB per GPU) are far larger than the 126 MB L2; no flush needed"

@@ -1,0 +1,56 @@
+"""GPU: run the step kernels of a bounds-checked debug build (ALB_DEBUG_BOUNDS=1) over awkward
+lattices.  compute-sanitizer is not available on the GPU pool, so the library carries its own
+check: every population load/store address is validated against its allocation and a violation
+traps (surfacing as a CUDA error from alb_sync).  Runs in a subprocess because the debug build is
+a different shared library (AEROLAB_LBM_LIB)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import PKG_DIR, ROOT
+
+pytestmark = pytest.mark.gpu
+
+SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import aerolab_lbm as al
+rng = np.random.default_rng(0)
+for nx, ny in ((3, 3), (5, 4), (127, 9), (128, 8), (129, 7), (320, 160), (513, 33), (1024, 300)):
+    t = al.WindTunnel(nx, ny, 0)
+    m = (rng.random((ny, nx)) < 0.15).astype(np.uint8) * 255
+    t.set_mask(m)
+    for n in (1, 1, 7, 2):          # single-launch, persistent and split paths
+        t.step(n)
+    t.macro(); t.forces(); t.update_stats(); t.sync()
+    t.close()
+# slabs with halo pushes
+a = al.WindTunnel(200, 50, 0, y0=0, ny_local=1); b = al.WindTunnel(200, 50, 0, y0=1, ny_local=49)
+for s in (a, b): s.load_shape("naca0012", alpha=4.0)
+a.connect_local(None, b); b.connect_local(a, None)
+for _ in range(10):
+    a.step(1); b.step(1)
+a.sync(); b.sync()
+big = al.WindTunnel(4096, 600, 0); big.load_shape("naca4412", alpha=10.0); big.step(3); big.forces(); big.sync()
+print("BOUNDS_OK")
+""" % PKG_DIR
+
+
+def test_bounds_checked_build_runs_clean(tmp_path):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("alb_build", os.path.join(PKG_DIR, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = os.path.join(ROOT, "variants", "lib_bounds.so")
+    if not os.path.exists(lib):
+        try:
+            mod.nvcc_path()
+        except RuntimeError:
+            pytest.skip("no nvcc and no prebuilt variants/lib_bounds.so")
+        mod.build(defines=["ALB_DEBUG_BOUNDS=1"], out=lib)
+    r = subprocess.run([sys.executable, "-c", SCRIPT], env=dict(os.environ, AEROLAB_LBM_LIB=lib),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "BOUNDS_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "bounds violation" not in r.stdout

@@ -415,3 +415,20 @@ def test_slab_restart_needs_prime(al):
         for s in slabs:
             s.step(1)
     assert_bitwise(np.concatenate([s.populations() for s in slabs], 1), whole.populations(), "restarted slabs")
+
+
+def test_png_export(al, tmp_path):
+    import struct
+    import zlib
+    t = al.build_lbm_component(al.SHAPES["naca0012"](), "NACA 0012")
+    t.step(40)
+    t.update_stats()
+    path = t.save_png(str(tmp_path / t.png_name()), "vort")
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    w, h = struct.unpack(">II", data[16:24])
+    assert (w, h) == (320, 160)
+    idat = data[data.index(b"IDAT") + 4:data.index(b"IEND") - 8]
+    raw = zlib.decompress(idat)
+    rows = np.frombuffer(raw, np.uint8).reshape(160, 1 + 320 * 4)[:, 1:].reshape(160, 320, 4)
+    assert np.array_equal(rows[::-1], t.rgba("vort"))
