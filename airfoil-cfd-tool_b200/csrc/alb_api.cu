@@ -7,6 +7,7 @@
 // CUDA device and reports ALB_ERR_CUDA otherwise.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -17,7 +18,7 @@ using namespace alb;
 
 namespace {
 
-constexpr int ME_RING = ALB_ME_HISTORY + 1;   // 4096 slots of {Fx, Fy}
+constexpr int GRAPH_STEPS = 8;                // steps replayed per CUDA-graph launch (even)
 constexpr int DIAG_BLOCKS = 148 * 4;          // fixed reduction grid -> deterministic partials
 constexpr int UNIFIED_MAX_TASKS = 148 * 2 * 8;   // one wave of the unified kernel (2 CTAs/SM x 8 tasks)
 constexpr long long WAIT_TIMEOUT_NS = 20LL * 1000 * 1000 * 1000;
@@ -74,7 +75,8 @@ struct alb_handle {
     bool timed = false;
     long long steps = 0;          // user-visible step count
     long long sync_steps = 0;     // monotonic, drives the halo flags and the ME ring
-    long long *me_ring = nullptr;
+    MeState *me = nullptr;
+    cudaGraphExec_t graph = nullptr;   // GRAPH_STEPS steps starting at cur == 0 (see alb_step)
     unsigned long long *clamp_hits = nullptr;
     double *d_xp = nullptr, *d_yp = nullptr;
     double xp[ALB_NPANEL + 1], yp[ALB_NPANEL + 1];
@@ -86,6 +88,7 @@ struct alb_handle {
     double cl_smooth = 0, cd_smooth = 0, sep_frac = 0;
     Peer lo, hi;
     bool external_halo = false;
+    bool use_graph = true;        // replay step batches as a CUDA graph when nothing per-step is dynamic
     int *h_err = nullptr;         // mapped pinned: set by a wait kernel that timed out
     int *d_err = nullptr;
     std::string err;
@@ -140,6 +143,13 @@ __global__ void signal_kernel(int *peer_a, int *peer_b, int value) {
     __threadfence_system();
 }
 
+void drop_graph(alb_handle *h) {
+    if (h->graph) {
+        cudaGraphExecDestroy(h->graph);
+        h->graph = nullptr;
+    }
+}
+
 void refresh_params(alb_handle *h) {
     h->u0f = (float)h->u0;
     h->tauf = (float)h->tau;
@@ -170,6 +180,8 @@ StepParams make_params(alb_handle *h, int src_idx) {
     p.ux = h->ux;
     p.uy = h->uy;
     p.clamp_hits = h->clamp_hits;
+    p.me = h->me;
+    p.parity = src_idx;
     return p;
 }
 
@@ -264,6 +276,7 @@ int rebuild_info(alb_handle *h) {
     CK(cudaMemcpyAsync(&h->ngen, h->gen_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->diag_valid = false;      // faces and the solid set changed
+    drop_graph(h);              // grid sizes depend on the number of general tasks
     return ALB_OK;
 }
 
@@ -282,7 +295,9 @@ int do_reset(alb_handle *h, double u0) {
     h->u0 = u0;
     refresh_params(h);
     CK(launch_fill_init(h->f[0], h->f[1], h->plane, e, h->rho, h->ux, h->uy, (float)u0, h->stream));
-    CK(cudaMemsetAsync(h->me_ring, 0, sizeof(long long) * 2 * ME_RING, h->stream));
+    CK(cudaMemsetAsync(h->me, 0, sizeof(MeState), h->stream));
+    CK(cudaMemcpyAsync(&h->me->count, &h->sync_steps, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // sync_steps is host memory
     CK(cudaMemsetAsync(h->clamp_hits, 0, sizeof(unsigned long long), h->stream));
     h->cur = 0;
     h->steps = 0;
@@ -321,7 +336,8 @@ void free_handle(alb_handle *h) {
     cudaFree(h->tclass);
     cudaFree(h->gen_list);
     cudaFree(h->gen_count);
-    cudaFree(h->me_ring);
+    cudaFree(h->me);
+    if (h->graph) cudaGraphExecDestroy(h->graph);
     cudaFree(h->clamp_hits);
     cudaFree(h->d_xp);
     cudaFree(h->d_yp);
@@ -431,7 +447,7 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaMalloc(&h->tclass, (size_t)h->nrows * h->tpr));
         CK(cudaMalloc(&h->gen_list, sizeof(int) * (size_t)h->nrows * h->tpr));
         CK(cudaMalloc(&h->gen_count, sizeof(int)));
-        CK(cudaMalloc(&h->me_ring, sizeof(long long) * 2 * ME_RING));
+        CK(cudaMalloc(&h->me, sizeof(MeState)));
         CK(cudaMalloc(&h->clamp_hits, sizeof(unsigned long long)));
         CK(cudaMalloc(&h->d_xp, sizeof(double) * 1024));
         CK(cudaMalloc(&h->d_yp, sizeof(double) * 1024));
@@ -449,6 +465,7 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         if (r) return r;
         CK(cudaStreamSynchronize(h->stream));
         h->small_capacity = small_lattice_capacity(device);
+        h->use_graph = getenv("AEROLAB_LBM_NO_GRAPH") == nullptr;   // A/B switch for measurements
         return ALB_OK;
     };
     rc = body();
@@ -489,6 +506,7 @@ int alb_set_params(alb_handle *h, double u0, double tau) {
     h->u0 = u0;
     h->tau = tau;
     h->diag_valid = false;      // statistics and force normalisation depend on U0
+    drop_graph(h);              // tau, U0 and the inlet constants are kernel arguments
     refresh_params(h);
     return ALB_OK;
 }
@@ -572,50 +590,35 @@ int alb_get_panels(const alb_handle *h, double *xp, double *yp) {
     return ALB_OK;
 }
 
-int alb_step(alb_handle *h, int nsteps) {
-    NEED(h);
-    ARG(nsteps >= 0, "alb_step: nsteps must be >= 0");
-    if (nsteps == 0) return ALB_OK;
-    const bool halo = !h->external_halo && (h->lo.base || h->hi.base);
-    CK(cudaEventRecord(h->ev0, h->stream));
-    const bool persistent = h->whole() && !halo && !h->external_halo && nsteps >= 2 &&
-                            (long long)h->nx * h->nyl <= h->small_capacity;
-    if (persistent) {
-        // small lattice: the whole batch of steps in ONE cooperative launch (grid barrier per step)
-        StepParams p = make_params(h, h->cur);
-        CK(launch_small_lattice(p, h->f[0], h->f[1], h->cur, nsteps, h->me_ring, h->sync_steps % ME_RING,
-                                ME_RING, h->stream));
-        h->cur = (h->cur + nsteps) & 1;
-        h->steps += nsteps;
-        h->sync_steps += nsteps;
-    }
-    for (int s = 0; s < (persistent ? 0 : nsteps); s++) {
-        StepParams p = make_params(h, h->cur);
-        const long long slot = h->sync_steps % ME_RING;
-        p.me_slot = h->me_ring + 2 * slot;
-        p.me_next = h->me_ring + 2 * ((slot + 1) % ME_RING);
-        if (halo) {
-            // my step k needs the neighbours' k completed steps: their edge rows of state k are in
-            // my ghost rows, and they no longer read the ghost rows I am about to overwrite.
-            wait_kernel<<<1, 1, 0, h->stream>>>(h->lo.base ? h->flags + 0 : nullptr,
-                                                h->hi.base ? h->flags + 1 : nullptr,
-                                                (int)h->sync_steps, h->d_err, WAIT_TIMEOUT_NS);
-            const int dst_idx = 1 - h->cur;
-            if (h->lo.base) {
-                p.peer_lo_dst = h->lo.base + (size_t)dst_idx * 9 * h->lo.plane;
-                p.peer_lo_plane = h->lo.plane;
-                p.peer_lo_row = (size_t)(h->lo.nyl + 1) * h->pitch;
-            }
-            if (h->hi.base) {
-                p.peer_hi_dst = h->hi.base + (size_t)dst_idx * 9 * h->hi.plane;
-                p.peer_hi_plane = h->hi.plane;
-                p.peer_hi_row = 0;
-            }
+}  // extern "C" (reopened below)
+
+namespace {
+
+// Enqueue one step that reads buffer src_idx.  Used directly and under stream capture.
+int issue_step(alb_handle *h, int src_idx, bool halo, long long sync_step) {
+    StepParams p = make_params(h, src_idx);
+    if (halo) {
+        // my step k needs the neighbours' k completed steps: their edge rows of state k are in
+        // my ghost rows, and they no longer read the ghost rows I am about to overwrite.
+        wait_kernel<<<1, 1, 0, h->stream>>>(h->lo.base ? h->flags + 0 : nullptr,
+                                            h->hi.base ? h->flags + 1 : nullptr, (int)sync_step, h->d_err,
+                                            WAIT_TIMEOUT_NS);
+        const int dst_idx = 1 - src_idx;
+        if (h->lo.base) {
+            p.peer_lo_dst = h->lo.base + (size_t)dst_idx * 9 * h->lo.plane;
+            p.peer_lo_plane = h->lo.plane;
+            p.peer_lo_row = (size_t)(h->lo.nyl + 1) * h->pitch;
         }
-        if (p.ntasks <= UNIFIED_MAX_TASKS) {
-            // small lattice: launch-latency bound, one launch for both paths
-            CK(launch_step_unified(p, h->stream));
-        } else {
+        if (h->hi.base) {
+            p.peer_hi_dst = h->hi.base + (size_t)dst_idx * 9 * h->hi.plane;
+            p.peer_hi_plane = h->hi.plane;
+            p.peer_hi_row = 0;
+        }
+    }
+    if (p.ntasks <= UNIFIED_MAX_TASKS) {
+        // small lattice: launch-latency bound, one launch for both paths
+        CK(launch_step_unified(p, h->stream));
+    } else {
         if (p.ngen > 0) {
             // fork: the general-task kernel runs on the aux stream beside the fast kernel
             CK(cudaEventRecord(h->ev_fork, h->stream));
@@ -625,17 +628,79 @@ int alb_step(alb_handle *h, int nsteps) {
         }
         CK(launch_step_fast(p, h->stream));
         if (p.ngen > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-        }
-        h->cur = 1 - h->cur;
-        h->steps++;
-        h->sync_steps++;
-        if (halo) {
-            // I am the UPPER neighbour of lo (its flags[1]) and the LOWER neighbour of hi (its flags[0])
-            signal_kernel<<<1, 1, 0, h->stream>>>(h->lo.flags ? h->lo.flags + 1 : nullptr,
-                                                  h->hi.flags ? h->hi.flags + 0 : nullptr,
-                                                  (int)h->sync_steps);
-        }
     }
+    if (halo) {
+        // I am the UPPER neighbour of lo (its flags[1]) and the LOWER neighbour of hi (its flags[0])
+        signal_kernel<<<1, 1, 0, h->stream>>>(h->lo.flags ? h->lo.flags + 1 : nullptr,
+                                              h->hi.flags ? h->hi.flags + 0 : nullptr, (int)(sync_step + 1));
+    }
+    return ALB_OK;
+}
+
+// Capture GRAPH_STEPS steps starting from buffer 0.  Every address the kernels touch depends only
+// on the step's parity (MeState), so the instantiated graph can be replayed for the whole run; it
+// is dropped whenever a kernel argument changes (mask, parameters, neighbours).
+int capture_graph(alb_handle *h) {
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int r = ALB_OK;
+    for (int s = 0; s < GRAPH_STEPS && r == ALB_OK; s++) r = issue_step(h, s & 1, false, 0);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    if (r != ALB_OK) {
+        if (g) cudaGraphDestroy(g);
+        return r;
+    }
+    if (e != cudaSuccess) return h->fail(ALB_ERR_CUDA, "cudaStreamEndCapture", e);
+    e = cudaGraphInstantiate(&h->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+        h->graph = nullptr;
+        return h->fail(ALB_ERR_CUDA, "cudaGraphInstantiate", e);
+    }
+    return ALB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int alb_step(alb_handle *h, int nsteps) {
+    NEED(h);
+    ARG(nsteps >= 0, "alb_step: nsteps must be >= 0");
+    if (nsteps == 0) return ALB_OK;
+    const bool halo = !h->external_halo && (h->lo.base || h->hi.base);
+    CK(cudaEventRecord(h->ev0, h->stream));
+    int left = nsteps;
+    const bool persistent = h->whole() && !halo && !h->external_halo && nsteps >= 2 &&
+                            (long long)h->nx * h->nyl <= h->small_capacity;
+    if (persistent) {
+        // small lattice: the whole batch of steps in ONE cooperative launch (grid barrier per step)
+        StepParams p = make_params(h, h->cur);
+        CK(launch_small_lattice(p, h->f[0], h->f[1], h->cur, nsteps, h->stream));
+        h->cur = (h->cur + nsteps) & 1;
+        left = 0;
+    }
+    const bool use_graph = !persistent && !halo && !h->external_halo && h->use_graph && nsteps >= GRAPH_STEPS + 1;
+    int done = 0;
+    while (left > 0) {
+        if (use_graph && h->cur == 0 && left >= GRAPH_STEPS) {
+            if (!h->graph) {
+                int r = capture_graph(h);
+                if (r) return r;
+            }
+            CK(cudaGraphLaunch(h->graph, h->stream));
+            left -= GRAPH_STEPS;
+            done += GRAPH_STEPS;
+            continue;
+        }
+        int r = issue_step(h, h->cur, halo, h->sync_steps + done);
+        if (r) return r;
+        h->cur = 1 - h->cur;
+        left--;
+        done++;
+    }
+    h->steps += nsteps;
+    h->sync_steps += nsteps;
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
@@ -906,10 +971,18 @@ int alb_get_me_history(alb_handle *h, int n, long long *fxfy) {
     ARG(fxfy && n >= 0 && n <= ALB_ME_HISTORY, "alb_get_me_history: need 0 <= n <= ALB_ME_HISTORY");
     if (n > h->steps) return h->fail(ALB_ERR_STATE, "alb_get_me_history: fewer steps taken than requested");
     CK(cudaStreamSynchronize(h->stream));
+    struct { long long acc[2][2]; long long count; int pending; int pad; } head;
+    CK(cudaMemcpy(&head, h->me, sizeof head, cudaMemcpyDeviceToHost));
     for (int k = 0; k < n; k++) {
         const long long step = h->sync_steps - n + k;
-        const long long slot = step % ME_RING;
-        CK(cudaMemcpy(fxfy + 2 * k, h->me_ring + 2 * slot, sizeof(long long) * 2, cudaMemcpyDeviceToHost));
+        if (step < head.count) {
+            CK(cudaMemcpy(fxfy + 2 * k, &h->me->ring[step % ME_RING][0], sizeof(long long) * 2, cudaMemcpyDeviceToHost));
+        } else {
+            // the last step: still in the accumulator of its parity (= the buffer it read from)
+            const int parity = 1 - h->cur;
+            fxfy[2 * k] = head.acc[parity][0];
+            fxfy[2 * k + 1] = head.acc[parity][1];
+        }
     }
     return check_wait_error(h);
 }

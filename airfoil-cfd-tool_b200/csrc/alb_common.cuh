@@ -57,6 +57,19 @@ struct DiagAcc {
     unsigned long long surf, rev;    // number of faces, faces whose fluid cell has ux < 0
 };
 
+// Momentum-exchange bookkeeping (device).  The step that reads population buffer `parity`
+// accumulates into acc[parity]; the NEXT step's first thread commits acc[parity] to
+// ring[count % ME_RING] and clears it.  All addresses a kernel touches depend only on the parity,
+// so a pair of steps is a static CUDA graph.
+constexpr int ME_RING = ALB_ME_HISTORY + 1;
+struct MeState {
+    long long acc[2][2];
+    long long count;          // step number the next commit goes to
+    int pending;              // 1: acc[parity of the last step] is not yet in the ring
+    int pad;
+    long long ring[ME_RING][2];
+};
+
 struct StepParams {
     const float *__restrict__ src;
     float *__restrict__ dst;
@@ -80,9 +93,9 @@ struct StepParams {
     float rho_lo, rho_hi;    // Cp window (-4, 1.2) expressed as a closed rho interval
     double U0d;              // the double U0 of the JS host code
     double m2_lo, m2_hi;     // (4 U0)^2 (1 -/+ 1e-9): below -> s < 4 for sure, above -> s >= 4 for sure
-    // momentum exchange: slot of this step, slot to clear for the next one
-    long long *me_slot;
-    long long *me_next;
+    // momentum exchange (see MeState); parity = index of the source buffer
+    MeState *me;
+    int parity;
     unsigned long long *clamp_hits;
     // halo push into the neighbours' ghost rows (nullable)
     float *peer_lo_dst;      // base of the lower neighbour's DESTINATION buffer
@@ -101,8 +114,7 @@ cudaError_t launch_step_general(const StepParams &p, cudaStream_t s);
 cudaError_t launch_step_unified(const StepParams &p, cudaStream_t s);
 cudaError_t launch_macro(const StepParams &p, cudaStream_t s);
 int small_lattice_capacity(int device);
-cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps,
-                                 long long *me_ring, long long me_base, int me_ring_size, cudaStream_t s);
+cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps, cudaStream_t s);
 void host_feq0(float u0, float *out9);
 
 // alb_geometry.cu

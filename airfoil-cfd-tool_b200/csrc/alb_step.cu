@@ -206,6 +206,20 @@ __device__ __forceinline__ float4 from_right(const float4 &v, float edge, int la
 
 constexpr int MODE_STEP = 0, MODE_MACRO = 1;
 
+// first thread of a step: commit the previous step's momentum-exchange sums, clear that accumulator
+__device__ __forceinline__ void me_begin_step(MeState *m, int parity) {
+    const int prev = parity ^ 1;
+    if (m->pending) {
+        const long long c = m->count;
+        m->ring[c % ME_RING][0] = m->acc[prev][0];
+        m->ring[c % ME_RING][1] = m->acc[prev][1];
+        m->count = c + 1;
+    }
+    m->acc[prev][0] = 0;
+    m->acc[prev][1] = 0;
+    m->pending = 1;
+}
+
 // ---- fused diagnostics of the macro pass (HTML:596-614 statistics, HTML:649-700 faces) ----------
 struct DiagLocal {
     float rmin = INFINITY, rmax = -INFINITY;
@@ -317,10 +331,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, KIND == KIND_FAST ? ALB_FAST_MI
 step_kernel(const __grid_constant__ StepParams p) {
     const int lane = threadIdx.x & 31;
     int task = blockIdx.x * TASKS_PER_BLOCK + (threadIdx.x >> 5);
-    if (KIND != KIND_GENERAL && MODE == MODE_STEP && blockIdx.x == 0 && threadIdx.x == 0 && p.me_next) {
-        p.me_next[0] = 0;   // next step's accumulator; kernels of one handle run in stream order
-        p.me_next[1] = 0;
-    }
+    if (KIND != KIND_GENERAL && MODE == MODE_STEP && blockIdx.x == 0 && threadIdx.x == 0 && p.me)
+        me_begin_step(p.me, p.parity);   // the previous step of this handle has completed (stream order)
     constexpr bool from_list = KIND == KIND_GENERAL;
     if (from_list) {
         if (task >= p.ngen) return;
@@ -542,7 +554,7 @@ step_kernel(const __grid_constant__ StepParams p) {
             st4(p.peer_lo_dst + 8 * p.peer_lo_plane + p.peer_lo_row + x0, o[8]);
         }
 
-        if (GENERAL && p.me_slot) {
+        if (GENERAL && p.me) {
             // integer sums are exact and order independent: shuffle tree, one atomic per warp
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
@@ -550,8 +562,9 @@ step_kernel(const __grid_constant__ StepParams p) {
                 me_fy += __shfl_xor_sync(FULL, me_fy, d);
             }
             if (lane == 0) {
-                if (me_fx) atomicAdd(reinterpret_cast<unsigned long long *>(p.me_slot), (unsigned long long)me_fx);
-                if (me_fy) atomicAdd(reinterpret_cast<unsigned long long *>(p.me_slot + 1), (unsigned long long)me_fy);
+                long long *acc = p.me->acc[p.parity];
+                if (me_fx) atomicAdd(reinterpret_cast<unsigned long long *>(acc), (unsigned long long)me_fx);
+                if (me_fy) atomicAdd(reinterpret_cast<unsigned long long *>(acc + 1), (unsigned long long)me_fy);
             }
         }
         if (hits && p.clamp_hits) atomicAdd(p.clamp_hits, (unsigned long long)hits);
@@ -573,8 +586,7 @@ step_kernel(const __grid_constant__ StepParams p) {
 // batch of steps inside one launch with a grid-wide barrier between steps.  The arithmetic is the
 // same moments_clamped()/collide() as the streaming kernels -> bit-identical results.
 __global__ void __launch_bounds__(BLOCK_THREADS)
-small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, int cur, int nsteps,
-                     long long *me_ring, long long me_base, int me_ring_size) {
+small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, int cur, int nsteps) {
     cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31;
     const int tid = blockIdx.x * BLOCK_THREADS + threadIdx.x;
@@ -595,12 +607,9 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
         const float *src = ((cur + s) & 1) ? f1 : f0;
         float *dst = ((cur + s) & 1) ? f0 : f1;
         [[maybe_unused]] float *const dst_base = dst;
-        long long *slot = me_ring + 2 * ((me_base + s) % me_ring_size);
-        if (tid == 0) {
-            long long *next = me_ring + 2 * ((me_base + s + 1) % me_ring_size);
-            next[0] = 0;
-            next[1] = 0;
-        }
+        const int parity = (cur + s) & 1;
+        long long *slot = p.me->acc[parity];
+        if (tid == 0) me_begin_step(p.me, parity);   // acc[parity] was cleared one step (one barrier) ago
         long long me_fx = 0, me_fy = 0;
         bool hit = false;
         if (active) {
@@ -684,12 +693,11 @@ int small_lattice_capacity(int device) {
     return sms * per_sm * BLOCK_THREADS;
 }
 
-cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps,
-                                 long long *me_ring, long long me_base, int me_ring_size, cudaStream_t s) {
+cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps, cudaStream_t s) {
     const int ncell = p.nx * p.nyl;
     const int nblocks = (ncell + BLOCK_THREADS - 1) / BLOCK_THREADS;
     StepParams pp = p;
-    void *args[] = {&pp, &f0, &f1, &cur, &nsteps, &me_ring, &me_base, &me_ring_size};
+    void *args[] = {&pp, &f0, &f1, &cur, &nsteps};
     return cudaLaunchCooperativeKernel((const void *)small_lattice_kernel, dim3(nblocks), dim3(BLOCK_THREADS), args, 0, s);
 }
 
