@@ -39,6 +39,7 @@ EXPORTS = [
     "alb_compute_forces", "alb_forces_partial", "alb_reset_force_emas",
     "alb_get_me_history", "alb_get_me_forces", "alb_clamp_hits",
     "alb_reynolds", "alb_stall_state",
+    "alb_particles_init", "alb_particles_resize", "alb_particles_step", "alb_particles_get",
     "alb_connect_local", "alb_ipc_export", "alb_ipc_connect", "alb_halo_prime", "alb_halo_ptrs",
     "alb_set_external_halo",
 ]
@@ -112,6 +113,10 @@ def lib():
     L.alb_clamp_hits.argtypes = [H, C.POINTER(C.c_longlong)]
     L.alb_reynolds.argtypes = [H, dp]
     L.alb_stall_state.argtypes = [H, ip, ip]
+    L.alb_particles_init.argtypes = [H, C.c_int, C.c_ulonglong]
+    L.alb_particles_resize.argtypes = [H, C.c_int]
+    L.alb_particles_step.argtypes = [H, C.c_double]
+    L.alb_particles_get.argtypes = [H, vp, ip]
     L.alb_connect_local.argtypes = [H, H, H]
     L.alb_ipc_export.argtypes = [H, vp]
     L.alb_ipc_connect.argtypes = [H, vp, vp]

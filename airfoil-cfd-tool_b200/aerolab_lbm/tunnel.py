@@ -315,6 +315,31 @@ class WindTunnel:
             return f"{pct.value}% sep"
         return f"STALL ≈ {pct.value}% sep"
 
+    # -- tracer particles (HTML:721-808) -------------------------------------------
+    def init_particles(self, n: int = 2600, seed: int = 0):
+        """``initParts`` with NPART = n (page default 2600)."""
+        self._ck(self._lib.alb_particles_init(self._h, int(n), int(seed)))
+        return self
+
+    def resize_particles(self, n: int):
+        """The trail-count slider (HTML:961-967)."""
+        self._ck(self._lib.alb_particles_resize(self._h, int(n)))
+        return self
+
+    def step_particles(self, dt_ms: float = 16.0):
+        """``stepParticles(dt)`` on the current macroscopic fields."""
+        self._ck(self._lib.alb_particles_step(self._h, float(dt_ms)))
+        return self
+
+    def particles(self) -> np.ndarray:
+        """(n, 8) float64: x, y, life, lane, x0, y0, speed/U0, respawned."""
+        n = C.c_int()
+        self._ck(self._lib.alb_particles_get(self._h, None, C.byref(n)))
+        out = np.zeros((n.value, 8))
+        if n.value:
+            self._ck(self._lib.alb_particles_get(self._h, ptr(out), C.byref(n)))
+        return out
+
     # -- multi-GPU y-slabs (one-row population halo) -----------------------------
     def connect_local(self, lo: "Optional[WindTunnel]", hi: "Optional[WindTunnel]"):
         """Neighbouring slabs driven by the same process (lo = below, hi = above)."""

@@ -87,6 +87,10 @@ struct alb_handle {
     bool ema_valid = false;
     double cl_smooth = 0, cd_smooth = 0, sep_frac = 0;
     Peer lo, hi;
+    ParticleState *parts = nullptr;
+    unsigned *part_ctr = nullptr;
+    int nparts = 0, parts_cap = 0;
+    unsigned long long part_seed = 0;
     bool external_halo = false;
     bool use_graph = true;        // replay step batches as a CUDA graph when nothing per-step is dynamic
     int *h_err = nullptr;         // mapped pinned: set by a wait kernel that timed out
@@ -337,6 +341,8 @@ void free_handle(alb_handle *h) {
     cudaFree(h->gen_list);
     cudaFree(h->gen_count);
     cudaFree(h->me);
+    cudaFree(h->parts);
+    cudaFree(h->part_ctr);
     if (h->graph) cudaGraphExecDestroy(h->graph);
     cudaFree(h->clamp_hits);
     cudaFree(h->d_xp);
@@ -1022,6 +1028,87 @@ int alb_stall_state(const alb_handle *h, int *state, int *sep_pct) {
     if (sep_pct) *sep_pct = pct;
     if (state) *state = pct < 5 ? 0 : (pct < 25 ? 1 : 2);  // HTML:872-884
     return ALB_OK;
+}
+
+/* ---- tracer particles -------------------------------------------------------- */
+
+static int particles_reserve(alb_handle *h, int n) {
+    if (n <= h->parts_cap) return ALB_OK;
+    ParticleState *np = nullptr;
+    unsigned *nc = nullptr;
+    CK(cudaMalloc(&np, sizeof(ParticleState) * n));
+    CK(cudaMalloc(&nc, sizeof(unsigned) * n));
+    if (h->nparts > 0) {
+        CK(cudaMemcpyAsync(np, h->parts, sizeof(ParticleState) * h->nparts, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(nc, h->part_ctr, sizeof(unsigned) * h->nparts, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    cudaFree(h->parts);
+    cudaFree(h->part_ctr);
+    h->parts = np;
+    h->part_ctr = nc;
+    h->parts_cap = n;
+    return ALB_OK;
+}
+
+int alb_particles_init(alb_handle *h, int n, unsigned long long seed) {
+    NEED(h);
+    ARG(n >= 0 && n <= ALB_MAX_PARTICLES, "alb_particles_init: need 0 <= n <= ALB_MAX_PARTICLES");
+    if (!h->whole()) return h->fail(ALB_ERR_STATE, "particles need a whole-lattice handle");
+    h->nparts = 0;
+    int r = particles_reserve(h, n);
+    if (r) return r;
+    h->part_seed = seed;
+    CK(launch_particles_init(h->parts, h->part_ctr, 0, n, n, seed, 0, h->stream));
+    h->nparts = n;
+    return ALB_OK;
+}
+
+int alb_particles_resize(alb_handle *h, int n) {
+    NEED(h);
+    ARG(n >= 0 && n <= ALB_MAX_PARTICLES, "alb_particles_resize: need 0 <= n <= ALB_MAX_PARTICLES");
+    if (!h->whole()) return h->fail(ALB_ERR_STATE, "particles need a whole-lattice handle");
+    if (n > h->nparts) {
+        int r = particles_reserve(h, n);
+        if (r) return r;
+        CK(launch_particles_init(h->parts, h->part_ctr, h->nparts, n, n, h->part_seed, 1, h->stream));
+    }
+    h->nparts = n;
+    return ALB_OK;
+}
+
+int alb_particles_step(alb_handle *h, double dt_ms) {
+    NEED(h);
+    ARG(isfinite(dt_ms), "alb_particles_step: dt must be finite");
+    if (!h->whole()) return h->fail(ALB_ERR_STATE, "particles need a whole-lattice handle");
+    int r = ensure_macro(h);
+    if (r) return r;
+    CK(launch_particles_step(h->parts, h->part_ctr, h->nparts, h->part_seed, dt_ms, h->mask, h->ux, h->uy, h->pitch,
+                             h->nx, h->nyl, h->u0, h->stream));
+    return ALB_OK;
+}
+
+int alb_particles_get(alb_handle *h, double *out8, int *n) {
+    NEED(h);
+    if (n) *n = h->nparts;
+    if (out8 && h->nparts > 0) {
+        static_assert(sizeof(ParticleState) == 8 * sizeof(double), "ParticleState must be 8 doubles wide");
+        std::vector<ParticleState> tmp;
+        try {
+            tmp.resize(h->nparts);
+        } catch (const std::bad_alloc &) {
+            return h->fail(ALB_ERR_NOMEM, "alb_particles_get: host allocation failed");
+        }
+        CK(cudaMemcpyAsync(tmp.data(), h->parts, sizeof(ParticleState) * h->nparts, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < h->nparts; i++) {
+            const ParticleState &p = tmp[i];
+            double *o = out8 + 8 * (size_t)i;
+            o[0] = p.x; o[1] = p.y; o[2] = p.life; o[3] = p.lane; o[4] = p.x0; o[5] = p.y0; o[6] = p.speed;
+            o[7] = (double)p.respawned;
+        }
+    }
+    return check_wait_error(h);
 }
 
 /* ---- multi-GPU y-slabs ------------------------------------------------------ */

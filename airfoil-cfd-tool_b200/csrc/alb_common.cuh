@@ -108,6 +108,19 @@ struct StepParams {
 
 struct Handle;
 
+// alb_particles.cu -- one tracer (HTML:730-736): position, remaining life, home lane; plus the
+// segment of the last step (x0,y0 -> x,y) and its speed for whoever draws the trails
+struct ParticleState {
+    double x, y, life, lane;
+    double x0, y0, speed;
+    int respawned, pad;
+};
+cudaError_t launch_particles_init(ParticleState *ps, unsigned *ctrs, int first, int n, int npart_total,
+                                  unsigned long long seed, int slider_push, cudaStream_t s);
+cudaError_t launch_particles_step(ParticleState *ps, unsigned *ctrs, int n, unsigned long long seed, double dt,
+                                  const uint8_t *mask, const float *ux, const float *uy, int pitch, int nx, int ny,
+                                  double U0, cudaStream_t s);
+
 // alb_step.cu
 cudaError_t launch_step_fast(const StepParams &p, cudaStream_t s);
 cudaError_t launch_step_general(const StepParams &p, cudaStream_t s);

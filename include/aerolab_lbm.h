@@ -175,6 +175,21 @@ int alb_reynolds(const alb_handle *h, double *re);
  * (<25 %), 2 "STALL"; *sep_pct = round(100*sep_frac). */
 int alb_stall_state(const alb_handle *h, int *state, int *sep_pct);
 
+/* ---- tracer particles: initParts/spawn/advect/stepParticles, HTML:721-808 ---
+ * Whole-lattice handles only.  Math.random() is replaced by a counter-based
+ * generator keyed by (seed, particle, draw), so runs are reproducible. */
+#define ALB_MAX_PARTICLES 1000000
+/* initParts() with NPART = n (page default 2600, slider 800..5000). */
+int alb_particles_init(alb_handle *h, int n, unsigned long long seed);
+/* The trail-count slider (HTML:961-967): drop from the end or push spawn(false). */
+int alb_particles_resize(alb_handle *h, int n);
+/* stepParticles(dt) on the current macroscopic fields; dt in milliseconds
+ * (the page passes min(frame time, 40), 16 on the first frame; HTML:903). */
+int alb_particles_step(alb_handle *h, double dt_ms);
+/* out: n rows of {x, y, life, lane, x0, y0, speed, respawned}: the segment
+ * (x0,y0)->(x,y) is what the page strokes, speed is in units of U0. */
+int alb_particles_get(alb_handle *h, double *out8, int *n);
+
 /* ---- multi-GPU y-slabs: one-row population halo over NVLink ---------------- */
 
 /* In-process neighbours (several slabs driven by one process). lo = the slab
