@@ -55,7 +55,8 @@ struct alb_handle {
     bool macro_valid = true;
     bool diag_valid = false;      // h_diag holds the fused statistics/forces of the current state
     DiagAcc *d_diag = nullptr;
-    DiagAcc *h_diag = nullptr;    // pinned
+    DiagAcc *h_diag = nullptr;    // pinned: results
+    DiagAcc *h_diag_init = nullptr;   // pinned: the constant initial value (zero sums, +/-inf extrema)
     double thr_u0 = -1;           // U0 the cached thresholds below were derived for
     float rho_lo = 0, rho_hi = 0;
     double m2_lo = -1, m2_hi = -1;
@@ -239,24 +240,23 @@ void refresh_thresholds(alb_handle *h) {
     h->m2_hi = cut * (1 + 1e-9);
 }
 
-// One pass over the previous state that yields the autoscale statistics (HTML:596-614) and the
-// pressure-face sums (HTML:649-700) of the current state, optionally also storing rho/ux/uy.
-int run_macro_pass(alb_handle *h, bool write_macro) {
+void arm_diag(alb_handle *h, StepParams &p) {
     refresh_thresholds(h);
-    DiagAcc init;
-    memset(&init, 0, sizeof init);
-    init.rho_min = INFINITY;
-    init.rho_max = -INFINITY;
-    *h->h_diag = init;
-    CK(cudaMemcpyAsync(h->d_diag, h->h_diag, sizeof(DiagAcc), cudaMemcpyHostToDevice, h->stream));
-    StepParams p = make_params(h, 1 - h->cur);
-    p.write_macro = write_macro ? 1 : 0;
     p.diag = h->d_diag;
     p.rho_lo = h->rho_lo;
     p.rho_hi = h->rho_hi;
     p.U0d = h->u0;
     p.m2_lo = h->m2_lo;
     p.m2_hi = h->m2_hi;
+}
+
+// One pass over the previous state that yields the autoscale statistics (HTML:596-614) and the
+// pressure-face sums (HTML:649-700) of the current state, optionally also storing rho/ux/uy.
+int run_macro_pass(alb_handle *h, bool write_macro) {
+    CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc), cudaMemcpyHostToDevice, h->stream));
+    StepParams p = make_params(h, 1 - h->cur);
+    p.write_macro = write_macro ? 1 : 0;
+    arm_diag(h, p);
     CK(launch_macro(p, h->stream));
     CK(cudaMemcpyAsync(h->h_diag, h->d_diag, sizeof(DiagAcc), cudaMemcpyDeviceToHost, h->stream));
     if (write_macro) h->macro_valid = true;
@@ -352,6 +352,7 @@ void free_handle(alb_handle *h) {
     if (h->h_part) cudaFreeHost(h->h_part);
     if (h->h_err) cudaFreeHost(h->h_err);
     if (h->h_diag) cudaFreeHost(h->h_diag);
+    if (h->h_diag_init) cudaFreeHost(h->h_diag_init);
     cudaFree(h->d_diag);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -461,6 +462,10 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaHostAlloc(&h->h_part, sizeof(double) * 4 * DIAG_BLOCKS, cudaHostAllocDefault));
         CK(cudaMalloc(&h->d_diag, sizeof(DiagAcc)));
         CK(cudaHostAlloc(&h->h_diag, sizeof(DiagAcc), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&h->h_diag_init, sizeof(DiagAcc), cudaHostAllocDefault));
+        memset(h->h_diag_init, 0, sizeof(DiagAcc));
+        h->h_diag_init->rho_min = INFINITY;
+        h->h_diag_init->rho_max = -INFINITY;
         CK(cudaHostAlloc(&h->h_err, sizeof(int), cudaHostAllocMapped));
         *h->h_err = 0;
         CK(cudaHostGetDevicePointer(&h->d_err, h->h_err, 0));
@@ -601,8 +606,13 @@ int alb_get_panels(const alb_handle *h, double *xp, double *yp) {
 namespace {
 
 // Enqueue one step that reads buffer src_idx.  Used directly and under stream capture.
-int issue_step(alb_handle *h, int src_idx, bool halo, long long sync_step) {
+int issue_step(alb_handle *h, int src_idx, bool halo, long long sync_step, bool diag) {
     StepParams p = make_params(h, src_idx);
+    if (diag) {
+        // the last step of a batch also reduces the statistics / face sums of the state it writes
+        CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc), cudaMemcpyHostToDevice, h->stream));
+        arm_diag(h, p);
+    }
     if (halo) {
         // my step k needs the neighbours' k completed steps: their edge rows of state k are in
         // my ghost rows, and they no longer read the ghost rows I am about to overwrite.
@@ -650,7 +660,7 @@ int capture_graph(alb_handle *h) {
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     int r = ALB_OK;
-    for (int s = 0; s < GRAPH_STEPS && r == ALB_OK; s++) r = issue_step(h, s & 1, false, 0);
+    for (int s = 0; s < GRAPH_STEPS && r == ALB_OK; s++) r = issue_step(h, s & 1, false, 0, false);
     cudaError_t e = cudaStreamEndCapture(h->stream, &g);
     if (r != ALB_OK) {
         if (g) cudaGraphDestroy(g);
@@ -680,16 +690,20 @@ int alb_step(alb_handle *h, int nsteps) {
     const bool persistent = h->whole() && !halo && !h->external_halo && nsteps >= 2 &&
                             (long long)h->nx * h->nyl <= h->small_capacity;
     if (persistent) {
-        // small lattice: the whole batch of steps in ONE cooperative launch (grid barrier per step)
+        // small lattice: the whole batch of steps in ONE cooperative launch (grid barrier per
+        // step); its last iteration also reduces the statistics / face sums of the final state
+        // (measured: as fast as a kernel without that code, and no extra launch)
         StepParams p = make_params(h, h->cur);
+        CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc), cudaMemcpyHostToDevice, h->stream));
+        arm_diag(h, p);
         CK(launch_small_lattice(p, h->f[0], h->f[1], h->cur, nsteps, h->stream));
         h->cur = (h->cur + nsteps) & 1;
         left = 0;
     }
     const bool use_graph = !persistent && !halo && !h->external_halo && h->use_graph && nsteps >= GRAPH_STEPS + 1;
-    int done = 0;
+    int done = nsteps - left;
     while (left > 0) {
-        if (use_graph && h->cur == 0 && left >= GRAPH_STEPS) {
+        if (use_graph && h->cur == 0 && left > GRAPH_STEPS) {   // ">": the last step is issued below, with diagnostics
             if (!h->graph) {
                 int r = capture_graph(h);
                 if (r) return r;
@@ -699,7 +713,7 @@ int alb_step(alb_handle *h, int nsteps) {
             done += GRAPH_STEPS;
             continue;
         }
-        int r = issue_step(h, h->cur, halo, h->sync_steps + done);
+        int r = issue_step(h, h->cur, halo, h->sync_steps + done, left == 1);
         if (r) return r;
         h->cur = 1 - h->cur;
         left--;
@@ -709,9 +723,10 @@ int alb_step(alb_handle *h, int nsteps) {
     h->sync_steps += nsteps;
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaMemcpyAsync(h->h_diag, h->d_diag, sizeof(DiagAcc), cudaMemcpyDeviceToHost, h->stream));
     h->timed = true;
     h->macro_valid = false;
-    h->diag_valid = false;
+    h->diag_valid = true;       // the last step reduced the new state's statistics and face sums
     return ALB_OK;
 }
 

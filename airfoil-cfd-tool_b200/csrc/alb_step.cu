@@ -326,7 +326,9 @@ __device__ __forceinline__ void diag_flush(const StepParams &p, DiagLocal &d, in
 // occupancy is irrelevant.
 constexpr int KIND_FAST = 0, KIND_GENERAL = 1, KIND_UNIFIED = 2;
 
-template <int MODE, int KIND>
+// DIAG (step mode): also accumulate the autoscale statistics and pressure-face sums of the state
+// being WRITTEN (its rho/ux/uy are computed here anyway) -- used for the last step of a batch.
+template <int MODE, int KIND, bool DIAG = false>
 __global__ void __launch_bounds__(BLOCK_THREADS, KIND == KIND_FAST ? ALB_FAST_MINBLOCKS : 2)
 step_kernel(const __grid_constant__ StepParams p) {
     const int lane = threadIdx.x & 31;
@@ -360,6 +362,11 @@ step_kernel(const __grid_constant__ StepParams p) {
             for (int i = 0; i < 9; i++) {
                 const float v = p.feq0[i];
                 ST4(p.dst + i * plane + c, make_float4(v, v, v, v));
+            }
+            if (DIAG) {   // 128 identical border cells (1, U0, 0), none of them next to a solid
+                DiagLocal d;
+                if (lane == 0) diag_cell(p, d, 1.0f, p.u0, 0.0f);
+                diag_flush(p, d, lane);
             }
         } else {
             if (p.write_macro) {
@@ -445,7 +452,7 @@ step_kernel(const __grid_constant__ StepParams p) {
     long long me_fx = 0, me_fy = 0;
     unsigned hits = 0;
     DiagLocal dl;
-    const bool want_diag = MODE == MODE_MACRO && p.diag != nullptr;
+    const bool want_diag = (MODE == MODE_MACRO && p.diag != nullptr) || (MODE == MODE_STEP && DIAG);
 
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -554,6 +561,7 @@ step_kernel(const __grid_constant__ StepParams p) {
             st4(p.peer_lo_dst + 8 * p.peer_lo_plane + p.peer_lo_row + x0, o[8]);
         }
 
+        if (DIAG) diag_flush(p, dl, lane);
         if (GENERAL && p.me) {
             // integer sums are exact and order independent: shuffle tree, one atomic per warp
 #pragma unroll
@@ -585,6 +593,7 @@ step_kernel(const __grid_constant__ StepParams p) {
 // by HBM.  So: one thread per cell (shortest chain, most warps), all CTAs co-resident, the whole
 // batch of steps inside one launch with a grid-wide barrier between steps.  The arithmetic is the
 // same moments_clamped()/collide() as the streaming kernels -> bit-identical results.
+// The last step of the batch also reduces the statistics / face sums of the final state (p.diag).
 __global__ void __launch_bounds__(BLOCK_THREADS)
 small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, int cur, int nsteps) {
     cg::grid_group grid = cg::this_grid();
@@ -612,8 +621,11 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
         if (tid == 0) me_begin_step(p.me, parity);   // acc[parity] was cleared one step (one barrier) ago
         long long me_fx = 0, me_fy = 0;
         bool hit = false;
+        const bool diag_now = p.diag != nullptr && s == nsteps - 1;   // statistics of the final state
+        DiagLocal dl;
         if (active) {
             float f[9];
+            float rho = 1.0f, ux = p.u0, uy = 0.0f;                    // equilibrium border values
             if (type == CT_FLUID) {
 #pragma unroll
                 for (int i = 0; i < 9; i++) {
@@ -630,19 +642,26 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
                 const Moments m = moments_clamped(f);
                 collide(f, m, p.tau, p.inv_tau);
                 hit = m.hit;
+                rho = m.rho; ux = m.ux; uy = m.uy;
             } else if (type == CT_SOLID) {
 #pragma unroll
                 for (int i = 0; i < 9; i++) f[i] = LD1CG(src + opp[i] * plane + c);
             } else if (type == CT_OUTLET) {
 #pragma unroll
                 for (int i = 0; i < 9; i++) f[i] = LD1CG(src + i * plane + c - 1);
+                if (diag_now) moments_plain(f, rho, ux, uy);
             } else {
 #pragma unroll
                 for (int i = 0; i < 9; i++) f[i] = p.feq0[i];
             }
 #pragma unroll
             for (int i = 0; i < 9; i++) { ALB_CHECK_DST(dst + i * plane + c, 1); dst[i * plane + c] = f[i]; }
+            if (diag_now && type != CT_SOLID && !(info & INFO_PAD)) {
+                diag_cell(p, dl, rho, ux, uy);
+                diag_faces(dl, info & 0xffu, rho, ux);
+            }
         }
+        if (diag_now) diag_flush(p, dl, lane);
         if (__any_sync(FULL, links != 0)) {
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
@@ -665,20 +684,23 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
 // disjoint cells, so the caller may run them concurrently on two streams.
 cudaError_t launch_step_fast(const StepParams &p, cudaStream_t s) {
     const int nblocks = (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
-    step_kernel<MODE_STEP, KIND_FAST><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    if (p.diag) step_kernel<MODE_STEP, KIND_FAST, true><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    else step_kernel<MODE_STEP, KIND_FAST><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_step_general(const StepParams &p, cudaStream_t s) {
     if (p.ngen == 0) return cudaSuccess;
     const int gblocks = (p.ngen + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
-    step_kernel<MODE_STEP, KIND_GENERAL><<<gblocks, BLOCK_THREADS, 0, s>>>(p);
+    if (p.diag) step_kernel<MODE_STEP, KIND_GENERAL, true><<<gblocks, BLOCK_THREADS, 0, s>>>(p);
+    else step_kernel<MODE_STEP, KIND_GENERAL><<<gblocks, BLOCK_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_step_unified(const StepParams &p, cudaStream_t s) {
     const int nblocks = (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
-    step_kernel<MODE_STEP, KIND_UNIFIED><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    if (p.diag) step_kernel<MODE_STEP, KIND_UNIFIED, true><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    else step_kernel<MODE_STEP, KIND_UNIFIED><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -275,6 +275,25 @@ def main():
     wall_ms = comm.max_float(wall_ms)
     glups = cells_global * args.steps / (ms_dev * 1e-3) / 1e9
 
+    # same-box calibration of the denominator: a plain device copy (what MEASURED_PEAKS.json holds)
+    copy_here = None
+    if rank == 0 and world == 1:
+        try:
+            a = torch.empty(1 << 30, dtype=torch.bfloat16, device=f"cuda:{local_rank}")
+            b = torch.empty_like(a)
+            best = 1e9
+            for _ in range(6):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                b.copy_(a)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            copy_here = 2 * a.numel() * 2 / (best * 1e-3) / 1e9
+            del a, b
+        except Exception:
+            copy_here = None
+
     # roofline of the dominant kernel: per launch, this rank's cells
     peak, peak_src = measured_peak()
     cells_local = nx * tun.ny_local
@@ -282,6 +301,7 @@ def main():
     achieved = BYTES_PER_LUP * cells_local / (launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": committed_traffic(args.workload), "peak_source": peak_src,
+                "copy_gbs_measured_in_this_run": copy_here,
                 "kernel": "alb::step_kernel<MODE_STEP>",
                 "algorithmic_bytes_per_launch": BYTES_PER_LUP * cells_local}
 
