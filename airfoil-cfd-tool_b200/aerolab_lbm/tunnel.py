@@ -55,7 +55,6 @@ class WindTunnel:
         self.name = ""
         self.coords: Optional[np.ndarray] = None
         self.alpha = DEFAULT_ALPHA
-        self._frame_counter = 0
         if u0 != DEFAULT_U0 or tau != DEFAULT_TAU:
             self.reset(u0)
             self.set_tau(tau)
@@ -171,7 +170,6 @@ class WindTunnel:
         """``initSim`` (HTML:492-500)."""
         self._ck(self._lib.alb_reset(self._h, float(self.params()[0] if u0 is None else u0)))
         self._lib.alb_reset_force_emas(self._h)
-        self._frame_counter = 0
         return self
 
     # -- stepping ---------------------------------------------------------------
@@ -388,17 +386,40 @@ class WindTunnel:
         return self
 
     # -- the reference's frame loop ---------------------------------------------
+    FRAME_COLUMNS = ("CL", "CD", "sep_frac", "CL_raw", "CD_raw", "surf", "rev", "maxS", "cpMin", "cpMax",
+                     "CL_me", "CD_me")
+
+    def run_frames(self, nframes: int, controls=None, steps_per_frame: int = STEPS_PER_FRAME,
+                   forces_every: int = FORCES_EVERY_FRAMES) -> dict:
+        """``frame()`` x nframes (HTML:902-930) without host synchronisation inside the loop.
+
+        ``controls``: optional (nframes, 2) array of (U0, tau) per frame (the sliders).  Returns a
+        dict of per-frame arrays, see ``FRAME_COLUMNS``: EMA-smoothed CL/CD and the separation
+        fraction (updated every ``forces_every``-th frame, as on the page), raw coefficients (NaN
+        on the other frames), autoscale values, momentum-exchange coefficients."""
+        ctrl = None
+        if controls is not None:
+            ctrl = np.ascontiguousarray(controls, dtype=np.float64).reshape(int(nframes), 2)
+        series = np.empty((int(nframes), _ffi.ALB_FRAME_ROW))
+        self._ck(self._lib.alb_run_frames(self._h, int(nframes), int(steps_per_frame), int(forces_every),
+                                          ptr(ctrl), ptr(series)))
+        return {k: series[:, i] for i, k in enumerate(self.FRAME_COLUMNS)}
+
     def frame(self, want_field: Optional[str] = None) -> dict:
-        """One animation frame (HTML:902-930): 4 steps, render with the previous
-        frame's autoscale, refresh the autoscale, forces every 3rd frame."""
-        self.step(STEPS_PER_FRAME)
-        out = {}
+        """One animation frame (HTML:902-930): 4 steps, render with the previous frame's
+        autoscale, refresh the autoscale, forces every 3rd frame."""
+        prev = self.stats()
+        s = self.run_frames(1)
+        out = {"stats": dict(maxS=s["maxS"][0], cpMin=s["cpMin"][0], cpMax=s["cpMax"][0])}
         if want_field is not None:
+            # the page renders BEFORE updateFieldsFromMacro (HTML:909-911)
+            self.set_stats(prev["maxS"], prev["cpMin"], prev["cpMax"])
             out["field"] = self.field(want_field)
-        out["stats"] = self.update_stats()
-        self._frame_counter += 1
-        if self._frame_counter % FORCES_EVERY_FRAMES == 0:
-            out["forces"] = self.forces()
+            self.set_stats(**{k: out["stats"][v] for k, v in (("max_s", "maxS"), ("cp_min", "cpMin"), ("cp_max", "cpMax"))})
+        if not np.isnan(s["surf"][0]):
+            out["forces"] = dict(CL=s["CL"][0], CD=s["CD"][0], CL_raw=s["CL_raw"][0], CD_raw=s["CD_raw"][0],
+                                 sep_frac=s["sep_frac"][0], surf=int(s["surf"][0]), rev=int(s["rev"][0]),
+                                 any=bool(s["surf"][0] > 0), CL_me=s["CL_me"][0], CD_me=s["CD_me"][0])
         return out
 
     def save_png(self, path: Optional[str] = None, mode="speed") -> str:

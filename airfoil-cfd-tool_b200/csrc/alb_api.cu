@@ -55,6 +55,9 @@ struct alb_handle {
     bool macro_valid = true;
     bool diag_valid = false;      // h_diag holds the fused statistics/forces of the current state
     DiagAcc *d_diag = nullptr;
+    DiagAcc *d_diag_pub = nullptr;    // copy published by the frame-finalize kernel
+    int diag_slots_host = 0;          // how many slots of h_diag the last copy filled (merged on read)
+    bool diag_prearmed = false;       // d_diag was re-armed on the device: skip the next init copy
     DiagAcc *h_diag = nullptr;    // pinned: results
     DiagAcc *h_diag_init = nullptr;   // pinned: the constant initial value (zero sums, +/-inf extrema)
     double thr_u0 = -1;           // U0 the cached thresholds below were derived for
@@ -88,6 +91,10 @@ struct alb_handle {
     bool ema_valid = false;
     double cl_smooth = 0, cd_smooth = 0, sep_frac = 0;
     Peer lo, hi;
+    FrameDev *d_frame = nullptr, *h_frame = nullptr;   // device state of the frame loop + pinned staging
+    double *d_rows = nullptr, *h_rows = nullptr;      // per-frame records (device, pinned host)
+    int rows_cap = 0;
+    long long frame_counter = 0;                      // statCounter, HTML:594, 913
     ParticleState *parts = nullptr;
     unsigned *part_ctr = nullptr;
     int nparts = 0, parts_cap = 0;
@@ -248,17 +255,20 @@ void arm_diag(alb_handle *h, StepParams &p) {
     p.U0d = h->u0;
     p.m2_lo = h->m2_lo;
     p.m2_hi = h->m2_hi;
+    p.m2f_cap = (float)(h->m2_hi * (1 + 1e-5));
 }
 
 // One pass over the previous state that yields the autoscale statistics (HTML:596-614) and the
 // pressure-face sums (HTML:649-700) of the current state, optionally also storing rho/ux/uy.
 int run_macro_pass(alb_handle *h, bool write_macro) {
-    CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc) * DIAG_SLOTS, cudaMemcpyHostToDevice, h->stream));
+    h->diag_prearmed = false;
     StepParams p = make_params(h, 1 - h->cur);
     p.write_macro = write_macro ? 1 : 0;
     arm_diag(h, p);
     CK(launch_macro(p, h->stream));
-    CK(cudaMemcpyAsync(h->h_diag, h->d_diag, sizeof(DiagAcc), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_diag, h->d_diag, sizeof(DiagAcc) * DIAG_SLOTS, cudaMemcpyDeviceToHost, h->stream));
+    h->diag_slots_host = DIAG_SLOTS;
     if (write_macro) h->macro_valid = true;
     h->diag_valid = true;     // h_diag is readable after the next stream synchronisation
     return ALB_OK;
@@ -305,6 +315,7 @@ int do_reset(alb_handle *h, double u0) {
     CK(cudaMemsetAsync(h->clamp_hits, 0, sizeof(unsigned long long), h->stream));
     h->cur = 0;
     h->steps = 0;
+    h->frame_counter = 0;
     h->macro_valid = true;
     h->diag_valid = false;
     return ALB_OK;
@@ -342,6 +353,9 @@ void free_handle(alb_handle *h) {
     cudaFree(h->gen_count);
     cudaFree(h->me);
     cudaFree(h->parts);
+    cudaFree(h->d_frame);
+    if (h->h_frame) cudaFreeHost(h->h_frame);
+    if (h->h_rows) cudaFreeHost(h->h_rows);
     cudaFree(h->part_ctr);
     if (h->graph) cudaGraphExecDestroy(h->graph);
     cudaFree(h->clamp_hits);
@@ -354,6 +368,7 @@ void free_handle(alb_handle *h) {
     if (h->h_diag) cudaFreeHost(h->h_diag);
     if (h->h_diag_init) cudaFreeHost(h->h_diag_init);
     cudaFree(h->d_diag);
+    cudaFree(h->d_diag_pub);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -407,6 +422,7 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         g_create_error = "alb_create: need 3 <= nx <= 2^24, 3 <= ny <= 65000, 0 <= y0, y0 + ny_local <= ny";
         return ALB_ERR_INVALID;
     }
+    cudaGetLastError();   // do not inherit a stale error from unrelated earlier CUDA calls of the process
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -460,12 +476,17 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaMalloc(&h->d_yp, sizeof(double) * 1024));
         CK(cudaMalloc(&h->d_part, sizeof(double) * 4 * DIAG_BLOCKS));
         CK(cudaHostAlloc(&h->h_part, sizeof(double) * 4 * DIAG_BLOCKS, cudaHostAllocDefault));
-        CK(cudaMalloc(&h->d_diag, sizeof(DiagAcc)));
-        CK(cudaHostAlloc(&h->h_diag, sizeof(DiagAcc), cudaHostAllocDefault));
-        CK(cudaHostAlloc(&h->h_diag_init, sizeof(DiagAcc), cudaHostAllocDefault));
-        memset(h->h_diag_init, 0, sizeof(DiagAcc));
-        h->h_diag_init->rho_min = INFINITY;
-        h->h_diag_init->rho_max = -INFINITY;
+        CK(cudaMalloc(&h->d_diag, sizeof(DiagAcc) * DIAG_SLOTS));
+        CK(cudaMalloc(&h->d_diag_pub, sizeof(DiagAcc)));
+        CK(cudaHostAlloc(&h->h_diag, sizeof(DiagAcc) * DIAG_SLOTS, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&h->h_diag_init, sizeof(DiagAcc) * DIAG_SLOTS, cudaHostAllocDefault));
+        memset(h->h_diag_init, 0, sizeof(DiagAcc) * DIAG_SLOTS);
+        for (int k = 0; k < DIAG_SLOTS; k++) {
+            h->h_diag_init[k].rho_min = INFINITY;
+            h->h_diag_init[k].rho_max = -INFINITY;
+        }
+        CK(cudaMalloc(&h->d_frame, sizeof(FrameDev)));
+        CK(cudaHostAlloc(&h->h_frame, sizeof(FrameDev), cudaHostAllocDefault));
         CK(cudaHostAlloc(&h->h_err, sizeof(int), cudaHostAllocMapped));
         *h->h_err = 0;
         CK(cudaHostGetDevicePointer(&h->d_err, h->h_err, 0));
@@ -610,7 +631,9 @@ int issue_step(alb_handle *h, int src_idx, bool halo, long long sync_step, bool 
     StepParams p = make_params(h, src_idx);
     if (diag) {
         // the last step of a batch also reduces the statistics / face sums of the state it writes
-        CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc), cudaMemcpyHostToDevice, h->stream));
+        if (!h->diag_prearmed)
+            CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc) * DIAG_SLOTS, cudaMemcpyHostToDevice, h->stream));
+        h->diag_prearmed = false;
         arm_diag(h, p);
     }
     if (halo) {
@@ -680,12 +703,9 @@ int capture_graph(alb_handle *h) {
 
 extern "C" {
 
-int alb_step(alb_handle *h, int nsteps) {
-    NEED(h);
-    ARG(nsteps >= 0, "alb_step: nsteps must be >= 0");
-    if (nsteps == 0) return ALB_OK;
+// nsteps >= 1 steps; the last one also reduces the new state's statistics / face sums
+static int step_batch(alb_handle *h, int nsteps) {
     const bool halo = !h->external_halo && (h->lo.base || h->hi.base);
-    CK(cudaEventRecord(h->ev0, h->stream));
     int left = nsteps;
     const bool persistent = h->whole() && !halo && !h->external_halo && nsteps >= 2 &&
                             (long long)h->nx * h->nyl <= h->small_capacity;
@@ -694,7 +714,9 @@ int alb_step(alb_handle *h, int nsteps) {
         // step); its last iteration also reduces the statistics / face sums of the final state
         // (measured: as fast as a kernel without that code, and no extra launch)
         StepParams p = make_params(h, h->cur);
-        CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc), cudaMemcpyHostToDevice, h->stream));
+        if (!h->diag_prearmed)
+            CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc) * DIAG_SLOTS, cudaMemcpyHostToDevice, h->stream));
+        h->diag_prearmed = false;
         arm_diag(h, p);
         CK(launch_small_lattice(p, h->f[0], h->f[1], h->cur, nsteps, h->stream));
         h->cur = (h->cur + nsteps) & 1;
@@ -722,12 +744,83 @@ int alb_step(alb_handle *h, int nsteps) {
     h->steps += nsteps;
     h->sync_steps += nsteps;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev1, h->stream));
-    CK(cudaMemcpyAsync(h->h_diag, h->d_diag, sizeof(DiagAcc), cudaMemcpyDeviceToHost, h->stream));
-    h->timed = true;
     h->macro_valid = false;
     h->diag_valid = true;       // the last step reduced the new state's statistics and face sums
     return ALB_OK;
+}
+
+int alb_step(alb_handle *h, int nsteps) {
+    NEED(h);
+    ARG(nsteps >= 0, "alb_step: nsteps must be >= 0");
+    if (nsteps == 0) return ALB_OK;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    int r = step_batch(h, nsteps);
+    if (r) return r;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaMemcpyAsync(h->h_diag, h->d_diag, sizeof(DiagAcc) * DIAG_SLOTS, cudaMemcpyDeviceToHost, h->stream));
+    h->diag_slots_host = DIAG_SLOTS;
+    h->timed = true;
+    return ALB_OK;
+}
+
+int alb_run_frames(alb_handle *h, int nframes, int steps_per_frame, int forces_every, const double *controls,
+                   double *series) {
+    NEED(h);
+    ARG(nframes >= 0 && steps_per_frame >= 1, "alb_run_frames: need nframes >= 0 and steps_per_frame >= 1");
+    if (!h->whole() || h->lo.base || h->hi.base)
+        return h->fail(ALB_ERR_STATE, "alb_run_frames needs a whole-lattice handle");
+    if (nframes == 0) return ALB_OK;
+    if (controls)
+        for (int f = 0; f < 2 * nframes; f++) ARG(isfinite(controls[f]), "alb_run_frames: controls must be finite");
+    if (nframes > h->rows_cap) {
+        if (h->h_rows) cudaFreeHost(h->h_rows);
+        h->d_rows = nullptr; h->h_rows = nullptr; h->rows_cap = 0;
+        // mapped pinned memory: the finalize kernel stores each frame's record straight to the host
+        CK(cudaHostAlloc(&h->h_rows, sizeof(double) * FRAME_ROW * nframes, cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer(&h->d_rows, h->h_rows, 0));
+        h->rows_cap = nframes;
+    }
+    // sticky host state -> device
+    FrameDev st;
+    st.maxS = h->maxS; st.cpMin = h->cpMin; st.cpMax = h->cpMax;
+    st.cl_smooth = h->cl_smooth; st.cd_smooth = h->cd_smooth; st.sep_frac = h->sep_frac;
+    st.ema_valid = h->ema_valid ? 1 : 0; st.pad = 0;
+    CK(cudaStreamSynchronize(h->stream));          // h_frame may still be the target of an earlier copy
+    *h->h_frame = st;
+    CK(cudaMemcpyAsync(h->d_frame, h->h_frame, sizeof(FrameDev), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    for (int f = 0; f < nframes; f++) {
+        if (controls) {
+            const double u0 = controls[2 * f], tau = controls[2 * f + 1];
+            ARG((float)tau != 0.0f, "alb_run_frames: tau must be non-zero");
+            if (u0 != h->u0 || tau != h->tau) {
+                // slider change between frames (HTML:956-959): only the next steps see it
+                h->u0 = u0;
+                h->tau = tau;
+                drop_graph(h);
+                refresh_params(h);
+            }
+        }
+        int r = step_batch(h, steps_per_frame);
+        if (r) return r;
+        h->frame_counter++;
+        const int do_forces = forces_every > 0 && (h->frame_counter % forces_every == 0);
+        CK(launch_frame_finalize(h->d_diag, h->d_diag_pub, h->me, 1 - h->cur, h->d_frame, do_forces, h->u0,
+                                 h->qdyn(), h->d_rows + (size_t)FRAME_ROW * f, h->stream));
+        h->diag_prearmed = true;
+    }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    CK(cudaMemcpyAsync(h->h_diag, h->d_diag_pub, sizeof(DiagAcc), cudaMemcpyDeviceToHost, h->stream));
+    h->diag_slots_host = 1;
+    CK(cudaMemcpyAsync(h->h_frame, h->d_frame, sizeof(FrameDev), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const FrameDev &o = *h->h_frame;
+    h->maxS = o.maxS; h->cpMin = o.cpMin; h->cpMax = o.cpMax;
+    h->cl_smooth = o.cl_smooth; h->cd_smooth = o.cd_smooth; h->sep_frac = o.sep_frac;
+    h->ema_valid = o.ema_valid != 0;
+    if (series) memcpy(series, h->h_rows, sizeof(double) * FRAME_ROW * nframes);
+    return check_wait_error(h);
 }
 
 int alb_sync(alb_handle *h) {
@@ -815,6 +908,20 @@ int alb_total_mass(alb_handle *h, double *mass) {
     return ALB_OK;
 }
 
+// merge the accumulator copies that the last device->host copy delivered (call after a sync)
+static DiagAcc merged_diag(const alb_handle *h) {
+    DiagAcc m = h->h_diag[0];
+    for (int k = 1; k < h->diag_slots_host; k++) {
+        const DiagAcc &a = h->h_diag[k];
+        if (a.smax_bits > m.smax_bits) m.smax_bits = a.smax_bits;
+        if (a.m2max_bits > m.m2max_bits) m.m2max_bits = a.m2max_bits;
+        m.rho_min = fminf(m.rho_min, a.rho_min);
+        m.rho_max = fmaxf(m.rho_max, a.rho_max);
+        m.fx += a.fx; m.fy += a.fy; m.surf += a.surf; m.rev += a.rev;
+    }
+    return m;
+}
+
 // true when the fused pass can serve the request: the previous state is still the source of the
 // current macroscopic fields (i.e. they were not injected by reset/set_macro)
 static int fused_diag(alb_handle *h) {
@@ -835,7 +942,7 @@ int alb_stats_partial(alb_handle *h, double *out3, float *U, float *V, float *Cp
         r = fused_diag(h);
         if (r < 0) return r;
         if (r == ALB_OK) {
-            const DiagAcc &d = *h->h_diag;
+            const DiagAcc d = merged_diag(h);
             double smax;
             memcpy(&smax, &d.smax_bits, 8);
             if (out3) {
@@ -930,7 +1037,7 @@ int alb_forces_partial(alb_handle *h, double *out4) {
     if (r == ALB_OK) {
         // HTML:663-668: p = rho/3 per face; here (sum of rho)/3, exact integer sum (differs from the
         // sequential float64 sum by rounding only, ~1e-16 relative)
-        const DiagAcc &d = *h->h_diag;
+        const DiagAcc d = merged_diag(h);
         out4[0] = (double)d.fx / ALB_ME_SCALE / 3;
         out4[1] = (double)d.fy / ALB_ME_SCALE / 3;
         out4[2] = (double)d.surf;

@@ -49,7 +49,10 @@ constexpr unsigned INFO_TYPE_SHIFT = 8, INFO_TYPE_MASK = 3, INFO_PAD = 0x400;
 
 // Accumulators of one fused macroscopic/diagnostics pass (step_kernel<MODE_MACRO,*>): everything is
 // a max/min or an integer sum, so the result does not depend on the order of the atomics.
-struct DiagAcc {
+// The device keeps DIAG_SLOTS copies (warps pick one by their index) so that the pre-check loads
+// and atomics of millions of warps do not pile up on one L2 line; the copies are merged afterwards.
+constexpr int DIAG_SLOTS = 256;
+struct alignas(64) DiagAcc {
     unsigned long long smax_bits;    // double bits of max s = hypot(ux/U0, uy/U0) over cells with s < 4 (0: none)
     unsigned long long m2max_bits;   // double bits of ux^2 + uy^2 of that cell (pre-filter for the atomics)
     float rho_min, rho_max;          // over non-solid cells whose Cp lies in (-4, 1.2); +inf / -inf: none
@@ -93,6 +96,7 @@ struct StepParams {
     float rho_lo, rho_hi;    // Cp window (-4, 1.2) expressed as a closed rho interval
     double U0d;              // the double U0 of the JS host code
     double m2_lo, m2_hi;     // (4 U0)^2 (1 -/+ 1e-9): below -> s < 4 for sure, above -> s >= 4 for sure
+    float m2f_cap;           // fp32 ux^2+uy^2 above this is s >= 4 for sure (m2_hi with fp32 slack)
     // momentum exchange (see MeState); parity = index of the source buffer
     MeState *me;
     int parity;
@@ -107,6 +111,17 @@ struct StepParams {
 };
 
 struct Handle;
+
+// Device-side mirror of the page's sticky host state (autoscale values HTML:593, force EMAs
+// HTML:641), so that whole frames (HTML:902-930) can run without host synchronisation.
+struct FrameDev {
+    double maxS, cpMin, cpMax;
+    double cl_smooth, cd_smooth, sep_frac;
+    int ema_valid, pad;
+};
+constexpr int FRAME_ROW = 12;   // doubles per frame record, see alb_run_frames() in the header
+cudaError_t launch_frame_finalize(DiagAcc *d, DiagAcc *published, const MeState *me, int me_parity, FrameDev *st,
+                                  int do_forces, double U0, double q, double *row, cudaStream_t s);
 
 // alb_particles.cu -- one tracer (HTML:730-736): position, remaining life, home lane; plus the
 // segment of the last step (x0,y0 -> x,y) and its speed for whoever draws the trails

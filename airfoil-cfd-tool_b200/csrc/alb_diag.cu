@@ -253,7 +253,92 @@ __global__ void fill_kernel(float *f0, float *f1, size_t plane, float e0, float 
     }
 }
 
+// End of a frame, one warp: merge the DIAG_SLOTS accumulator copies, then lane 0 performs
+// updateFieldsFromMacro()'s sticky update (HTML:611-613) and, on force frames, computeForces()'s
+// normalisation and EMAs (HTML:672-679, 699) -- the same float64 operations the host path
+// performs.  `row` may be mapped host memory.  Finally the merged reductions are published for
+// the host and all copies re-armed for the next frame (saves a host->device copy per frame).
+__global__ void frame_finalize_kernel(DiagAcc *d, DiagAcc *published, const MeState *me, int me_parity,
+                                      FrameDev *st, int do_forces, double U0, double q, double *row) {
+    const int lane = threadIdx.x;
+    DiagAcc m;
+    m.smax_bits = 0; m.m2max_bits = 0; m.rho_min = INFINITY; m.rho_max = -INFINITY;
+    m.fx = 0; m.fy = 0; m.surf = 0; m.rev = 0;
+    DiagAcc z = m;
+    for (int k = lane; k < DIAG_SLOTS; k += 32) {
+        const DiagAcc a = d[k];
+        m.smax_bits = max(m.smax_bits, a.smax_bits);
+        m.m2max_bits = max(m.m2max_bits, a.m2max_bits);
+        m.rho_min = fminf(m.rho_min, a.rho_min);
+        m.rho_max = fmaxf(m.rho_max, a.rho_max);
+        m.fx += a.fx; m.fy += a.fy; m.surf += a.surf; m.rev += a.rev;
+        d[k] = z;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        m.smax_bits = max(m.smax_bits, __shfl_xor_sync(FULL, m.smax_bits, s));
+        m.m2max_bits = max(m.m2max_bits, __shfl_xor_sync(FULL, m.m2max_bits, s));
+        m.rho_min = fminf(m.rho_min, __shfl_xor_sync(FULL, m.rho_min, s));
+        m.rho_max = fmaxf(m.rho_max, __shfl_xor_sync(FULL, m.rho_max, s));
+        m.fx += __shfl_xor_sync(FULL, m.fx, s);
+        m.fy += __shfl_xor_sync(FULL, m.fy, s);
+        m.surf += __shfl_xor_sync(FULL, m.surf, s);
+        m.rev += __shfl_xor_sync(FULL, m.rev, s);
+    }
+    if (lane != 0) return;
+    *published = m;
+    const double cden = __dmul_rn(__dmul_rn(1.5, U0), U0);
+    const double smax = __longlong_as_double((long long)m.smax_bits);
+    if (smax > 0) st->maxS = smax;
+    if (m.rho_min <= m.rho_max) {
+        const double cmin = __ddiv_rn(__dsub_rn((double)m.rho_min, 1.0), cden);
+        const double cmax = __ddiv_rn(__dsub_rn((double)m.rho_max, 1.0), cden);
+        if (isfinite(cmin)) st->cpMin = cmin;
+        if (isfinite(cmax)) st->cpMax = cmax;
+    }
+    double cl_raw = NAN, cd_raw = NAN, surf = NAN, rev = NAN;
+    if (do_forces) {
+        surf = (double)m.surf;
+        rev = (double)m.rev;
+        if (m.surf > 0) {
+            const double fx = __ddiv_rn(__ddiv_rn((double)m.fx, ALB_ME_SCALE), 3.0);
+            const double fy = __ddiv_rn(__ddiv_rn((double)m.fy, ALB_ME_SCALE), 3.0);
+            cl_raw = __ddiv_rn(fy, q);
+            cd_raw = __ddiv_rn(fx, q);
+            if (!st->ema_valid) {
+                st->cl_smooth = cl_raw;
+                st->cd_smooth = cd_raw;
+                st->ema_valid = 1;
+            } else {
+                st->cl_smooth = __dadd_rn(__dmul_rn(st->cl_smooth, 0.9), __dmul_rn(cl_raw, 0.1));
+                st->cd_smooth = __dadd_rn(__dmul_rn(st->cd_smooth, 0.9), __dmul_rn(cd_raw, 0.1));
+            }
+            st->sep_frac = __dadd_rn(__dmul_rn(st->sep_frac, 0.85), __dmul_rn(__ddiv_rn(rev, surf), 0.15));
+        }
+    }
+    const double mfx = __ddiv_rn((double)me->acc[me_parity][0], ALB_ME_SCALE);
+    const double mfy = __ddiv_rn((double)me->acc[me_parity][1], ALB_ME_SCALE);
+    row[0] = st->ema_valid ? st->cl_smooth : NAN;
+    row[1] = st->ema_valid ? st->cd_smooth : NAN;
+    row[2] = st->sep_frac;
+    row[3] = cl_raw;
+    row[4] = cd_raw;
+    row[5] = surf;
+    row[6] = rev;
+    row[7] = st->maxS;
+    row[8] = st->cpMin;
+    row[9] = st->cpMax;
+    row[10] = __ddiv_rn(mfy, q);
+    row[11] = __ddiv_rn(mfx, q);
+}
+
 }  // namespace
+
+cudaError_t launch_frame_finalize(DiagAcc *d, DiagAcc *published, const MeState *me, int me_parity, FrameDev *st,
+                                  int do_forces, double U0, double q, double *row, cudaStream_t s) {
+    frame_finalize_kernel<<<1, 32, 0, s>>>(d, published, me, me_parity, st, do_forces, U0, q, row);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_stats(const uint8_t *mask, const float *rho, const float *ux, const float *uy,
                          int pitch, int nx, int nyl, double u0, float *U, float *V, float *Cp,

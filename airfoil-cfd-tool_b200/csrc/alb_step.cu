@@ -42,6 +42,10 @@ constexpr unsigned FULL = 0xffffffffu;
 #define ALB_ST_HINT 0
 #endif
 //   ALB_EDGE_IN_FAST  (alb_common.cuh) inlet/outlet cells of otherwise all-fluid tasks patched in the fast kernel
+//   ALB_DIAG_MINBLOCKS  resident CTAs per SM the DIAG variant of the fast kernel is compiled for
+#ifndef ALB_DIAG_MINBLOCKS
+#define ALB_DIAG_MINBLOCKS 4
+#endif
 #ifndef ALB_FAST_MINBLOCKS
 #define ALB_FAST_MINBLOCKS 4
 #endif
@@ -223,6 +227,7 @@ __device__ __forceinline__ void me_begin_step(MeState *m, int parity) {
 // ---- fused diagnostics of the macro pass (HTML:596-614 statistics, HTML:649-700 faces) ----------
 struct DiagLocal {
     float rmin = INFINITY, rmax = -INFINITY;
+    float m2f = -1.0f;       // fp32 pre-filter: largest fp32 ux^2+uy^2 among the cells accepted so far
     double m2 = -1.0;        // largest ux^2+uy^2 among cells with s < 4
     float bux = 0.f, buy = 0.f;
     long long fx = 0, fy = 0;
@@ -240,9 +245,14 @@ __device__ __forceinline__ void diag_cell(const StepParams &p, DiagLocal &d, flo
         d.rmin = fminf(d.rmin, rho);
         d.rmax = fmaxf(d.rmax, rho);
     }
+    // fp32 pre-filter (relative error of m2f < 2e-7): a cell can only be the arg-max if its fp32
+    // value is within 1e-6 of the largest fp32 value seen so far; everything else skips the fp64 part
+    const float m2f = ux * ux + uy * uy;
+    if (!(m2f >= d.m2f * (1.0f - 1e-6f)) || m2f > p.m2f_cap) return;   // also drops NaN and s >= 4 for sure
     const double m2 = __dadd_rn(__dmul_rn((double)ux, (double)ux), __dmul_rn((double)uy, (double)uy));
     if (m2 > d.m2 && m2 < p.m2_hi) {
         if (m2 >= p.m2_lo && !(speed_ratio(ux, uy, p.U0d) < 4.0)) return;
+        d.m2f = fmaxf(d.m2f, m2f);   // only ACCEPTED cells (s < 4) may raise the pre-filter level
         d.m2 = m2;
         d.bux = ux;
         d.buy = uy;
@@ -284,6 +294,9 @@ __device__ __forceinline__ void atomic_max_float(float *a, float v) {
 
 // warp tree, then at most a handful of atomics per warp -- and none at all once the global
 // extrema have settled (plain-load pre-check)
+// FACES = false for tasks that cannot have fluid/solid faces (all-fluid, all-equilibrium): the
+// four face sums are known to be zero and are left out of the shuffle tree.
+template <bool FACES = true>
 __device__ __forceinline__ void diag_flush(const StepParams &p, DiagLocal &d, int lane) {
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
@@ -292,17 +305,21 @@ __device__ __forceinline__ void diag_flush(const StepParams &p, DiagLocal &d, in
         const double om = __shfl_xor_sync(FULL, d.m2, s);
         const float ox = __shfl_xor_sync(FULL, d.bux, s), oy = __shfl_xor_sync(FULL, d.buy, s);
         if (om > d.m2) { d.m2 = om; d.bux = ox; d.buy = oy; }
-        d.fx += __shfl_xor_sync(FULL, d.fx, s);
-        d.fy += __shfl_xor_sync(FULL, d.fy, s);
-        d.surf += __shfl_xor_sync(FULL, d.surf, s);
-        d.rev += __shfl_xor_sync(FULL, d.rev, s);
+        if (FACES) {
+            d.fx += __shfl_xor_sync(FULL, d.fx, s);
+            d.fy += __shfl_xor_sync(FULL, d.fy, s);
+            d.surf += __shfl_xor_sync(FULL, d.surf, s);
+            d.rev += __shfl_xor_sync(FULL, d.rev, s);
+        }
     }
     if (lane != 0) return;
-    DiagAcc *g = p.diag;
-    if (d.rmin < *(volatile float *)&g->rho_min) atomic_min_float(&g->rho_min, d.rmin);
-    if (d.rmax > *(volatile float *)&g->rho_max) atomic_max_float(&g->rho_max, d.rmax);
+    DiagAcc *g = p.diag + ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (DIAG_SLOTS - 1));
+    // pre-checks through L1 (ld.global.ca): a stale value only makes the filter less tight, the
+    // atomics below re-check against the true value
+    if (d.rmin < __ldca(&g->rho_min)) atomic_min_float(&g->rho_min, d.rmin);
+    if (d.rmax > __ldca(&g->rho_max)) atomic_max_float(&g->rho_max, d.rmax);
     if (d.m2 >= 0.0) {
-        const double cur = __longlong_as_double((long long)*(volatile unsigned long long *)&g->m2max_bits);
+        const double cur = __longlong_as_double((long long)__ldca(&g->m2max_bits));
         if (d.m2 >= cur * (1.0 - 1e-12)) {
             const double sr = speed_ratio(d.bux, d.buy, p.U0d);
             if (sr < 4.0) {
@@ -311,7 +328,7 @@ __device__ __forceinline__ void diag_flush(const StepParams &p, DiagLocal &d, in
             }
         }
     }
-    if (d.surf) {
+    if (FACES && d.surf) {
         atomicAdd(reinterpret_cast<unsigned long long *>(&g->fx), (unsigned long long)d.fx);
         atomicAdd(reinterpret_cast<unsigned long long *>(&g->fy), (unsigned long long)d.fy);
         atomicAdd(&g->surf, (unsigned long long)d.surf);
@@ -329,7 +346,7 @@ constexpr int KIND_FAST = 0, KIND_GENERAL = 1, KIND_UNIFIED = 2;
 // DIAG (step mode): also accumulate the autoscale statistics and pressure-face sums of the state
 // being WRITTEN (its rho/ux/uy are computed here anyway) -- used for the last step of a batch.
 template <int MODE, int KIND, bool DIAG = false>
-__global__ void __launch_bounds__(BLOCK_THREADS, KIND == KIND_FAST ? ALB_FAST_MINBLOCKS : 2)
+__global__ void __launch_bounds__(BLOCK_THREADS, KIND == KIND_FAST ? (DIAG ? ALB_DIAG_MINBLOCKS : ALB_FAST_MINBLOCKS) : 2)
 step_kernel(const __grid_constant__ StepParams p) {
     const int lane = threadIdx.x & 31;
     int task = blockIdx.x * TASKS_PER_BLOCK + (threadIdx.x >> 5);
@@ -366,7 +383,7 @@ step_kernel(const __grid_constant__ StepParams p) {
             if (DIAG) {   // 128 identical border cells (1, U0, 0), none of them next to a solid
                 DiagLocal d;
                 if (lane == 0) diag_cell(p, d, 1.0f, p.u0, 0.0f);
-                diag_flush(p, d, lane);
+                diag_flush<false>(p, d, lane);
             }
         } else {
             if (p.write_macro) {
@@ -377,7 +394,7 @@ step_kernel(const __grid_constant__ StepParams p) {
             if (p.diag) {   // 128 identical border cells (1, U0, 0), none of them next to a solid
                 DiagLocal d;
                 if (lane == 0) diag_cell(p, d, 1.0f, p.u0, 0.0f);
-                diag_flush(p, d, lane);
+                diag_flush<false>(p, d, lane);
             }
         }
         return;
@@ -561,7 +578,10 @@ step_kernel(const __grid_constant__ StepParams p) {
             st4(p.peer_lo_dst + 8 * p.peer_lo_plane + p.peer_lo_row + x0, o[8]);
         }
 
-        if (DIAG) diag_flush(p, dl, lane);
+        if (DIAG) {
+            if (KIND == KIND_FAST) diag_flush<false>(p, dl, lane);
+            else diag_flush<true>(p, dl, lane);
+        }
         if (GENERAL && p.me) {
             // integer sums are exact and order independent: shuffle tree, one atomic per warp
 #pragma unroll
@@ -582,7 +602,10 @@ step_kernel(const __grid_constant__ StepParams p) {
             st4(p.ux + c, mx);
             st4(p.uy + c, my);
         }
-        if (want_diag) diag_flush(p, dl, lane);
+        if (want_diag) {
+            if (KIND == KIND_FAST) diag_flush<false>(p, dl, lane);
+            else diag_flush<true>(p, dl, lane);
+        }
     }
 }
 

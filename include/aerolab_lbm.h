@@ -175,6 +175,22 @@ int alb_reynolds(const alb_handle *h, double *re);
  * (<25 %), 2 "STALL"; *sep_pct = round(100*sep_frac). */
 int alb_stall_state(const alb_handle *h, int *state, int *sep_pct);
 
+/* ---- the page's frame loop, frame(), HTML:902-930, run autonomously ----------
+ * nframes frames of steps_per_frame steps each (the page: 4, HTML:80).  After
+ * every frame the sticky autoscale values are refreshed (updateFieldsFromMacro)
+ * and, on every forces_every-th frame counted since create/reset (the page: 3,
+ * HTML:914), computeForces() with its EMAs runs -- all on the device: nothing
+ * synchronises with the host inside the loop; one 12-double record per frame is
+ * copied to host memory as the frames complete.  controls (nullable): nframes
+ * pairs {U0, tau} applied before each frame (the sliders).  series (nullable):
+ * nframes x 12 doubles = {CL, CD (EMA; NaN before the first force frame),
+ * sep_frac, CL_raw, CD_raw, surf, rev (NaN on frames without forces), maxS,
+ * cpMin, cpMax, CL_me, CD_me (momentum exchange of the frame's last step)}.
+ * Whole-lattice handles only.  Synchronises at the end. */
+#define ALB_FRAME_ROW 12
+int alb_run_frames(alb_handle *h, int nframes, int steps_per_frame, int forces_every,
+                   const double *controls, double *series);
+
 /* ---- tracer particles: initParts/spawn/advect/stepParticles, HTML:721-808 ---
  * Whole-lattice handles only.  Math.random() is replaced by a counter-based
  * generator keyed by (seed, particle, draw), so runs are reproducible. */

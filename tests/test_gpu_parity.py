@@ -432,3 +432,70 @@ def test_png_export(al, tmp_path):
     raw = zlib.decompress(idat)
     rows = np.frombuffer(raw, np.uint8).reshape(160, 1 + 320 * 4)[:, 1:].reshape(160, 320, 4)
     assert np.array_equal(rows[::-1], t.rgba("vort"))
+
+
+def test_run_frames_matches_oracle_frame_loop(al):
+    """alb_run_frames = the page's frame() x n with device-side sticky state; slider changes between frames."""
+    t, o = make_pair(al, 320, 160, "naca4412", 14.0)
+    nframes = 36
+    controls = np.tile(np.array([0.06, 0.58]), (nframes, 1))
+    controls[12:, 0] = 0.08            # U0 slider moved after frame 12
+    controls[24:, 1] = 0.6             # relaxation time changed after frame 24
+    s1 = t.run_frames(10, controls=controls[:10])
+    s2 = t.run_frames(nframes - 10, controls=controls[10:])
+    s = {k: np.concatenate([s1[k], s2[k]]) for k in s1}
+    for f in range(nframes):
+        o.u0, o.tau = float(controls[f, 0]), float(controls[f, 1])
+        o.step(4)
+        o.update_fields()
+        assert s["cpMin"][f] == o.cp_min and s["cpMax"][f] == o.cp_max, f
+        assert s["maxS"][f] == pytest.approx(o.max_s, rel=1e-14)
+        cl_me, cd_me = o.me_coeffs()
+        assert s["CL_me"][f] == pytest.approx(cl_me, rel=1e-13) and s["CD_me"][f] == pytest.approx(cd_me, rel=1e-13)
+        if (f + 1) % 3 == 0:
+            w = o.compute_forces()
+            assert (s["surf"][f], s["rev"][f]) == (w["surf"], w["rev"])
+            assert s["CL_raw"][f] == pytest.approx(w["CL_raw"], rel=1e-12)
+            assert s["CL"][f] == pytest.approx(o.cl_smooth, rel=1e-12)
+            assert s["CD"][f] == pytest.approx(o.cd_smooth, rel=1e-12)
+            assert s["sep_frac"][f] == pytest.approx(o.sep_frac, rel=1e-12, abs=1e-300)
+        else:
+            assert np.isnan(s["CL_raw"][f]) and np.isnan(s["surf"][f])
+    assert np.isnan(s["CL"][0]) and np.isnan(s["CL"][1]) and not np.isnan(s["CL"][2])
+    compare_state(t, o, "after run_frames")
+    # the host-side sticky state continues seamlessly
+    assert t.stall_state() == o.stall_state()[0]
+    o.step(4); o.update_fields()
+    out = t.frame()
+    assert out["stats"]["cpMin"] == o.cp_min and "forces" not in out
+    with pytest.raises(al.AerolabLbmError):
+        t.run_frames(2, controls=[[0.06, float("nan")], [0.06, 0.58]])
+
+
+def test_stats_exclude_fast_cells(al):
+    """updateFieldsFromMacro ignores speeds >= 4 U0 (HTML:608); with a slow inlet and a violently
+    perturbed state many cells exceed that, and the fused reductions must still pick the largest
+    s < 4 (the fp32 pre-filter may only be raised by accepted cells)."""
+    nx, ny = 256, 96
+    t = al.WindTunnel(nx, ny, 0, u0=0.03, tau=0.8)
+    o = olbm.OracleTunnel(nx, ny, 0.03, 0.8)
+    m = np.zeros((ny, nx), np.uint8); m[30:60, 100:110] = 255
+    t.set_mask(m); o.set_mask(m)
+    rng = np.random.default_rng(5)
+    F = t.populations()
+    F[1] *= (1 + 1.2 * rng.random(F[1].shape)).astype(np.float32)     # eastward bias: |u| up to ~5 U0
+    F[2] *= (1 + 0.6 * rng.random(F[2].shape)).astype(np.float32)
+    t.set_populations(F); o.F[...] = F
+    seen_excluded = False
+    for k in range(8):
+        t.step(2); o.step(2)
+        st = t.update_stats()
+        s_all = np.hypot(o.ux.astype(np.float64) / o.u0, o.uy.astype(np.float64) / o.u0)[o.mask == 0]
+        seen_excluded |= bool((s_all >= 4).any())
+        o.update_fields()
+        assert st["maxS"] == pytest.approx(o.max_s, rel=1e-14), k
+        assert st["cpMin"] == o.cp_min and st["cpMax"] == o.cp_max
+        s = t.run_frames(1, steps_per_frame=1)
+        o.step(1); o.update_fields()
+        assert s["maxS"][0] == pytest.approx(o.max_s, rel=1e-14) and s["cpMax"][0] == o.cp_max
+    assert seen_excluded
