@@ -40,7 +40,7 @@ EXPORTS = [
     "alb_compute_forces", "alb_forces_partial", "alb_reset_force_emas",
     "alb_get_me_history", "alb_get_me_forces", "alb_clamp_hits",
     "alb_reynolds", "alb_stall_state",
-    "alb_run_frames",
+    "alb_run_frames", "alb_frames_enqueue", "alb_frames_collect",
     "alb_particles_init", "alb_particles_resize", "alb_particles_step", "alb_particles_get",
     "alb_connect_local", "alb_ipc_export", "alb_ipc_connect", "alb_halo_prime", "alb_halo_ptrs",
     "alb_set_external_halo",
@@ -116,6 +116,8 @@ def lib():
     L.alb_reynolds.argtypes = [H, dp]
     L.alb_stall_state.argtypes = [H, ip, ip]
     L.alb_run_frames.argtypes = [H, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.alb_frames_enqueue.argtypes = [H, C.c_int, C.c_int, C.c_int, vp]
+    L.alb_frames_collect.argtypes = [H, vp]
     L.alb_particles_init.argtypes = [H, C.c_int, C.c_ulonglong]
     L.alb_particles_resize.argtypes = [H, C.c_int]
     L.alb_particles_step.argtypes = [H, C.c_double]

@@ -50,12 +50,17 @@ def run_cases(coords, alphas: Sequence[float], nx: int = 2048, ny: int = 1024, s
         for t in tunnels:
             t.step(n)
         done += n
+    # settle phase: the page's force cadence (one EMA sample per 12 steps) as an on-device frame
+    # loop per case -- enqueued on every handle first, collected afterwards, so the cases overlap
+    # and nothing synchronises with the host inside the loops
+    nsamples = settle_steps // FORCE_CADENCE
     last = [None] * len(tunnels)
-    for _ in range(settle_steps // FORCE_CADENCE):
+    if nsamples > 0:
         for t in tunnels:
-            t.step(FORCE_CADENCE)
+            t.frames_enqueue(nsamples, steps_per_frame=FORCE_CADENCE, forces_every=1)
         for k, t in enumerate(tunnels):
-            last[k] = t.forces()
+            s = t.frames_collect()
+            last[k] = dict(CL=s["CL"][-1], CD=s["CD"][-1], sep_frac=s["sep_frac"][-1])
     rows = []
     for a, t, f in zip(alphas, tunnels, last):
         if f is None:

@@ -405,6 +405,24 @@ class WindTunnel:
                                           ptr(ctrl), ptr(series)))
         return {k: series[:, i] for i, k in enumerate(self.FRAME_COLUMNS)}
 
+    def frames_enqueue(self, nframes: int, controls=None, steps_per_frame: int = STEPS_PER_FRAME,
+                       forces_every: int = FORCES_EVERY_FRAMES):
+        """First half of ``run_frames``: enqueue without waiting (pair with ``frames_collect``)."""
+        ctrl = None
+        if controls is not None:
+            ctrl = np.ascontiguousarray(controls, dtype=np.float64).reshape(int(nframes), 2)
+        self._ck(self._lib.alb_frames_enqueue(self._h, int(nframes), int(steps_per_frame), int(forces_every),
+                                              ptr(ctrl)))
+        self._pending_frames = int(nframes)
+        return self
+
+    def frames_collect(self) -> dict:
+        n = getattr(self, "_pending_frames", 0)
+        series = np.empty((n, _ffi.ALB_FRAME_ROW))
+        self._ck(self._lib.alb_frames_collect(self._h, ptr(series) if n else None))
+        self._pending_frames = 0
+        return {k: series[:, i] for i, k in enumerate(self.FRAME_COLUMNS)}
+
     def frame(self, want_field: Optional[str] = None) -> dict:
         """One animation frame (HTML:902-930): 4 steps, render with the previous frame's
         autoscale, refresh the autoscale, forces every 3rd frame."""

@@ -94,6 +94,7 @@ struct alb_handle {
     FrameDev *d_frame = nullptr, *h_frame = nullptr;   // device state of the frame loop + pinned staging
     double *d_rows = nullptr, *h_rows = nullptr;      // per-frame records (device, pinned host)
     int rows_cap = 0;
+    int frames_pending = 0;                           // frames enqueued by alb_frames_enqueue, not yet collected
     long long frame_counter = 0;                      // statCounter, HTML:594, 913
     ParticleState *parts = nullptr;
     unsigned *part_ctr = nullptr;
@@ -763,12 +764,12 @@ int alb_step(alb_handle *h, int nsteps) {
     return ALB_OK;
 }
 
-int alb_run_frames(alb_handle *h, int nframes, int steps_per_frame, int forces_every, const double *controls,
-                   double *series) {
+int alb_frames_enqueue(alb_handle *h, int nframes, int steps_per_frame, int forces_every, const double *controls) {
     NEED(h);
     ARG(nframes >= 0 && steps_per_frame >= 1, "alb_run_frames: need nframes >= 0 and steps_per_frame >= 1");
     if (!h->whole() || h->lo.base || h->hi.base)
         return h->fail(ALB_ERR_STATE, "alb_run_frames needs a whole-lattice handle");
+    if (h->frames_pending) return h->fail(ALB_ERR_STATE, "alb_frames_enqueue: collect the previous batch first");
     if (nframes == 0) return ALB_OK;
     if (controls)
         for (int f = 0; f < 2 * nframes; f++) ARG(isfinite(controls[f]), "alb_run_frames: controls must be finite");
@@ -814,13 +815,29 @@ int alb_run_frames(alb_handle *h, int nframes, int steps_per_frame, int forces_e
     CK(cudaMemcpyAsync(h->h_diag, h->d_diag_pub, sizeof(DiagAcc), cudaMemcpyDeviceToHost, h->stream));
     h->diag_slots_host = 1;
     CK(cudaMemcpyAsync(h->h_frame, h->d_frame, sizeof(FrameDev), cudaMemcpyDeviceToHost, h->stream));
+    h->frames_pending = nframes;
+    return ALB_OK;
+}
+
+int alb_frames_collect(alb_handle *h, double *series) {
+    NEED(h);
+    const int nframes = h->frames_pending;
+    if (nframes == 0) return ALB_OK;
     CK(cudaStreamSynchronize(h->stream));
+    h->frames_pending = 0;
     const FrameDev &o = *h->h_frame;
     h->maxS = o.maxS; h->cpMin = o.cpMin; h->cpMax = o.cpMax;
     h->cl_smooth = o.cl_smooth; h->cd_smooth = o.cd_smooth; h->sep_frac = o.sep_frac;
     h->ema_valid = o.ema_valid != 0;
     if (series) memcpy(series, h->h_rows, sizeof(double) * FRAME_ROW * nframes);
     return check_wait_error(h);
+}
+
+int alb_run_frames(alb_handle *h, int nframes, int steps_per_frame, int forces_every, const double *controls,
+                   double *series) {
+    int r = alb_frames_enqueue(h, nframes, steps_per_frame, forces_every, controls);
+    if (r) return r;
+    return alb_frames_collect(h, series);
 }
 
 int alb_sync(alb_handle *h) {

@@ -190,6 +190,13 @@ int alb_stall_state(const alb_handle *h, int *state, int *sep_pct);
 #define ALB_FRAME_ROW 12
 int alb_run_frames(alb_handle *h, int nframes, int steps_per_frame, int forces_every,
                    const double *controls, double *series);
+/* The same in two halves, so that several handles (e.g. the cases of an alpha
+ * sweep sharing one GPU) can run their frame loops concurrently: enqueue on each
+ * handle, then collect each.  Between the two calls only alb_frames_collect may
+ * be used on the handle. */
+int alb_frames_enqueue(alb_handle *h, int nframes, int steps_per_frame, int forces_every,
+                       const double *controls);
+int alb_frames_collect(alb_handle *h, double *series /* nframes x 12, nullable */);
 
 /* ---- tracer particles: initParts/spawn/advect/stepParticles, HTML:721-808 ---
  * Whole-lattice handles only.  Math.random() is replaced by a counter-based
