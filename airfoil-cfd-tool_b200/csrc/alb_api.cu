@@ -71,7 +71,7 @@ struct alb_handle {
     int ngen = 0;
     int small_capacity = 0;       // cells the persistent small-lattice kernel can hold on this GPU
     double u0 = 0.06, tau = 0.58;
-    float u0f = 0, tauf = 0, inv_tau = 0;
+    float u0f = 0, tauf = 0, inv_tau = 0, inv_tau_lo = 0;
     float feq0[9];
     cudaStream_t stream = nullptr;
     cudaStream_t aux = nullptr;   // runs the general-task kernel concurrently with the fast kernel
@@ -167,6 +167,7 @@ void refresh_params(alb_handle *h) {
     h->u0f = (float)h->u0;
     h->tauf = (float)h->tau;
     h->inv_tau = 1.0f / h->tauf;
+    h->inv_tau_lo = (float)(1.0 / (double)h->tauf - (double)h->inv_tau);
     host_feq0(h->u0f, h->feq0);
 }
 
@@ -187,6 +188,7 @@ StepParams make_params(alb_handle *h, int src_idx) {
     p.nx = h->nx;
     p.tau = h->tauf;
     p.inv_tau = h->inv_tau;
+    p.inv_tau_lo = h->inv_tau_lo;
     p.u0 = h->u0f;
     memcpy(p.feq0, h->feq0, sizeof p.feq0);
     p.rho = h->rho;

@@ -87,6 +87,7 @@ struct StepParams {
     int nyl;                 // rows owned by this slab
     int nx;
     float tau, inv_tau;      // inv_tau = RN(1/tau)
+    float inv_tau_lo;        // RN(1/tau - inv_tau): the part of the reciprocal that fp32 cannot hold
     float u0;
     float feq0[9];           // feq_i(1, U0, 0) in fp32, source order (HTML:315-317)
     // macro output (macro mode only)

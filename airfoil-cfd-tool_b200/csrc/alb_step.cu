@@ -97,18 +97,16 @@ __device__ __forceinline__ void st4(float *p, const float4 &v) {
 }
 
 // x / tau, correctly rounded (== IEEE division), for the uniform divisor tau.
-// rcp = RN(1/tau) is computed once on the host.  q0 = RN(x*rcp) is within a
-// few ulp; one residual correction makes it faithful; by Markstein's theorem a
-// second correction with an exact residual (FMA) and a correctly rounded
-// reciprocal yields RN(x/tau).  5 instructions instead of the ~10 + slow path
-// of the generic division.  (Operands here are differences of populations: 0
-// or >= 2^-30 in magnitude, far from underflow.)  Checked exhaustively against
-// true division in tests/test_div_by_tau.py.
-__device__ __forceinline__ float div_by_tau(float x, float tau, float rcp) {
-    float q = __fmul_rn(x, rcp);
-    float r = __fmaf_rn(-tau, q, x);
-    q = __fmaf_rn(r, rcp, q);
-    r = __fmaf_rn(-tau, q, x);
+// rcp = RN(1/tau) and rcp_lo = RN(1/tau - rcp) are computed once on the host.  x*(rcp + rcp_lo),
+// rounded once by the FMA, is a faithful estimate of the quotient; by Markstein's theorem one
+// correction with the exact residual (FMA) and the correctly rounded reciprocal then yields
+// RN(x/tau).  4 instructions instead of the ~10 + slow path of the generic division.  (Operands
+// here are differences of populations: 0 or >= 2^-30 in magnitude, far from underflow.)  Checked
+// exhaustively against true division in tests/test_div_by_tau.py.
+__device__ __forceinline__ float div_by_tau(float x, float tau, float rcp, float rcp_lo) {
+    const float t = __fmul_rn(x, rcp_lo);
+    float q = __fmaf_rn(x, rcp, t);
+    const float r = __fmaf_rn(-tau, q, x);
     q = __fmaf_rn(r, rcp, q);
     return q;
 }
@@ -158,7 +156,7 @@ __device__ __forceinline__ void moments_plain(const float (&f)[9], float &rho, f
 // HTML:276-281 and 352-356.  feq_i = wt(i)*rho*(1+3eu+4.5eu*eu-1.5uu), left to
 // right; opposite directions share 3*eu and 4.5*eu*eu (negating eu negates the
 // first exactly and leaves the second unchanged, so sharing is bit-neutral).
-__device__ __forceinline__ void collide(float (&f)[9], const Moments &m, float tau, float rcp) {
+__device__ __forceinline__ void collide(float (&f)[9], const Moments &m, float tau, float rcp, float rcp_lo) {
     const float w0 = 4.0f / 9.0f, ws = 1.0f / 9.0f, wd = 1.0f / 36.0f;
     const float rho = m.rho, ux = m.ux, uy = m.uy;
     const float uu = ux * ux + uy * uy;
@@ -166,7 +164,7 @@ __device__ __forceinline__ void collide(float (&f)[9], const Moments &m, float t
     const float wr0 = w0 * rho, wrs = ws * rho, wrd = wd * rho;
     {
         float eq = wr0 * (1.0f - c15);
-        f[0] = f[0] - div_by_tau(f[0] - eq, tau, rcp);
+        f[0] = f[0] - div_by_tau(f[0] - eq, tau, rcp, rcp_lo);
     }
 #define ALB_PAIR(A, B, EU, WR)                                      \
     {                                                               \
@@ -175,8 +173,8 @@ __device__ __forceinline__ void collide(float (&f)[9], const Moments &m, float t
         const float t2 = (4.5f * eu) * eu;                          \
         const float ea = (WR) * (((1.0f + t1) + t2) - c15);         \
         const float eb = (WR) * (((1.0f - t1) + t2) - c15);         \
-        f[A] = f[A] - div_by_tau(f[A] - ea, tau, rcp);              \
-        f[B] = f[B] - div_by_tau(f[B] - eb, tau, rcp);              \
+        f[A] = f[A] - div_by_tau(f[A] - ea, tau, rcp, rcp_lo);              \
+        f[B] = f[B] - div_by_tau(f[B] - eb, tau, rcp, rcp_lo);              \
     }
     ALB_PAIR(1, 3, ux, wrs)
     ALB_PAIR(2, 4, uy, wrs)
@@ -504,7 +502,7 @@ step_kernel(const __grid_constant__ StepParams p) {
 
         const Moments m = moments_clamped(f);
         float rho = m.rho, ux = m.ux, uy = m.uy;
-        if (MODE == MODE_STEP) collide(f, m, p.tau, p.inv_tau);
+        if (MODE == MODE_STEP) collide(f, m, p.tau, p.inv_tau, p.inv_tau_lo);
         bool hit = m.hit;
 
         if (GENERAL) {
@@ -663,7 +661,7 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
                     }
                 }
                 const Moments m = moments_clamped(f);
-                collide(f, m, p.tau, p.inv_tau);
+                collide(f, m, p.tau, p.inv_tau, p.inv_tau_lo);
                 hit = m.hit;
                 rho = m.rho; ux = m.ux; uy = m.uy;
             } else if (type == CT_SOLID) {

@@ -13,6 +13,7 @@ import csv
 import io
 import json
 import os
+import re
 import subprocess
 import sys
 from collections import defaultdict
@@ -117,8 +118,8 @@ def main():
     if os.path.exists(tpath):
         traffic_json = json.load(open(tpath))
     if full:
-        fast = [d for d in full if "step_kernel<0, 0>" in d["kernel"]]
-        gen = [d for d in full if "step_kernel<0, 1>" in d["kernel"]]
+        fast = [d for d in full if re.search(r"step_kernel<0, 0(, 0)?>", d["kernel"])]
+        gen = [d for d in full if re.search(r"step_kernel<0, 1(, 0)?>", d["kernel"])]
 
         def dram(d):
             return (to_bytes(d["dram__bytes_read.sum"]["value"], d["dram__bytes_read.sum"]["unit"])
@@ -127,8 +128,8 @@ def main():
             t = sum(dram(d) for d in fast) / len(fast) + (sum(dram(d) for d in gen) / len(gen) if gen else 0)
             traffic_json["configs[2]"] = t
     if tr:
-        fast = [d for d in tr if "step_kernel<0, 0>" in d["kernel"]]
-        gen = [d for d in tr if "step_kernel<0, 1>" in d["kernel"]]
+        fast = [d for d in tr if re.search(r"step_kernel<0, 0(, 0)?>", d["kernel"])]
+        gen = [d for d in tr if re.search(r"step_kernel<0, 1(, 0)?>", d["kernel"])]
         s = lambda L: sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in L) / max(1, len(L))
         traffic_json["configs[3]"] = s(fast) + s(gen)
     traffic_json["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per step (fast + general kernel), "

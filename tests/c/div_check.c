@@ -5,12 +5,14 @@
 #include <stdint.h>
 #include <string.h>
 
-static inline float div_by_tau(float x, float tau, float rcp)
+/* rcp = RN(1/tau), rcp_lo = RN(1/tau - rcp) (host, float64): x*(rcp+rcp_lo) rounded once is a
+ * faithful quotient estimate; one Markstein correction with the exact residual then gives the
+ * correctly rounded x/tau. */
+static inline float div_by_tau(float x, float tau, float rcp, float rcp_lo)
 {
-    float q = x * rcp;
+    float t = x * rcp_lo;
+    float q = fmaf(x, rcp, t);
     float r = fmaf(-tau, q, x);
-    q = fmaf(r, rcp, q);
-    r = fmaf(-tau, q, x);
     q = fmaf(r, rcp, q);
     return q;
 }
@@ -20,6 +22,7 @@ static inline float div_by_tau(float x, float tau, float rcp)
 long div_check(float tau, uint32_t lo_bits, uint32_t hi_bits, uint32_t stride, uint32_t *first_bad)
 {
     const float rcp = 1.0f / tau;
+    const float rcp_lo = (float)(1.0 / (double)tau - (double)rcp);
     long bad = 0;
     uint32_t fb = 0;
 #pragma omp parallel for reduction(+ : bad) schedule(static)
@@ -29,7 +32,7 @@ long div_check(float tau, uint32_t lo_bits, uint32_t hi_bits, uint32_t stride, u
         memcpy(&x, &u, 4);
         for (int sgn = 0; sgn < 2; sgn++) {
             float xs = sgn ? -x : x;
-            q1 = div_by_tau(xs, tau, rcp);
+            q1 = div_by_tau(xs, tau, rcp, rcp_lo);
             q2 = xs / tau;
             uint32_t a, c;
             memcpy(&a, &q1, 4);

@@ -499,3 +499,40 @@ def test_stats_exclude_fast_cells(al):
         o.step(1); o.update_fields()
         assert s["maxS"][0] == pytest.approx(o.max_s, rel=1e-14) and s["cpMax"][0] == o.cp_max
     assert seen_excluded
+
+
+def test_randomized_configurations_bitwise(al):
+    """Random lattice sizes (all launch paths: persistent, unified, split+graph), mask densities,
+    parameters and batch lengths; every configuration must match the oracle bit for bit,
+    including the momentum-exchange integers and the statistics of the final state."""
+    rng = np.random.default_rng(2024)
+    sizes = [(rng.integers(3, 40), rng.integers(3, 30)) for _ in range(6)]
+    sizes += [(int(rng.integers(100, 700)), int(rng.integers(40, 300))) for _ in range(8)]
+    sizes += [(1536, 640), (2048, 520)]          # beyond the persistent-kernel capacity: split kernels + graph
+    for k, (nx, ny) in enumerate(sizes):
+        nx, ny = int(nx), int(ny)
+        u0 = float(rng.uniform(0.03, 0.1))
+        tau = float(rng.uniform(0.51, 1.2))
+        dens = float(rng.choice([0.0, 0.02, 0.1, 0.3]))
+        m = (rng.random((ny, nx)) < dens).astype(np.uint8) * 255
+        t = al.WindTunnel(nx, ny, 0, u0=u0, tau=tau)
+        o = olbm.OracleTunnel(nx, ny, u0, tau)
+        t.set_mask(m); o.set_mask(m)
+        total = 0
+        for n in (1, int(rng.integers(2, 8)), int(rng.integers(9, 30))):
+            t.step(n); o.step(n)
+            total += n
+        what = f"case {k}: {nx}x{ny} u0={u0:.3f} tau={tau:.3f} dens={dens}"
+        compare_state(t, o, what)
+        assert np.array_equal(t.me_history(total), np.array(o.me_hist, dtype=np.int64)), what
+        st = t.update_stats(); o.update_fields()
+        assert st["cpMin"] == o.cp_min and st["cpMax"] == o.cp_max, what
+        assert st["maxS"] == pytest.approx(o.max_s, rel=1e-14), what
+        f = t.forces(); w = o.compute_forces()
+        if w is None:
+            assert not f["any"], what
+        else:
+            assert (f["surf"], f["rev"]) == (w["surf"], w["rev"]), what
+            assert f["CL_raw"] == pytest.approx(w["CL_raw"], rel=1e-11, abs=1e-11), what
+        assert t.clamp_hits() == o.clamp_hits, what
+        t.close()

@@ -1,3 +1,5 @@
+"""Measure the cost of the DIAG variant of the step (statistics/force reductions in the last step of a
+batch) against a plain step, and one frame of alb_run_frames, at configs[3].  Run on a B200."""
 import sys, time
 sys.path.insert(0, "airfoil-cfd-tool_b200")
 import aerolab_lbm as al

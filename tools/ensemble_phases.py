@@ -1,3 +1,5 @@
+"""Wall-clock breakdown of an alpha sweep with four 2048x1024 cases sharing one GPU: handle creation,
+free-running phase (CUDA-graph replay, four streams), settle phase (on-device frame loops)."""
 import sys, time
 sys.path.insert(0, "airfoil-cfd-tool_b200")
 import aerolab_lbm as al
