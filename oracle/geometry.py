@@ -1,8 +1,7 @@
 """Float64 restatement of the reference tunnel's geometry pipeline (ORACLE).
 
-TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  PARITY UNPINNED by the
-reference (no golden vectors); pinned only against the surveyor's probe values
- and the committed fixtures under ``tests/golden/``.
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  Pinned against the reference's own JavaScript executed by tests/refexec (tests/test_reference_pins.py):
+panel nodes bitwise, masks identical.
 
 Follows ``pages/airfoil_flow_lbm_aerolab.html`` (cited as HTML:line):
 

@@ -1,6 +1,7 @@
 """ctypes front end of the C oracle + a frame-loop mirror (ORACLE, tests only).
 
-TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  PARITY UNPINNED.
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  Pinned against the reference's own source executed by tests/refexec (see oracle/__init__.py).
+
 
 ``OracleTunnel`` restates the reference's host-side driver around the step:
 ``initSim`` (HTML:492-500), ``applyGeometry`` (HTML:579-586, no flow reset),

@@ -1,6 +1,7 @@
 """Second, independently written restatement of the reference step (NumPy, fp32).
 
-TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  PARITY UNPINNED.
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  Pinned through oracle/lbm_ref.c (see oracle/__init__.py).
+
 
 Purpose: guard against a reading error in ``oracle/lbm_ref.c``.  The two are
 written differently (scalar C with branches versus whole-array NumPy with

@@ -1,7 +1,8 @@
 /*
  * ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
- * PARITY UNPINNED: the reference has no golden vectors for this path and its
- * own implementation (GLSL in a browser) cannot run here.
+ * Pinned against the reference's own shader / JavaScript text executed by the
+ * minimal interpreters in tests/refexec (tests/test_reference_pins.py): bitwise
+ * equal populations, macro fields, statistics, force EMAs and render output.
  *
  * Strict IEEE-754 binary32 restatement, in source operation order, of the
  * reference's D2Q9 step and its host-side diagnostics.  "HTML:n" cites

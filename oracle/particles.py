@@ -1,7 +1,8 @@
 """CPU restatement of the tunnel's tracer particles (ORACLE, tests only).
 
-TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  PARITY UNPINNED (and the reference
-seeds with ``Math.random``, so only the algorithm can be mirrored, not a run).
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  ``sampleScalar/sampleUV/advect`` are pinned against the
+reference's own JavaScript executed by tests/refexec (tests/test_reference_pins.py); spawning uses
+``Math.random`` in the reference, so there only the algorithm can be mirrored, not a run.
 
 Follows pages/airfoil_flow_lbm_aerolab.html: ``sampleScalar``/``sampleUV`` 616-639, ``spawn``
 730-736, ``initParts`` 737-753, ``advect`` 754-767, ``stepParticles`` 780-808 (without the canvas
@@ -87,6 +88,26 @@ class Particles:
                 w += ws[k]
         return s / w if w > 0 else None
 
+    @classmethod
+    def advect(cls, U, V, mask, x, y, dt):
+        """advect(), HTML:754-767: (nx, ny, speed) or None."""
+        u1 = cls._sample(U, mask, x, y)
+        v1 = cls._sample(V, mask, x, y)
+        if u1 is None or v1 is None:
+            return None
+        k_base = 0.00105 * dt
+        speed1 = math.hypot(u1, v1)
+        dt_eff = k_base
+        max_disp = 0.05
+        if speed1 * dt_eff > max_disp:
+            dt_eff = max_disp / max(speed1, 1e-6)
+        midx, midy = x + u1 * dt_eff * 0.5, y + v1 * dt_eff * 0.5
+        u2 = cls._sample(U, mask, midx, midy)
+        v2 = cls._sample(V, mask, midx, midy)
+        if u2 is None or v2 is None:
+            u2, v2 = u1, v1
+        return (x + u2 * dt_eff, y + v2 * dt_eff, math.hypot(u2, v2))
+
     def step(self, dt, mask, ux, uy, u0):
         """stepParticles(dt), HTML:780-808; returns (n, 8) like alb_particles_get."""
         with np.errstate(all="ignore"):
@@ -94,22 +115,7 @@ class Particles:
             V = (uy.astype(np.float64) / u0).astype(np.float32)
         out = np.zeros((len(self.p), 8))
         for i, p in enumerate(self.p):
-            adv = None
-            u1 = self._sample(U, mask, p["x"], p["y"])
-            v1 = self._sample(V, mask, p["x"], p["y"])
-            if u1 is not None and v1 is not None:            # advect(), HTML:754-767
-                k_base = 0.00105 * dt
-                speed1 = math.hypot(u1, v1)
-                dt_eff = k_base
-                max_disp = 0.05
-                if speed1 * dt_eff > max_disp:
-                    dt_eff = max_disp / max(speed1, 1e-6)
-                midx, midy = p["x"] + u1 * dt_eff * 0.5, p["y"] + v1 * dt_eff * 0.5
-                u2 = self._sample(U, mask, midx, midy)
-                v2 = self._sample(V, mask, midx, midy)
-                if u2 is None or v2 is None:
-                    u2, v2 = u1, v1
-                adv = (p["x"] + u2 * dt_eff, p["y"] + v2 * dt_eff, math.hypot(u2, v2))
+            adv = self.advect(U, V, mask, p["x"], p["y"], dt)
             stalled = adv is not None and adv[2] * adv[2] < self.STALL_SPEED2
             p["life"] -= dt * (self.STALL_DRAIN if stalled else 0.06)
             if adv is None or p["life"] <= 0:
