@@ -466,6 +466,92 @@ class WindTunnel:
         return f"{'_'.join(base)}_alpha{self.alpha:.1f}deg_lbm.png"
 
 
+class LocalMultiTunnel:
+    """One process, several GPUs: y-slabs created and connected by ``alb_create_multi``.
+
+    Same control surface as ``WindTunnel`` for the calls that make sense on a decomposed
+    lattice; whole-lattice arrays are assembled on the host on request."""
+
+    def __init__(self, nx: int, ny: int, devices: Sequence[int], u0: float = DEFAULT_U0, tau: float = DEFAULT_TAU):
+        lib = _ffi.lib()
+        n = len(devices)
+        devs = (C.c_int * n)(*[int(d) for d in devices])
+        handles = (C.c_void_p * n)()
+        check(lib.alb_create_multi(int(nx), int(ny), devs, n, handles))
+        self._lib, self.nx, self.ny = lib, int(nx), int(ny)
+        self._handles = handles
+        self.slabs = []
+        y0 = 0
+        for k in range(n):
+            t = WindTunnel.__new__(WindTunnel)          # adopt the handle created by the library
+            t._lib, t._h = lib, C.c_void_p(handles[k])
+            nyl = C.c_int()
+            y0c = C.c_int()
+            check(lib.alb_get_dims(t._h, None, None, C.byref(y0c), C.byref(nyl)), t._h)
+            t.nx, t.ny, t.y0, t.ny_local, t.device = self.nx, self.ny, y0c.value, nyl.value, int(devices[k])
+            t.name, t.coords, t.alpha = "", None, DEFAULT_ALPHA
+            self.slabs.append(t)
+        if u0 != DEFAULT_U0 or tau != DEFAULT_TAU:
+            for t in self.slabs:
+                t.reset(u0)
+                t.set_tau(tau)
+
+    def load_coords(self, coords, name="", alpha=None):
+        for t in self.slabs:
+            t.load_coords(coords, name=name, alpha=alpha)
+        return self
+
+    def load_shape(self, key, alpha=None):
+        return self.load_coords(geom.SHAPES[key](), name=key, alpha=alpha)
+
+    def set_alpha(self, alpha):
+        for t in self.slabs:
+            t.set_alpha(alpha)
+        return self
+
+    def set_params(self, u0, tau):
+        for t in self.slabs:
+            t.set_params(u0, tau)
+        return self
+
+    def step(self, n: int = 1):
+        check(self._lib.alb_step_multi(self._handles, len(self.slabs), int(n)))
+        return self
+
+    def sync(self):
+        for t in self.slabs:
+            t.sync()
+        return self
+
+    def populations(self):
+        return np.concatenate([t.populations() for t in self.slabs], axis=1)
+
+    def macro(self):
+        parts = [t.macro() for t in self.slabs]
+        return tuple(np.concatenate([p[k] for p in parts], axis=0) for k in range(3))
+
+    def mask(self):
+        return np.concatenate([t.mask() for t in self.slabs], axis=0)
+
+    def forces_raw(self) -> dict:
+        """Pressure-face sums and momentum exchange of the current state, summed over the slabs."""
+        part = sum(t.forces_partial() for t in self.slabs)
+        u0, _ = self.slabs[0].params()
+        q = 0.5 * u0 * u0 * (self.nx / (geom.DX1 - geom.DX0))
+        out = dict(fx=part[0], fy=part[1], surf=int(part[2]), rev=int(part[3]))
+        if part[2] > 0:
+            out.update(CL_raw=part[1] / q, CD_raw=part[0] / q)
+        if self.slabs[0].steps > 0:
+            me = sum(t.me_history(1)[0] for t in self.slabs)
+            out.update(CL_me=float(me[1]) / _ffi.ALB_ME_SCALE / q, CD_me=float(me[0]) / _ffi.ALB_ME_SCALE / q)
+        return out
+
+    def close(self):
+        for t in self.slabs:
+            t.close()
+        self.slabs = []
+
+
 def build_lbm_component(coords_after, airfoil_name: str = "", *, nx: int = DEFAULT_NX,
                         ny: int = DEFAULT_NY, device: int = 0) -> WindTunnel:
     """Drop-in for pages/Airfoil_Analysis.py:20-42.

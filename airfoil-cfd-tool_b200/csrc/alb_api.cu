@@ -454,6 +454,7 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        // general-task kernel: high priority (measured: priority makes no difference)
         CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, prio_hi));
         CK(cudaEventCreate(&h->ev0));
         CK(cudaEventCreate(&h->ev1));
@@ -1276,6 +1277,51 @@ int alb_connect_local(alb_handle *h, alb_handle *lo, alb_handle *hi) {
     h->hi = Peer();
     if (lo) { h->lo.base = lo->f[0]; h->lo.flags = lo->flags; h->lo.plane = lo->plane; h->lo.nyl = lo->nyl; }
     if (hi) { h->hi.base = hi->f[0]; h->hi.flags = hi->flags; h->hi.plane = hi->plane; h->hi.nyl = hi->nyl; }
+    return ALB_OK;
+}
+
+int alb_create_multi(int nx, int ny, const int *devices, int ndev, alb_handle **out_slabs) {
+    if (!out_slabs || !devices || ndev < 1 || ndev > ny) {
+        g_create_error = "alb_create_multi: need 1 <= ndev <= ny, devices and out_slabs non-NULL";
+        return ALB_ERR_INVALID;
+    }
+    for (int k = 0; k < ndev; k++) out_slabs[k] = nullptr;
+    const int base = ny / ndev, rem = ny % ndev;
+    int y0 = 0, rc = ALB_OK;
+    for (int k = 0; k < ndev && rc == ALB_OK; k++) {
+        const int n = base + (k < rem ? 1 : 0);
+        rc = alb_create_slab(nx, ny, y0, n, devices[k], &out_slabs[k]);
+        y0 += n;
+    }
+    for (int k = 0; k < ndev && rc == ALB_OK; k++) {
+        rc = alb_connect_local(out_slabs[k], k > 0 ? out_slabs[k - 1] : nullptr, k + 1 < ndev ? out_slabs[k + 1] : nullptr);
+        if (rc != ALB_OK) g_create_error = out_slabs[k]->err;
+    }
+    if (rc != ALB_OK) {
+        for (int k = 0; k < ndev; k++) {
+            if (out_slabs[k]) free_handle(out_slabs[k]);
+            out_slabs[k] = nullptr;
+        }
+    }
+    return rc;
+}
+
+int alb_step_multi(alb_handle **slabs, int nslabs, int nsteps) {
+    if (!slabs || nslabs < 1 || nsteps < 0) return ALB_ERR_INVALID;
+    // Chunks keep every slab's stream fed while bounding how far one slab is enqueued ahead.  Slabs
+    // that share a GPU are stepped one step at a time: then every flag a wait kernel needs was
+    // signalled by work enqueued EARLIER, so hardware queues shared between streams cannot deadlock.
+    int chunk = 16;
+    for (int a = 0; a < nslabs; a++)
+        for (int b = a + 1; b < nslabs; b++)
+            if (slabs[a] && slabs[b] && slabs[a]->device == slabs[b]->device) chunk = 1;
+    for (int done = 0; done < nsteps; done += chunk) {
+        const int n = nsteps - done < chunk ? nsteps - done : chunk;
+        for (int k = 0; k < nslabs; k++) {
+            int rc = alb_step(slabs[k], n);
+            if (rc != ALB_OK) return rc;
+        }
+    }
     return ALB_OK;
 }
 

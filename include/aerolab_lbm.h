@@ -218,6 +218,14 @@ int alb_particles_get(alb_handle *h, double *out8, int *n);
 /* In-process neighbours (several slabs driven by one process). lo = the slab
  * below (smaller y), hi = the slab above; NULL at the lattice edge. */
 int alb_connect_local(alb_handle *h, alb_handle *lo, alb_handle *hi);
+/* One process driving several GPUs: ndev slabs with (nearly) equal row counts on
+ * the given devices, already connected (peer access is enabled as needed);
+ * out_slabs receives ndev handles, bottom slab first.  Devices may repeat
+ * (several slabs on one GPU).  Geometry calls (alb_rasterize, alb_set_mask) go
+ * to every slab; alb_step_multi steps them all; partial diagnostics
+ * (alb_forces_partial, alb_stats_partial, alb_get_me_history) add up. */
+int alb_create_multi(int nx, int ny, const int *devices, int ndev, alb_handle **out_slabs);
+int alb_step_multi(alb_handle **slabs, int nslabs, int nsteps);
 /* Cross-process neighbours through CUDA IPC: export a blob, exchange it by any
  * means (torch.distributed all_gather in the Python package), connect. */
 int alb_ipc_export(alb_handle *h, void *blob /* ALB_IPC_BYTES */);

@@ -56,3 +56,15 @@ def test_distributed_tunnel_torchrun(al, halo):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "bitwise_ok=True" in r.stdout
+
+
+def test_create_multi_across_devices(al):
+    n = min(al.device_count(), 4)
+    nx, ny = 1024, 400
+    whole = al.WindTunnel(nx, ny, 0)
+    whole.load_shape("naca4412", alpha=6.0)
+    multi = al.LocalMultiTunnel(nx, ny, list(range(n)))
+    multi.load_shape("naca4412", alpha=6.0)
+    whole.step(64); multi.step(64); multi.sync()
+    assert_bitwise(multi.populations(), whole.populations(), "multi-GPU populations")
+    multi.close()

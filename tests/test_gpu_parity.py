@@ -536,3 +536,25 @@ def test_randomized_configurations_bitwise(al):
             assert f["CL_raw"] == pytest.approx(w["CL_raw"], rel=1e-11, abs=1e-11), what
         assert t.clamp_hits() == o.clamp_hits, what
         t.close()
+
+
+def test_create_multi_in_process(al):
+    """alb_create_multi: several slabs driven by one process (here all on device 0; on a multi-GPU
+    box tests/test_gpu_multi.py spreads them over the devices)."""
+    nx, ny = 640, 301
+    whole = al.WindTunnel(nx, ny, 0)
+    whole.load_shape("naca2412", alpha=11.0)
+    multi = al.LocalMultiTunnel(nx, ny, [0, 0, 0])
+    assert [t.ny_local for t in multi.slabs] == [101, 100, 100] and [t.y0 for t in multi.slabs] == [0, 101, 201]
+    multi.load_shape("naca2412", alpha=11.0)
+    assert np.array_equal(multi.mask(), whole.mask())
+    whole.step(45); multi.step(45); multi.sync()
+    assert_bitwise(multi.populations(), whole.populations(), "multi populations")
+    for a, b in zip(multi.macro(), whole.macro()):
+        assert_bitwise(a, b, "multi macro")
+    f, w = multi.forces_raw(), whole.forces()
+    assert (f["surf"], f["rev"]) == (w["surf"], w["rev"])
+    assert f["CL_raw"] == pytest.approx(w["CL_raw"], rel=1e-12) and f["CL_me"] == pytest.approx(w["CL_me"], rel=1e-15)
+    multi.close()
+    with pytest.raises(al.AerolabLbmError):
+        al.LocalMultiTunnel(64, 32, [0, 7])
