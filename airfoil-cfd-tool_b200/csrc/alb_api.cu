@@ -130,6 +130,9 @@ struct alb_handle {
     if (cudaSetDevice((h)->device) != cudaSuccess) return (h)->fail(ALB_ERR_CUDA, "cudaSetDevice")
 #define ARG(cond, msg) \
     if (!(cond)) return h->fail(ALB_ERR_INVALID, msg)
+// state-changing calls are not allowed between alb_frames_enqueue and alb_frames_collect
+#define NO_PENDING_FRAMES(h) \
+    if ((h)->frames_pending) return (h)->fail(ALB_ERR_STATE, "frames are in flight: call alb_frames_collect first")
 
 namespace {
 
@@ -421,7 +424,8 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
     if (!out) return ALB_ERR_INVALID;
     *out = nullptr;
     if (nx < 3 || ny_global < 3 || ny_local < 1 || y0 < 0 || y0 + ny_local > ny_global ||
-        ny_global > 65000 || nx > (1 << 24)) {
+        ny_global > 65000 || nx > (1 << 24) ||
+        ((long long)((nx + TASK_CELLS - 1) / TASK_CELLS) * (ny_local + 2)) > 0x7fffffffLL / 2) {
         g_create_error = "alb_create: need 3 <= nx <= 2^24, 3 <= ny <= 65000, 0 <= y0, y0 + ny_local <= ny";
         return ALB_ERR_INVALID;
     }
@@ -535,6 +539,7 @@ int alb_get_dims(const alb_handle *h, int *nx, int *ny_global, int *y0, int *ny_
 
 int alb_set_params(alb_handle *h, double u0, double tau) {
     NEED(h);
+    NO_PENDING_FRAMES(h);
     ARG(isfinite(u0) && isfinite(tau) && (float)tau != 0.0f, "alb_set_params: u0 and tau must be finite, tau != 0");
     if (u0 == h->u0 && tau == h->tau) return ALB_OK;
     int r = ensure_macro(h);
@@ -556,12 +561,14 @@ int alb_get_params(const alb_handle *h, double *u0, double *tau) {
 
 int alb_reset(alb_handle *h, double u0) {
     NEED(h);
+    NO_PENDING_FRAMES(h);
     ARG(isfinite(u0), "alb_reset: u0 must be finite");
     return do_reset(h, u0);
 }
 
 int alb_rasterize_panels(alb_handle *h, const double *xp, const double *yp, int n, uint8_t *mask_out) {
     NEED(h);
+    NO_PENDING_FRAMES(h);
     ARG(xp && yp && n >= 2 && n <= 1024, "alb_rasterize_panels: need 2 <= n <= 1024 panel nodes");
     int r = ensure_macro(h);
     if (r) return r;
@@ -596,6 +603,7 @@ int alb_rasterize(alb_handle *h, const double *xy, int npts, double alpha_deg, u
 
 int alb_set_mask(alb_handle *h, const uint8_t *mask_global) {
     NEED(h);
+    NO_PENDING_FRAMES(h);
     ARG(mask_global, "alb_set_mask: mask is NULL");
     int r = ensure_macro(h);
     if (r) return r;
@@ -755,6 +763,7 @@ static int step_batch(alb_handle *h, int nsteps) {
 
 int alb_step(alb_handle *h, int nsteps) {
     NEED(h);
+    NO_PENDING_FRAMES(h);
     ARG(nsteps >= 0, "alb_step: nsteps must be >= 0");
     if (nsteps == 0) return ALB_OK;
     CK(cudaEventRecord(h->ev0, h->stream));
@@ -878,6 +887,7 @@ int alb_get_populations(alb_handle *h, float *f) {
 
 int alb_set_populations(alb_handle *h, const float *f) {
     NEED(h);
+    NO_PENDING_FRAMES(h);
     ARG(f, "alb_set_populations: input is NULL");
     int r = ensure_macro(h);
     if (r) return r;
@@ -904,6 +914,7 @@ int alb_get_macro(alb_handle *h, float *rho, float *ux, float *uy) {
 
 int alb_set_macro(alb_handle *h, const float *rho, const float *ux, const float *uy) {
     NEED(h);
+    NO_PENDING_FRAMES(h);
     const float *srcs[3] = {rho, ux, uy};
     float *dsts[3] = {h->rho, h->ux, h->uy};
     for (int k = 0; k < 3; k++)
@@ -1221,6 +1232,7 @@ int alb_particles_resize(alb_handle *h, int n) {
 
 int alb_particles_step(alb_handle *h, double dt_ms) {
     NEED(h);
+    NO_PENDING_FRAMES(h);
     ARG(isfinite(dt_ms), "alb_particles_step: dt must be finite");
     if (!h->whole()) return h->fail(ALB_ERR_STATE, "particles need a whole-lattice handle");
     int r = ensure_macro(h);

@@ -558,3 +558,16 @@ def test_create_multi_in_process(al):
     multi.close()
     with pytest.raises(al.AerolabLbmError):
         al.LocalMultiTunnel(64, 32, [0, 7])
+
+
+def test_no_state_change_while_frames_in_flight(al):
+    t = al.WindTunnel(128, 64, 0)
+    t.load_shape("naca0012", alpha=2.0)
+    t.frames_enqueue(5)
+    for call in (lambda: t.step(1), lambda: t.set_u0(0.05), lambda: t.set_alpha(3.0), lambda: t.reset(),
+                 lambda: t.frames_enqueue(2)):
+        with pytest.raises(al.AerolabLbmError):
+            call()
+    s = t.frames_collect()
+    assert s["maxS"].shape == (5,) and t.steps == 20
+    t.step(1)
