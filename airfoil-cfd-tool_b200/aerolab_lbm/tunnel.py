@@ -364,6 +364,17 @@ class WindTunnel:
         self._ck(self._lib.alb_set_external_halo(self._h, int(bool(on))))
         return self
 
+    def selftest_division(self, pairs: int = 1 << 30, seed: int = 1) -> dict:
+        """Compare the kernels' shared-reciprocal division with IEEE division on generated operands."""
+        out = np.zeros(3, dtype=np.uint64)
+        self._ck(self._lib.alb_selftest_division(self._h, int(seed), int(pairs), ptr(out)))
+        return {"checked": int(out[0]), "accepted": int(out[1]), "wrong": int(out[2])}
+
+    def set_double_steps(self, mode: int):
+        """-1 automatic, 0 never, 1 always: two steps per pass over HBM (bit-identical results)."""
+        self._ck(self._lib.alb_set_double_steps(self._h, int(mode)))
+        return self
+
     def halo_ptrs(self):
         """Device addresses (ints) of the rows crossing each face in the CURRENT state:
         dict(send_lo, send_hi, recv_lo, recv_hi), three pointers each, nx floats per row."""

@@ -22,11 +22,15 @@ constexpr int GRAPH_STEPS = 8;                // steps replayed per CUDA-graph l
 constexpr int DIAG_BLOCKS = 148 * 4;          // fixed reduction grid -> deterministic partials
 constexpr int UNIFIED_MAX_TASKS = 148 * 2 * 8;   // one wave of the unified kernel (2 CTAs/SM x 8 tasks)
 constexpr long long WAIT_TIMEOUT_NS = 20LL * 1000 * 1000 * 1000;
+// Lattices at least this wide and this large advance two steps per pass (see step_batch).  Measured:
+// 32768x16384 125 vs 94 GLUPS; 4096x2048 (7 strips, not enough tiles per SM) 74 vs 79 -> stays on single steps.
+constexpr int DOUBLE_MIN_NX = 8192;
+constexpr long long DOUBLE_MIN_CELLS = 32LL << 20;
 
 thread_local std::string g_create_error;
 
 struct Peer {
-    float *base = nullptr;      // the neighbour's population block (f[0] at base, f[1] at base + 9*plane)
+    float *base = nullptr;      // the neighbour's population block (f[k] at base + k*9*plane, k = 0..2)
     int *flags = nullptr;       // the neighbour's flag words (device memory, peer mapped)
     size_t plane = 0;
     int nyl = 0;
@@ -47,10 +51,11 @@ static_assert(sizeof(IpcBlob) <= ALB_IPC_BYTES, "blob too large");
 struct alb_handle {
     int nx = 0, ny_global = 0, y0 = 0, nyl = 0, nrows = 0, pitch = 0, tpr = 0, device = 0;
     size_t plane = 0;
-    char *block = nullptr;        // one allocation: f[0], f[1], flag words (exported through IPC)
-    float *f[2] = {nullptr, nullptr};
+    char *block = nullptr;        // one allocation: f[0], f[1], f[2], flag words (exported through IPC)
+    float *f[3] = {nullptr, nullptr, nullptr};   // ping-pong pair + the intermediate state of the two-pass path
     int *flags = nullptr;         // [0] steps completed by the lower neighbour, [1] by the upper one
     int cur = 0;
+    int parity = 0;               // parity of the NEXT step (momentum-exchange slot); == cur until a double step ran
     float *rho = nullptr, *ux = nullptr, *uy = nullptr;
     bool macro_valid = true;
     bool diag_valid = false;      // h_diag holds the fused statistics/forces of the current state
@@ -69,7 +74,16 @@ struct alb_handle {
     int *gen_list = nullptr;      // TC_GENERAL tasks of this slab, [0] of gen_count = how many
     int *gen_count = nullptr;
     int ngen = 0;
+    // two steps per pass (step2_kernel): task flags, the four task lists of the two-pass path
+    uint8_t *tflags = nullptr, *deep_tmp = nullptr;
+    int *lists[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // see launch_build_lists
+    int *list_counts = nullptr;
+    int nlist[5] = {0, 0, 0, 0, 0};
+    bool solid_synced = false;    // both ping-pong buffers hold the same values on the all-solid tasks (lists[4])
+    int double_mode = -1;         // -1 automatic, 0 never, 1 whenever possible (AEROLAB_LBM_DOUBLE / alb_set_option)
+    int graph_parity = 0;         // h->parity the graph was captured at
     int small_capacity = 0;       // cells the persistent small-lattice kernel can hold on this GPU
+    int nsm = 148;                // SMs of the device
     double u0 = 0.06, tau = 0.58;
     float u0f = 0, tauf = 0, inv_tau = 0, inv_tau_lo = 0;
     float feq0[9];
@@ -174,11 +188,11 @@ void refresh_params(alb_handle *h) {
     host_feq0(h->u0f, h->feq0);
 }
 
-StepParams make_params(alb_handle *h, int src_idx) {
+StepParams make_params(alb_handle *h, int src_idx, int dst_idx = -1, int parity = -1) {
     StepParams p;
     memset(&p, 0, sizeof p);
     p.src = h->f[src_idx];
-    p.dst = h->f[1 - src_idx];
+    p.dst = h->f[dst_idx < 0 ? 1 - src_idx : dst_idx];
     p.info = h->info;
     p.tclass = h->tclass;
     p.gen_list = h->gen_list;
@@ -199,7 +213,7 @@ StepParams make_params(alb_handle *h, int src_idx) {
     p.uy = h->uy;
     p.clamp_hits = h->clamp_hits;
     p.me = h->me;
-    p.parity = src_idx;
+    p.parity = parity < 0 ? src_idx : parity;
     return p;
 }
 
@@ -294,6 +308,10 @@ int rebuild_info(alb_handle *h) {
                          h->ny_global, h->y0 - 1, h->nrows, h->stream));
     // the host needs the number of general tasks to size that kernel's grid (mask changes are rare)
     CK(cudaMemcpyAsync(&h->ngen, h->gen_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(launch_build_lists(h->info, h->tclass, h->deep_tmp, h->tflags, h->lists, h->list_counts, h->pitch, h->nrows,
+                          h->stream));
+    CK(cudaMemcpyAsync(h->nlist, h->list_counts, 5 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    h->solid_synced = false;
     CK(cudaStreamSynchronize(h->stream));
     h->diag_valid = false;      // faces and the solid set changed
     drop_graph(h);              // grid sizes depend on the number of general tasks
@@ -320,6 +338,9 @@ int do_reset(alb_handle *h, double u0) {
     CK(cudaStreamSynchronize(h->stream));   // sync_steps is host memory
     CK(cudaMemsetAsync(h->clamp_hits, 0, sizeof(unsigned long long), h->stream));
     h->cur = 0;
+    h->parity = 0;
+    h->solid_synced = true;     // both buffers were filled alike
+    drop_graph(h);
     h->steps = 0;
     h->frame_counter = 0;
     h->macro_valid = true;
@@ -357,6 +378,10 @@ void free_handle(alb_handle *h) {
     cudaFree(h->tclass);
     cudaFree(h->gen_list);
     cudaFree(h->gen_count);
+    cudaFree(h->tflags);
+    cudaFree(h->deep_tmp);
+    for (auto &l : h->lists) cudaFree(l);
+    cudaFree(h->list_counts);
     cudaFree(h->me);
     cudaFree(h->parts);
     cudaFree(h->d_frame);
@@ -464,12 +489,14 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaEventCreate(&h->ev1));
         CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-        const size_t pop_bytes = sizeof(float) * 18 * h->plane;
+        const size_t pop_bytes = sizeof(float) * 27 * h->plane;
         CK(cudaMalloc(&h->block, pop_bytes + 256));
         h->f[0] = reinterpret_cast<float *>(h->block);
         h->f[1] = h->f[0] + 9 * h->plane;
+        h->f[2] = h->f[0] + 18 * h->plane;
         h->flags = reinterpret_cast<int *>(h->block + pop_bytes);
         CK(cudaMemsetAsync(h->flags, 0, 256, h->stream));
+        CK(cudaMemsetAsync(h->f[2], 0, sizeof(float) * 9 * h->plane, h->stream));   // ghost rows are read before any push
         CK(cudaMalloc(&h->rho, sizeof(float) * h->plane));
         CK(cudaMalloc(&h->ux, sizeof(float) * h->plane));
         CK(cudaMalloc(&h->uy, sizeof(float) * h->plane));
@@ -478,6 +505,10 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaMalloc(&h->tclass, (size_t)h->nrows * h->tpr));
         CK(cudaMalloc(&h->gen_list, sizeof(int) * (size_t)h->nrows * h->tpr));
         CK(cudaMalloc(&h->gen_count, sizeof(int)));
+        CK(cudaMalloc(&h->tflags, (size_t)h->nrows * h->tpr));
+        CK(cudaMalloc(&h->deep_tmp, (size_t)h->nrows * h->tpr));
+        for (auto &l : h->lists) CK(cudaMalloc(&l, sizeof(int) * (size_t)h->nrows * h->tpr));
+        CK(cudaMalloc(&h->list_counts, 5 * sizeof(int)));
         CK(cudaMalloc(&h->me, sizeof(MeState)));
         CK(cudaMalloc(&h->clamp_hits, sizeof(unsigned long long)));
         CK(cudaMalloc(&h->d_xp, sizeof(double) * 1024));
@@ -505,7 +536,9 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         if (r) return r;
         CK(cudaStreamSynchronize(h->stream));
         h->small_capacity = small_lattice_capacity(device);
+        CK(cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device));
         h->use_graph = getenv("AEROLAB_LBM_NO_GRAPH") == nullptr;   // A/B switch for measurements
+        if (const char *e = getenv("AEROLAB_LBM_DOUBLE")) h->double_mode = atoi(e) != 0 ? 1 : 0;
         return ALB_OK;
     };
     rc = body();
@@ -638,9 +671,35 @@ int alb_get_panels(const alb_handle *h, double *xp, double *yp) {
 
 namespace {
 
+void set_peers(alb_handle *h, StepParams &p, int dst_idx) {
+    if (h->lo.base) {
+        p.peer_lo_dst = h->lo.base + (size_t)dst_idx * 9 * h->lo.plane;
+        p.peer_lo_plane = h->lo.plane;
+        p.peer_lo_row = (size_t)(h->lo.nyl + 1) * h->pitch;
+    }
+    if (h->hi.base) {
+        p.peer_hi_dst = h->hi.base + (size_t)dst_idx * 9 * h->hi.plane;
+        p.peer_hi_plane = h->hi.plane;
+        p.peer_hi_row = 0;
+    }
+}
+
+// my step k needs the neighbours' k completed steps: their edge rows of state k are in my ghost
+// rows, and they no longer read the ghost rows I am about to overwrite.
+void halo_wait(alb_handle *h, long long sync_step, cudaStream_t st) {
+    wait_kernel<<<1, 1, 0, st>>>(h->lo.base ? h->flags + 0 : nullptr, h->hi.base ? h->flags + 1 : nullptr,
+                                 (int)sync_step, h->d_err, WAIT_TIMEOUT_NS);
+}
+// I am the UPPER neighbour of lo (its flags[1]) and the LOWER neighbour of hi (its flags[0])
+void halo_signal(alb_handle *h, long long steps_done, cudaStream_t st) {
+    signal_kernel<<<1, 1, 0, st>>>(h->lo.flags ? h->lo.flags + 1 : nullptr, h->hi.flags ? h->hi.flags + 0 : nullptr,
+                                   (int)steps_done);
+}
+
 // Enqueue one step that reads buffer src_idx.  Used directly and under stream capture.
-int issue_step(alb_handle *h, int src_idx, bool halo, long long sync_step, bool diag) {
-    StepParams p = make_params(h, src_idx);
+int issue_step(alb_handle *h, int src_idx, int parity, bool halo, long long sync_step, bool diag) {
+    StepParams p = make_params(h, src_idx, 1 - src_idx, parity);
+    h->solid_synced = false;    // solid cells swap their populations: the two buffers differ there now
     if (diag) {
         // the last step of a batch also reduces the statistics / face sums of the state it writes
         if (!h->diag_prearmed)
@@ -649,22 +708,8 @@ int issue_step(alb_handle *h, int src_idx, bool halo, long long sync_step, bool 
         arm_diag(h, p);
     }
     if (halo) {
-        // my step k needs the neighbours' k completed steps: their edge rows of state k are in
-        // my ghost rows, and they no longer read the ghost rows I am about to overwrite.
-        wait_kernel<<<1, 1, 0, h->stream>>>(h->lo.base ? h->flags + 0 : nullptr,
-                                            h->hi.base ? h->flags + 1 : nullptr, (int)sync_step, h->d_err,
-                                            WAIT_TIMEOUT_NS);
-        const int dst_idx = 1 - src_idx;
-        if (h->lo.base) {
-            p.peer_lo_dst = h->lo.base + (size_t)dst_idx * 9 * h->lo.plane;
-            p.peer_lo_plane = h->lo.plane;
-            p.peer_lo_row = (size_t)(h->lo.nyl + 1) * h->pitch;
-        }
-        if (h->hi.base) {
-            p.peer_hi_dst = h->hi.base + (size_t)dst_idx * 9 * h->hi.plane;
-            p.peer_hi_plane = h->hi.plane;
-            p.peer_hi_row = 0;
-        }
+        halo_wait(h, sync_step, h->stream);
+        set_peers(h, p, 1 - src_idx);
     }
     if (p.ntasks <= UNIFIED_MAX_TASKS) {
         // small lattice: launch-latency bound, one launch for both paths
@@ -680,22 +725,96 @@ int issue_step(alb_handle *h, int src_idx, bool halo, long long sync_step, bool 
         CK(launch_step_fast(p, h->stream));
         if (p.ngen > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     }
-    if (halo) {
-        // I am the UPPER neighbour of lo (its flags[1]) and the LOWER neighbour of hi (its flags[0])
-        signal_kernel<<<1, 1, 0, h->stream>>>(h->lo.flags ? h->lo.flags + 1 : nullptr,
-                                              h->hi.flags ? h->hi.flags + 0 : nullptr, (int)(sync_step + 1));
-    }
+    if (halo) halo_signal(h, sync_step + 1, h->stream);
     return ALB_OK;
+}
+
+// Enqueue TWO steps that read buffer src_idx and leave the result in buffer 1 - src_idx.
+//   main stream: step2_kernel -- every deep task, two steps per pass over HBM (36 B per cell update)
+//   aux stream:  the two-pass path for everything else: pass 1 writes the intermediate state of the
+//                shallow tasks and their neighbours into f[2], pass 2 advances the shallow tasks from
+//                f[2] into the destination.  The slab halo (edge rows are always shallow) is pushed
+//                by these passes exactly as by single steps; step2_kernel only has to wait for the
+//                neighbours' previous step (it reads the ghost rows of the source state).
+int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sync_step, bool copy_solid) {
+    const int dst_idx = 1 - src_idx;
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    for (int pass = 0; pass < 2; pass++) {
+        StepParams p = pass == 0 ? make_params(h, src_idx, 2, parity) : make_params(h, 2, dst_idx, parity ^ 1);
+        if (halo) {
+            halo_wait(h, sync_step + pass, h->aux);
+            set_peers(h, p, pass == 0 ? 2 : dst_idx);
+        }
+        p.gen_list = h->lists[2 * pass];
+        p.ngen = h->nlist[2 * pass];
+        CK(launch_step_fast_list(p, h->aux));
+        p.gen_list = h->lists[2 * pass + 1];
+        p.ngen = h->nlist[2 * pass + 1];
+        CK(launch_step_general(p, h->aux));
+        if (pass == 1 && copy_solid && h->nlist[4] > 0) {
+            // all-solid tasks return to their state after two steps: copy, unless the destination
+            // still holds the same values from the previous double step
+            StepParams c = make_params(h, src_idx, dst_idx, parity);
+            c.gen_list = h->lists[4];
+            c.ngen = h->nlist[4];
+            CK(launch_copy_tasks(c, h->aux));
+        }
+        // the second signal also tells the neighbours that they may overwrite the ghost rows of the
+        // SOURCE state, which step2_kernel reads: it is given on the main stream after the join
+        if (halo && pass == 0) halo_signal(h, sync_step + 1, h->aux);
+    }
+    CK(cudaEventRecord(h->ev_join, h->aux));
+    Step2Params q;
+    memset(&q, 0, sizeof q);
+    q.src = h->f[src_idx];
+    q.dst = h->f[dst_idx];
+    q.tflags = h->tflags;
+    q.plane = h->plane;
+    q.pitch = h->pitch;
+    q.tpr = h->tpr;
+    q.nyl = h->nyl;
+    q.tau = h->tauf;
+    q.inv_tau = h->inv_tau;
+    q.inv_tau_lo = h->inv_tau_lo;
+    q.clamp_hits = h->clamp_hits;
+    step2_plan(q, h->nsm);
+    // the fused kernel reads the ghost rows of the source state (intermediate rows 1 and nyl)
+    if (halo) halo_wait(h, sync_step, h->stream);
+    CK(launch_step2(q, h->stream));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    if (halo) halo_signal(h, sync_step + 2, h->stream);
+    return ALB_OK;
+}
+
+// Two steps per pass pay off once the fused kernel has enough tiles to fill the GPU; all slabs of
+// a lattice must decide alike (they address each other's buffers by index), so the rule only
+// looks at the global lattice and the environment.
+bool double_steps_enabled(const alb_handle *h) {
+    if (h->external_halo) return false;
+    if (h->double_mode >= 0) return h->double_mode != 0;
+    return h->nx >= DOUBLE_MIN_NX && (long long)h->nx * h->ny_global >= DOUBLE_MIN_CELLS;
 }
 
 // Capture GRAPH_STEPS steps starting from buffer 0.  Every address the kernels touch depends only
 // on the step's parity (MeState), so the instantiated graph can be replayed for the whole run; it
 // is dropped whenever a kernel argument changes (mask, parameters, neighbours).
-int capture_graph(alb_handle *h) {
+int capture_graph(alb_handle *h, bool doubles) {
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     int r = ALB_OK;
-    for (int s = 0; s < GRAPH_STEPS && r == ALB_OK; s++) r = issue_step(h, s & 1, false, 0, false);
+    int cur = 0, parity = h->parity;
+    for (int s = 0; s < GRAPH_STEPS && r == ALB_OK;) {
+        if (doubles) {
+            r = issue_double(h, cur, parity, false, 0, s == 0);   // replayed after anything: the first one always copies
+            s += 2;
+        } else {
+            r = issue_step(h, cur, parity, false, 0, false);
+            parity ^= 1;
+            s += 1;
+        }
+        cur ^= 1;
+    }
     cudaError_t e = cudaStreamEndCapture(h->stream, &g);
     if (r != ALB_OK) {
         if (g) cudaGraphDestroy(g);
@@ -708,6 +827,7 @@ int capture_graph(alb_handle *h) {
         h->graph = nullptr;
         return h->fail(ALB_ERR_CUDA, "cudaGraphInstantiate", e);
     }
+    h->graph_parity = h->parity;
     return ALB_OK;
 }
 
@@ -719,37 +839,54 @@ extern "C" {
 static int step_batch(alb_handle *h, int nsteps) {
     const bool halo = !h->external_halo && (h->lo.base || h->hi.base);
     int left = nsteps;
-    const bool persistent = h->whole() && !halo && !h->external_halo && nsteps >= 2 &&
+    const bool doubles = double_steps_enabled(h);
+    const bool persistent = !doubles && h->whole() && !halo && !h->external_halo && nsteps >= 2 &&
                             (long long)h->nx * h->nyl <= h->small_capacity;
     if (persistent) {
         // small lattice: the whole batch of steps in ONE cooperative launch (grid barrier per
         // step); its last iteration also reduces the statistics / face sums of the final state
         // (measured: as fast as a kernel without that code, and no extra launch)
-        StepParams p = make_params(h, h->cur);
+        StepParams p = make_params(h, h->cur);        // parity == cur: no double step ever ran on this handle
         if (!h->diag_prearmed)
             CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc) * DIAG_SLOTS, cudaMemcpyHostToDevice, h->stream));
         h->diag_prearmed = false;
         arm_diag(h, p);
         CK(launch_small_lattice(p, h->f[0], h->f[1], h->cur, nsteps, h->stream));
         h->cur = (h->cur + nsteps) & 1;
+        h->parity = h->cur;
+        h->solid_synced = false;
         left = 0;
     }
     const bool use_graph = !persistent && !halo && !h->external_halo && h->use_graph && nsteps >= GRAPH_STEPS + 1;
     int done = nsteps - left;
     while (left > 0) {
         if (use_graph && h->cur == 0 && left > GRAPH_STEPS) {   // ">": the last step is issued below, with diagnostics
+            if (h->graph && h->graph_parity != h->parity) drop_graph(h);
             if (!h->graph) {
-                int r = capture_graph(h);
+                int r = capture_graph(h, doubles);
                 if (r) return r;
             }
             CK(cudaGraphLaunch(h->graph, h->stream));
-            left -= GRAPH_STEPS;
+            h->solid_synced = doubles;
+            left -= GRAPH_STEPS;           // an even number of steps: cur and parity are unchanged
             done += GRAPH_STEPS;
             continue;
         }
-        int r = issue_step(h, h->cur, halo, h->sync_steps + done, left == 1);
+        if (doubles && left >= 3) {
+            // the batch must END with a single step: its source state stays intact in the other
+            // buffer, which the lazy macroscopic pass relies on
+            int r = issue_double(h, h->cur, h->parity, halo, h->sync_steps + done, !h->solid_synced);
+            if (r) return r;
+            h->solid_synced = true;
+            h->cur = 1 - h->cur;           // two steps: parity unchanged
+            left -= 2;
+            done += 2;
+            continue;
+        }
+        int r = issue_step(h, h->cur, h->parity, halo, h->sync_steps + done, left == 1);
         if (r) return r;
         h->cur = 1 - h->cur;
+        h->parity ^= 1;
         left--;
         done++;
     }
@@ -818,7 +955,7 @@ int alb_frames_enqueue(alb_handle *h, int nframes, int steps_per_frame, int forc
         if (r) return r;
         h->frame_counter++;
         const int do_forces = forces_every > 0 && (h->frame_counter % forces_every == 0);
-        CK(launch_frame_finalize(h->d_diag, h->d_diag_pub, h->me, 1 - h->cur, h->d_frame, do_forces, h->u0,
+        CK(launch_frame_finalize(h->d_diag, h->d_diag_pub, h->me, h->parity ^ 1, h->d_frame, do_forces, h->u0,
                                  h->qdyn(), h->d_rows + (size_t)FRAME_ROW * f, h->stream));
         h->diag_prearmed = true;
     }
@@ -898,6 +1035,7 @@ int alb_set_populations(alb_handle *h, const float *f) {
                              h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->diag_valid = false;
+    h->solid_synced = false;
     return ALB_OK;
 }
 
@@ -1138,7 +1276,7 @@ int alb_get_me_history(alb_handle *h, int n, long long *fxfy) {
             CK(cudaMemcpy(fxfy + 2 * k, &h->me->ring[step % ME_RING][0], sizeof(long long) * 2, cudaMemcpyDeviceToHost));
         } else {
             // the last step: still in the accumulator of its parity (= the buffer it read from)
-            const int parity = 1 - h->cur;
+            const int parity = h->parity ^ 1;
             fxfy[2 * k] = head.acc[parity][0];
             fxfy[2 * k + 1] = head.acc[parity][1];
         }
@@ -1345,7 +1483,7 @@ int alb_ipc_export(alb_handle *h, void *blob) {
     CK(cudaIpcGetMemHandle(&b.mem, h->block));
     b.nx = h->nx; b.nyl = h->nyl; b.pitch = h->pitch; b.device = h->device;
     b.plane = h->plane;
-    b.flags_offset_bytes = sizeof(float) * 18 * h->plane;
+    b.flags_offset_bytes = sizeof(float) * 27 * h->plane;
     b.magic = 0x414c4231;
     memset(blob, 0, ALB_IPC_BYTES);
     memcpy(blob, &b, sizeof b);
@@ -1421,6 +1559,30 @@ int alb_halo_ptrs(alb_handle *h, void **send_lo3, void **send_hi3, void **recv_l
 int alb_set_external_halo(alb_handle *h, int on) {
     if (!h) return ALB_ERR_INVALID;
     h->external_halo = on != 0;
+    return ALB_OK;
+}
+
+int alb_selftest_division(alb_handle *h, unsigned long long seed, long long pairs, unsigned long long *out3) {
+    NEED(h);
+    ARG(out3 && pairs > 0, "alb_selftest_division: need pairs > 0 and an output array");
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+    const int nblocks = 148 * 8, iters = (int)((pairs + (long long)nblocks * 256 - 1) / ((long long)nblocks * 256));
+    cudaError_t e = cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), h->stream);
+    if (e == cudaSuccess) e = launch_div_selftest(seed, nblocks, iters, d, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out3, d, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return h->fail(ALB_ERR_CUDA, "alb_selftest_division", e);
+    return ALB_OK;
+}
+
+int alb_set_double_steps(alb_handle *h, int mode) {
+    if (!h) return ALB_ERR_INVALID;
+    NO_PENDING_FRAMES(h);
+    ARG(mode >= -1 && mode <= 1, "alb_set_double_steps: mode must be -1, 0 or 1");
+    if (mode != h->double_mode) drop_graph(h);
+    h->double_mode = mode;
     return ALB_OK;
 }
 

@@ -111,6 +111,30 @@ struct StepParams {
     size_t peer_hi_row;      // float offset of its lower ghost row (row 0)
 };
 
+// Task flags of the two-steps-per-pass path (see step2_kernel in alb_step.cu), one byte per warp
+// task [nrows][tpr]:
+//   TF_DEEP  every cell of the task and every cell within one cell of it is a plain interior fluid
+//            cell (type fluid, no solid pull source) and the row is not a slab edge row: the fused
+//            kernel may write its state two steps ahead
+//   TF_NEED  some task of the 3x3 task neighbourhood is deep: the fused kernel needs the
+//            intermediate (one step ahead) state of this task
+constexpr unsigned TF_DEEP = 1, TF_NEED = 2;
+// list entries of the two-pass path: bit 30 = "clamp hits of this task are counted elsewhere"
+constexpr int LIST_NOHIT = 1 << 30, LIST_ID_MASK = LIST_NOHIT - 1;
+
+struct Step2Params {
+    const float *__restrict__ src;
+    float *__restrict__ dst;
+    const uint8_t *__restrict__ tflags;
+    size_t plane;
+    int pitch, tpr, nyl;
+    int wo;                  // output columns per strip (multiple of 4, <= 128*K - 8)
+    int hs;                  // output rows per segment
+    int nstrips, ntiles;
+    float tau, inv_tau, inv_tau_lo;
+    unsigned long long *clamp_hits;
+};
+
 struct Handle;
 
 // Device-side mirror of the page's sticky host state (autoscale values HTML:593, force EMAs
@@ -142,6 +166,12 @@ cudaError_t launch_step_fast(const StepParams &p, cudaStream_t s);
 cudaError_t launch_step_general(const StepParams &p, cudaStream_t s);
 cudaError_t launch_step_unified(const StepParams &p, cudaStream_t s);
 cudaError_t launch_macro(const StepParams &p, cudaStream_t s);
+cudaError_t launch_step_fast_list(const StepParams &p, cudaStream_t s);   // p.gen_list/p.ngen = the list
+cudaError_t launch_copy_tasks(const StepParams &p, cudaStream_t s);       // dst = src on the listed tasks
+// geometry of the fused two-step kernel for a pitch x nyl slab: fills wo/hs/nstrips/ntiles
+void step2_plan(Step2Params &p, int nsm);
+cudaError_t launch_step2(const Step2Params &p, cudaStream_t s);
+cudaError_t launch_div_selftest(unsigned long long seed, int nblocks, int iters, unsigned long long *d_out3, cudaStream_t s);
 int small_lattice_capacity(int device);
 cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps, cudaStream_t s);
 void host_feq0(float u0, float *out9);
@@ -153,6 +183,11 @@ cudaError_t launch_raster(const double *d_xp, const double *d_yp, int n, uint8_t
 cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tclass, int *gen_list,
                               int *gen_count, int pitch, int nx, int ny_global, int gy_first, int nrows,
                               cudaStream_t s);
+
+// lists[5] = pass-1 fast, pass-1 general, pass-2 fast, pass-2 general, all-solid (copied, not stepped);
+// counts = int[5] (device)
+cudaError_t launch_build_lists(const uint16_t *info, const uint8_t *tclass, uint8_t *deep_tmp, uint8_t *tflags,
+                               int *const lists[5], int *counts, int pitch, int nrows, cudaStream_t s);
 
 // alb_diag.cu
 struct DiagScratch {

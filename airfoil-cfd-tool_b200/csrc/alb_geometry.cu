@@ -198,6 +198,77 @@ __global__ void build_tclass_kernel(const uint16_t *__restrict__ info, uint8_t *
     }
 }
 
+
+// ---- task sets of the two-steps-per-pass path (step2_kernel, alb_step.cu) -----------------------
+// A cell is "plain" when its info word is 0: interior fluid, no solid pull source, not padding.
+// A task is deep when every cell within one cell of it (its own 128 cells, the last cell of the
+// task to its left, the first cell of the task to its right, in rows j-1, j, j+1) is plain, and
+// the row is neither the first nor the last owned row (those need the neighbouring slab's
+// intermediate state, or are the equilibrium border rows of a whole lattice).
+__global__ void build_deep_kernel(const uint16_t *__restrict__ info, const uint8_t *__restrict__ tclass,
+                                  uint8_t *__restrict__ deep, int pitch, int nrows) {
+    const int tpr = pitch / TASK_CELLS;
+    const int task = blockIdx.x * blockDim.x + threadIdx.x;
+    if (task >= tpr * nrows) return;
+    const int j = task / tpr, s = task - j * tpr;
+    bool d = j >= 2 && j <= nrows - 3 && s >= 1 && s <= tpr - 2;
+    if (d) {
+        for (int jj = j - 1; jj <= j + 1; jj++) {
+            d = d && tclass[jj * tpr + s] == TC_FLUID;
+            d = d && info[(size_t)jj * pitch + s * TASK_CELLS - 1] == 0;
+            d = d && info[(size_t)jj * pitch + (s + 1) * TASK_CELLS] == 0;
+        }
+    }
+    deep[task] = d ? 1 : 0;
+}
+
+// warp-aggregated append of (id | extra) for the lanes with pred set
+__device__ __forceinline__ void list_append(int *list, int *count, bool pred, int value) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (pred) list[base + __popc(m & ((1u << lane) - 1))] = value;
+}
+
+// Pass 1 of the two-pass path produces the intermediate state of every task within one task of a
+// shallow (= not deep) task; pass 2 advances the shallow tasks themselves.  Deep tasks that are
+// in pass 1 only as neighbours carry LIST_NOHIT: the fused kernel counts their clamp hits.
+// All-solid tasks are left out of both passes: a solid cell only swaps its own populations with
+// their opposites (HTML:287-294) and nobody ever pulls from it, so after TWO steps it is back
+// where it was -- such tasks (list 4) are just copied when the destination buffer does not hold
+// their values already.  (Not the last two tasks of a row: the outlet cell copies the populations
+// of its left neighbour whatever that is, HTML:301-312.)
+__global__ void build_lists_kernel(const uint8_t *__restrict__ tclass, const uint8_t *__restrict__ deep,
+                                   uint8_t *__restrict__ tflags, int *l1f, int *l1g, int *l2f, int *l2g, int *lsol,
+                                   int *counts, int tpr, int nrows) {
+    const int task = blockIdx.x * blockDim.x + threadIdx.x;   // blockDim is a multiple of 32: whole warps
+    const bool valid = task < tpr * nrows;
+    const int j = valid ? task / tpr : 0, s = valid ? task - j * tpr : 0;
+    const bool owned = valid && j >= 1 && j <= nrows - 2;
+    bool any_shallow = false, any_deep = false, is_deep = false, gen = false, solid = false;
+    if (owned) {
+        is_deep = deep[task] != 0;
+        gen = tclass[task] == TC_GENERAL;
+        solid = tclass[task] == TC_SOLID && s < tpr - 2;
+        for (int jj = max(1, j - 1); jj <= min(nrows - 2, j + 1); jj++)
+            for (int ss = max(0, s - 1); ss <= min(tpr - 1, s + 1); ss++) {
+                const bool d = deep[jj * tpr + ss] != 0;
+                any_deep |= d;
+                any_shallow |= !d;
+            }
+    }
+    if (valid) tflags[task] = (uint8_t)((is_deep ? TF_DEEP : 0u) | (any_deep ? TF_NEED : 0u));
+    const int id = (j - 1) * tpr + s;
+    list_append(l1f, counts + 0, owned && any_shallow && !gen && !solid, id | (is_deep ? LIST_NOHIT : 0));
+    list_append(l1g, counts + 1, owned && any_shallow && gen, id);
+    list_append(l2f, counts + 2, owned && !is_deep && !gen && !solid, id);
+    list_append(l2g, counts + 3, owned && !is_deep && gen, id);
+    list_append(lsol, counts + 4, owned && solid, id);
+}
+
 }  // namespace
 
 cudaError_t launch_raster(const double *d_xp, const double *d_yp, int n, uint8_t *mask, int pitch,
@@ -217,6 +288,19 @@ cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tcla
     if (e != cudaSuccess) return e;
     const int ntask = (pitch / TASK_CELLS) * nrows;
     build_tclass_kernel<<<(ntask + 7) / 8, 256, 0, s>>>(info, tclass, gen_list, gen_count, pitch, nrows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_lists(const uint16_t *info, const uint8_t *tclass, uint8_t *deep_tmp, uint8_t *tflags,
+                               int *const lists[5], int *counts, int pitch, int nrows, cudaStream_t s) {
+    const int tpr = pitch / TASK_CELLS, ntask = tpr * nrows;
+    build_deep_kernel<<<(ntask + 255) / 256, 256, 0, s>>>(info, tclass, deep_tmp, pitch, nrows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(counts, 0, 5 * sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    build_lists_kernel<<<(ntask + 255) / 256, 256, 0, s>>>(tclass, deep_tmp, tflags, lists[0], lists[1], lists[2],
+                                                           lists[3], lists[4], counts, tpr, nrows);
     return cudaGetLastError();
 }
 

@@ -243,6 +243,28 @@ int alb_halo_ptrs(alb_handle *h, void **send_lo3, void **send_hi3,
  * between single steps with alb_halo_ptrs(). */
 int alb_set_external_halo(alb_handle *h, int on);
 
+
+/* ---- execution strategy (no effect on results) ------------------------------ */
+
+/* Two LBM steps per pass over HBM (temporal blocking): the
+ * deep interior of the lattice is advanced by a fused two-step kernel, everything
+ * near borders, the body and slab edges by two list-driven single-step passes.
+ * Bit-identical to single steps.  mode: -1 automatic (lattices at least 8192 wide
+ * with 32 Mi cells or more),
+ * 0 never, 1 whenever a batch has three or more steps left.  All slabs of one
+ * lattice must use the same mode.  The environment variable AEROLAB_LBM_DOUBLE
+ * (0/1) sets the initial mode of new handles. */
+int alb_set_double_steps(alb_handle *h, int mode);
+
+/* Self-test of the shared-reciprocal division the fused kernels use for
+ * u = j / rho: runs it on about `pairs` generated operand
+ * triples (lattice-like values, the whole accepted exponent range and beyond,
+ * quotients next to rounding boundaries, zeros/inf/NaN) and compares every
+ * accepted result with IEEE division.  out3 = {checked, accepted, wrong};
+ * wrong must be 0. */
+int alb_selftest_division(alb_handle *h, unsigned long long seed, long long pairs,
+                          unsigned long long *out3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,21 @@ for _ in range(10):
     a.step(1); b.step(1)
 a.sync(); b.sync()
 big = al.WindTunnel(4096, 600, 0); big.load_shape("naca4412", alpha=10.0); big.step(3); big.forces(); big.sync()
+# two steps per pass: fused kernel (strip margins, last strip, short last segment), list-driven passes, solid copies
+for nx, ny in ((320, 160), (641, 131), (1279, 5), (1281, 140), (2500, 260), (130, 3)):
+    t = al.WindTunnel(nx, ny, 0)
+    t.set_double_steps(1)
+    t.load_shape("naca4412", alpha=10.0)
+    for n in (3, 4, 11, 1, 5):
+        t.step(n)
+    t.macro(); t.forces(); t.update_stats(); t.sync()
+    t.close()
+a = al.WindTunnel(700, 90, 0, y0=0, ny_local=40); b = al.WindTunnel(700, 90, 0, y0=40, ny_local=50)
+for s in (a, b): s.set_double_steps(1); s.load_shape("naca0012", alpha=4.0)
+a.connect_local(None, b); b.connect_local(a, None)
+for _ in range(3):
+    a.step(5); b.step(5)
+a.sync(); b.sync()
 print("BOUNDS_OK")
 """ % PKG_DIR
 

@@ -1,0 +1,20 @@
+"""The fused kernels compute ux = jx/rho, uy = jy/rho with a shared reciprocal (div_pair in
+alb_step.cu) instead of two generic divisions.  Inside its accepted operand range it must equal
+IEEE division bit for bit; outside it must decline (the kernels then divide for real)."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_shared_reciprocal_division_matches_ieee(built_lib):
+    import aerolab_lbm as al
+    with al.WindTunnel(64, 32, 0) as t:
+        total = {"checked": 0, "accepted": 0, "wrong": 0}
+        for seed in (1, 2, 3, 4):
+            r = t.selftest_division(pairs=3 << 30, seed=seed)      # two quotients per operand triple
+            for k in total:
+                total[k] += r[k]
+    assert total["wrong"] == 0, total
+    assert total["checked"] >= 4 * (3 << 30)
+    # most lattice-like and boundary-case operands are accepted; the special values are not
+    assert 0.5 * total["checked"] < total["accepted"] < total["checked"], total
