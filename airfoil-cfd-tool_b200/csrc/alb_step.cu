@@ -68,6 +68,13 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef ALB_S2_NST
 #define ALB_S2_NST 3
 #endif
+// step2_kernel: 1 = the A warps prefetch their next task with TMA bulk copies into private shared-memory
+// staging instead of loading it into registers just before the barrier.  Measured on 32768x16384:
+// long_scoreboard stalls drop from 15 % to 3 % of the samples, but the step is SLOWER (116 vs 125 GLUPS;
+// a cp.async version: 116-123) -- see DESIGN.md section 4.2.
+#ifndef ALB_S2_ASYNC
+#define ALB_S2_ASYNC 0
+#endif
 
 
 // ALB_DEBUG_BOUNDS=1 (compute-sanitizer is not available on the pool): every population load and
@@ -758,6 +765,28 @@ copy_tasks_kernel(const __grid_constant__ StepParams p) {
     for (int i = 0; i < 9; i++) ST4(p.dst + i * plane + c, v[i]);
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // loads that must stay where they are written (issued BEFORE the barrier that ends a super-step)
 __device__ __forceinline__ float4 ld4_pinned(const float *p) {
     float4 r;
@@ -769,6 +798,7 @@ __device__ __forceinline__ float ld1_pinned(const float *p) {
     asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
+constexpr int S2_STG = 4 + 128 + 4;    // floats per population in an A warp's private staging buffer
 #define LD4P(ptr) (ALB_CHECK_SRC((ptr), 4), ld4_pinned(ptr))
 #define LD1P(ptr) (ALB_CHECK_SRC((ptr), 1), ld1_pinned(ptr))
 
@@ -781,6 +811,7 @@ step2_kernel(const __grid_constant__ Step2Params p) {
     extern __shared__ float4 ring4[];
     float *ring = reinterpret_cast<float *>(ring4);   // [RS][9][WI]
     constexpr int WI = 128 * K, NW = RB * K, RS = 2 * RB + 2;
+    [[maybe_unused]] float *stage_all = ring + (size_t)RS * 9 * WI;   // ALB_S2_ASYNC: [NW][9][S2_STG]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool role_b = warp >= NW;
     const int w = role_b ? warp - NW : warp;
@@ -809,6 +840,100 @@ step2_kernel(const __grid_constant__ Step2Params p) {
             const int j = a0 + g * RB + r;
             return (g < nga && j <= y1 && inx) ? tfl[(size_t)j * p.tpr] : 0u;
         };
+#if ALB_S2_ASYNC
+        // Each A warp owns a private staging buffer of one task, 9 rows of 4 + 128 + 4 floats (the
+        // task's 128 cells plus the quad to its left and right, so the x-neighbours come along).
+        // As soon as the populations of the current task are in registers, one lane starts nine
+        // 1-D bulk copies (TMA, completion on the warp's own mbarrier) of the NEXT task into the
+        // same buffer: HBM latency is covered by a whole task of arithmetic plus the barrier, no
+        // registers are held, and the per-lane address arithmetic of nine LDG.128 disappears.
+        float *const stg_row = stage_all + (size_t)w * 9 * S2_STG;
+        unsigned long long *const bar = reinterpret_cast<unsigned long long *>(stage_all + (size_t)NW * 9 * S2_STG) + w;
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        // lattice columns [c_lo, c_hi) of this warp's segment incl. the two extra quads, clipped to the row
+        const int seg_x = strip * p.wo - 4 + seg * 128;
+        const int c_lo = max(seg_x - 4, 0), c_hi = min(seg_x + 132, p.pitch);
+        const bool seg_in = c_hi > c_lo;
+        const float *stg = stg_row + 4 + lane * 4;
+        auto issue_loads = [&](int g) {
+            if (lane == 0 && seg_in) {
+                const int j = a0 + g * RB + r;
+                const unsigned bytes = (unsigned)(c_hi - c_lo) * 4u;
+                mbar_arrive_expect_tx(bar, 9u * bytes);
+                const float *g0 = src + (size_t)j * p.pitch + c_lo;
+                float *s0 = stg_row + (c_lo - (seg_x - 4));
+                const int ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+#pragma unroll
+                for (int i = 0; i < 9; i++) {
+                    const float *gs = g0 + i * plane - (ptrdiff_t)ey[i] * p.pitch;
+                    ALB_CHECK_SRC(gs, c_hi - c_lo);
+                    tma_load_1d(s0 + i * S2_STG, gs, bytes, bar);
+                }
+            }
+        };
+        unsigned tf = flags_of(0), tf1 = flags_of(1), phase = 0;
+        bool have = __any_sync(FULL, tf & TF_NEED);
+        if (have) issue_loads(0);
+        for (int g = 0; g <= nga; g++) {
+            const unsigned tf2 = flags_of(g + 2);
+            const bool have_next = __any_sync(FULL, tf1 & TF_NEED);
+            float4 o[9];
+            if (have) {
+                if (seg_in) mbar_wait(bar, phase);
+                phase ^= 1u;
+                const float4 v0 = *reinterpret_cast<const float4 *>(stg + 0 * S2_STG);
+                const float4 v1 = *reinterpret_cast<const float4 *>(stg + 1 * S2_STG);
+                const float4 v2 = *reinterpret_cast<const float4 *>(stg + 2 * S2_STG);
+                const float4 v3 = *reinterpret_cast<const float4 *>(stg + 3 * S2_STG);
+                const float4 v4 = *reinterpret_cast<const float4 *>(stg + 4 * S2_STG);
+                const float4 v5 = *reinterpret_cast<const float4 *>(stg + 5 * S2_STG);
+                const float4 v6 = *reinterpret_cast<const float4 *>(stg + 6 * S2_STG);
+                const float4 v7 = *reinterpret_cast<const float4 *>(stg + 7 * S2_STG);
+                const float4 v8 = *reinterpret_cast<const float4 *>(stg + 8 * S2_STG);
+                float l1 = 0.f, l5 = 0.f, l8 = 0.f, r3 = 0.f, r6 = 0.f, r7 = 0.f;
+                if (lane == 0) {
+                    l1 = stg[1 * S2_STG - 1];
+                    l5 = stg[5 * S2_STG - 1];
+                    l8 = stg[8 * S2_STG - 1];
+                }
+                if (lane == 31) {
+                    r3 = stg[3 * S2_STG + 4];
+                    r6 = stg[6 * S2_STG + 4];
+                    r7 = stg[7 * S2_STG + 4];
+                }
+                o[0] = v0;
+                o[1] = from_left(v1, l1, lane);
+                o[2] = v2;
+                o[3] = from_right(v3, r3, lane);
+                o[4] = v4;
+                o[5] = from_left(v5, l5, lane);
+                o[6] = from_right(v6, r6, lane);
+                o[7] = from_right(v7, r7, lane);
+                o[8] = from_left(v8, l8, lane);
+            }
+            // the staged values are in registers (the shuffles consumed them): refill the buffer
+            if (have_next) {
+                __syncwarp();
+                issue_loads(g + 1);
+            }
+            if (have) {
+                const int j = a0 + g * RB + r;
+                const unsigned hm = collide_quad(o, p.tau, p.inv_tau, p.inv_tau_lo);
+                if ((tf & TF_DEEP) && ownx && j >= y0 && j < y1) hits += __popc(hm);
+                float *slot = ring + ((size_t)((j - a0) % RS) * 9) * WI + col;
+#pragma unroll
+                for (int i = 0; i < 9; i++) *reinterpret_cast<float4 *>(slot + i * WI) = o[i];
+            }
+            tf = tf1;
+            tf1 = tf2;
+            have = have_next;
+            __syncthreads();
+        }
+#else
         float4 v0, v1, v2, v3, v4, v5, v6, v7, v8;
         float l1 = 0.f, l5 = 0.f, l8 = 0.f, r3 = 0.f, r6 = 0.f, r7 = 0.f;
         v0 = v1 = v2 = v3 = v4 = v5 = v6 = v7 = v8 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -868,6 +993,7 @@ step2_kernel(const __grid_constant__ Step2Params p) {
             if (have) issue_loads(g + 1);
             __syncthreads();
         }
+#endif  // ALB_S2_ASYNC
     } else {
         // ---- B warps: step 2, ring -> HBM, one row group behind ----
         auto flags_of = [&](int g) -> unsigned {
@@ -941,28 +1067,6 @@ step2_kernel(const __grid_constant__ Step2Params p) {
 //   staging  [NST][RB][9][WI+8]   source populations as the pull needs them (population i of the row
 //                                 j - ey_i), 4 cells of padding left and right for the x-neighbours
 //   ring     [2RB+2][9][WI]       intermediate state (one step ahead)
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 template <int RB, int K, int NST>
 __global__ void __launch_bounds__((2 * RB * K + 1) * 32, 1)
 step2t_kernel(const __grid_constant__ Step2Params p) {
@@ -1398,7 +1502,7 @@ cudaError_t launch_step2(const Step2Params &p, cudaStream_t s) {
         return cudaGetLastError();
     }
 #endif
-    constexpr size_t smem = sizeof(float) * (2 * RB + 2) * 9 * 128 * K;
+    constexpr size_t smem = sizeof(float) * ((size_t)(2 * RB + 2) * 9 * 128 * K + (ALB_S2_ASYNC ? (size_t)RB * K * (9 * (4 + 128 + 4) + 2) : 0));
     static bool configured[64] = {};       // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);

@@ -4,6 +4,9 @@ import sys
 
 import numpy as np
 
+if len(sys.argv) > 1 and sys.argv[1].endswith("-double"):
+    os.environ["AEROLAB_LBM_DOUBLE"] = "1"      # read when a handle is created: two steps per pass
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "airfoil-cfd-tool_b200"))
 
@@ -14,6 +17,8 @@ from aerolab_lbm import distributed as dm  # noqa: E402
 def main():
     halo = sys.argv[1]
     nx, ny, nsteps = 512, 250, 48
+    if halo.endswith("-double"):
+        halo, nx = halo[:-len("-double")], 1400
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     comm = dm.init_comm(world, rank, local)
     tun = dm.DistributedTunnel(nx, ny, comm, device=local, halo=halo)

@@ -15,13 +15,15 @@ def al(built_lib):
     return aerolab_lbm
 
 
-def test_two_device_slabs_bitwise(al):
-    nx, ny = 512, 256
+@pytest.mark.parametrize("nx,ny,double", [(512, 256, 0), (1400, 256, 1)])
+def test_two_device_slabs_bitwise(al, nx, ny, double):
+    """double=1: two steps per pass; the halo is pushed by the list-driven passes over NVLink."""
     whole = al.WindTunnel(nx, ny, 0)
     whole.load_shape("naca2412", alpha=7.0)
     a = al.WindTunnel(nx, ny, 0, y0=0, ny_local=120)
     b = al.WindTunnel(nx, ny, 1, y0=120, ny_local=136)
     for s in (a, b):
+        s.set_double_steps(double)
         s.load_shape("naca2412", alpha=7.0)
     a.connect_local(None, b)
     b.connect_local(a, None)
@@ -41,7 +43,7 @@ def test_two_device_slabs_bitwise(al):
     assert np.array_equal(me, whole.me_history(1)[0])
 
 
-@pytest.mark.parametrize("halo", ["p2p", "nccl"])
+@pytest.mark.parametrize("halo", ["p2p", "nccl", "p2p-double"])
 def test_distributed_tunnel_torchrun(al, halo):
     """One process per GPU (torchrun, NCCL plumbing): IPC/NVLink halo push and the NCCL fallback
     must both reproduce the single-GPU run bit for bit."""
@@ -51,7 +53,7 @@ def test_distributed_tunnel_torchrun(al, halo):
     from conftest import ROOT
     n = min(al.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
-           "--master-addr", "127.0.0.1", "--master-port", "29577" if halo == "p2p" else "29578",
+           "--master-addr", "127.0.0.1", "--master-port", {"p2p": "29577", "nccl": "29578"}.get(halo, "29579"),
            os.path.join(ROOT, "tests", "_dist_gpu_worker.py"), halo]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
