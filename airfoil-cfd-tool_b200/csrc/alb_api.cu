@@ -82,6 +82,8 @@ struct alb_handle {
     bool solid_synced = false;    // both ping-pong buffers hold the same values on the all-solid tasks (lists[4])
     int double_mode = -1;         // -1 automatic, 0 never, 1 whenever possible (AEROLAB_LBM_DOUBLE / alb_set_option)
     int graph_parity = 0;         // h->parity the graph was captured at
+    int prev_idx = 1;             // buffer that holds the PREVIOUS state (what the lazy macro pass reads);
+                                  // -1 after a batch that ended with a double step: not materialised
     int small_capacity = 0;       // cells the persistent small-lattice kernel can hold on this GPU
     int nsm = 148;                // SMs of the device
     double u0 = 0.06, tau = 0.58;
@@ -278,12 +280,27 @@ void arm_diag(alb_handle *h, StepParams &p) {
     p.m2f_cap = (float)(h->m2_hi * (1 + 1e-5));
 }
 
+void arm_diag2(alb_handle *h, Step2Params &q) {
+    refresh_thresholds(h);
+    q.diag = h->d_diag;
+    q.rho_lo = h->rho_lo;
+    q.rho_hi = h->rho_hi;
+    q.U0d = h->u0;
+    q.m2_lo = h->m2_lo;
+    q.m2_hi = h->m2_hi;
+    q.m2f_cap = (float)(h->m2_hi * (1 + 1e-5));
+}
+
+int ensure_prev(alb_handle *h);
+
 // One pass over the previous state that yields the autoscale statistics (HTML:596-614) and the
 // pressure-face sums (HTML:649-700) of the current state, optionally also storing rho/ux/uy.
 int run_macro_pass(alb_handle *h, bool write_macro) {
     CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc) * DIAG_SLOTS, cudaMemcpyHostToDevice, h->stream));
     h->diag_prearmed = false;
-    StepParams p = make_params(h, 1 - h->cur);
+    int r = ensure_prev(h);
+    if (r) return r;
+    StepParams p = make_params(h, h->prev_idx, h->cur);
     p.write_macro = write_macro ? 1 : 0;
     arm_diag(h, p);
     CK(launch_macro(p, h->stream));
@@ -339,6 +356,7 @@ int do_reset(alb_handle *h, double u0) {
     CK(cudaMemsetAsync(h->clamp_hits, 0, sizeof(unsigned long long), h->stream));
     h->cur = 0;
     h->parity = 0;
+    h->prev_idx = 1;
     h->solid_synced = true;     // both buffers were filled alike
     drop_graph(h);
     h->steps = 0;
@@ -736,8 +754,15 @@ int issue_step(alb_handle *h, int src_idx, int parity, bool halo, long long sync
 //                f[2] into the destination.  The slab halo (edge rows are always shallow) is pushed
 //                by these passes exactly as by single steps; step2_kernel only has to wait for the
 //                neighbours' previous step (it reads the ghost rows of the source state).
-int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sync_step, bool copy_solid) {
+int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sync_step, bool copy_solid,
+                 bool diag = false) {
     const int dst_idx = 1 - src_idx;
+    if (diag) {
+        // a batch that ends with a double step: its second step reduces the statistics / face sums
+        if (!h->diag_prearmed)
+            CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc) * DIAG_SLOTS, cudaMemcpyHostToDevice, h->stream));
+        h->diag_prearmed = false;
+    }
     CK(cudaEventRecord(h->ev_fork, h->stream));
     CK(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
     for (int pass = 0; pass < 2; pass++) {
@@ -746,6 +771,7 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
             halo_wait(h, sync_step + pass, h->aux);
             set_peers(h, p, pass == 0 ? 2 : dst_idx);
         }
+        if (diag && pass == 1) arm_diag(h, p);
         p.gen_list = h->lists[2 * pass];
         p.ngen = h->nlist[2 * pass];
         CK(launch_step_fast_list(p, h->aux));
@@ -778,12 +804,36 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
     q.inv_tau = h->inv_tau;
     q.inv_tau_lo = h->inv_tau_lo;
     q.clamp_hits = h->clamp_hits;
+    if (diag) arm_diag2(h, q);
     step2_plan(q, h->nsm);
     // the fused kernel reads the ghost rows of the source state (intermediate rows 1 and nyl)
     if (halo) halo_wait(h, sync_step, h->stream);
     CK(launch_step2(q, h->stream));
     CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     if (halo) halo_signal(h, sync_step + 2, h->stream);
+    return ALB_OK;
+}
+
+}  // namespace
+
+// The macroscopic fields of the current state are a function of the state one step earlier.  After
+// a batch that ended with a double step that state was never written: advance the state of two
+// steps ago (still intact in the other ping-pong buffer) by one step into the scratch buffer,
+// without any side effect (no momentum-exchange bookkeeping, no clamp counting, no halo push --
+// the ghost rows of the scratch buffer still hold the neighbours' rows of exactly that state).
+namespace {
+int ensure_prev(alb_handle *h) {
+    if (h->prev_idx >= 0) return ALB_OK;
+    StepParams p = make_params(h, 1 - h->cur, 2, 0);
+    p.me = nullptr;
+    p.clamp_hits = nullptr;
+    if (p.ntasks <= UNIFIED_MAX_TASKS) {
+        CK(launch_step_unified(p, h->stream));
+    } else {
+        CK(launch_step_fast(p, h->stream));
+        CK(launch_step_general(p, h->stream));
+    }
+    h->prev_idx = 2;
     return ALB_OK;
 }
 
@@ -854,6 +904,7 @@ static int step_batch(alb_handle *h, int nsteps) {
         CK(launch_small_lattice(p, h->f[0], h->f[1], h->cur, nsteps, h->stream));
         h->cur = (h->cur + nsteps) & 1;
         h->parity = h->cur;
+        h->prev_idx = 1 - h->cur;
         h->solid_synced = false;
         left = 0;
     }
@@ -868,16 +919,18 @@ static int step_batch(alb_handle *h, int nsteps) {
             }
             CK(cudaGraphLaunch(h->graph, h->stream));
             h->solid_synced = doubles;
+            h->prev_idx = doubles ? -1 : 1;      // the graph starts at cur == 0 and has an even number of steps
             left -= GRAPH_STEPS;           // an even number of steps: cur and parity are unchanged
             done += GRAPH_STEPS;
             continue;
         }
-        if (doubles && left >= 3) {
-            // the batch must END with a single step: its source state stays intact in the other
-            // buffer, which the lazy macroscopic pass relies on
-            int r = issue_double(h, h->cur, h->parity, halo, h->sync_steps + done, !h->solid_synced);
+        if (doubles && left >= 2 && left != 3) {
+            // a batch may END with a double step (which then carries the diagnostics); the state in
+            // between is not materialised, ensure_prev() recomputes it if the fields are asked for
+            int r = issue_double(h, h->cur, h->parity, halo, h->sync_steps + done, !h->solid_synced, left == 2);
             if (r) return r;
             h->solid_synced = true;
+            h->prev_idx = -1;
             h->cur = 1 - h->cur;           // two steps: parity unchanged
             left -= 2;
             done += 2;
@@ -885,6 +938,7 @@ static int step_batch(alb_handle *h, int nsteps) {
         }
         int r = issue_step(h, h->cur, h->parity, halo, h->sync_steps + done, left == 1);
         if (r) return r;
+        h->prev_idx = h->cur;
         h->cur = 1 - h->cur;
         h->parity ^= 1;
         left--;

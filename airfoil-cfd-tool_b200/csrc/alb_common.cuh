@@ -133,6 +133,12 @@ struct Step2Params {
     int nstrips, ntiles;
     float tau, inv_tau, inv_tau_lo;
     unsigned long long *clamp_hits;
+    // fused statistics of the state being written (nullable), same meaning as in StepParams
+    DiagAcc *diag;
+    float rho_lo, rho_hi;
+    double U0d;
+    double m2_lo, m2_hi;
+    float m2f_cap;
 };
 
 struct Handle;

@@ -265,7 +265,8 @@ __device__ __forceinline__ double speed_ratio(float ux, float uy, double U0) {
 
 // One non-solid lattice cell.  s is monotone in ux^2+uy^2 (exact in double), so only the arg-max
 // candidate ever needs the hypot; cells within 1e-9 of the s < 4 cut are decided exactly.
-__device__ __forceinline__ void diag_cell(const StepParams &p, DiagLocal &d, float rho, float ux, float uy) {
+template <class P>
+__device__ __forceinline__ void diag_cell(const P &p, DiagLocal &d, float rho, float ux, float uy) {
     if (rho >= p.rho_lo && rho <= p.rho_hi) {
         d.rmin = fminf(d.rmin, rho);
         d.rmax = fmaxf(d.rmax, rho);
@@ -321,8 +322,8 @@ __device__ __forceinline__ void atomic_max_float(float *a, float v) {
 // extrema have settled (plain-load pre-check)
 // FACES = false for tasks that cannot have fluid/solid faces (all-fluid, all-equilibrium): the
 // four face sums are known to be zero and are left out of the shuffle tree.
-template <bool FACES = true>
-__device__ __forceinline__ void diag_flush(const StepParams &p, DiagLocal &d, int lane) {
+template <bool FACES = true, class P = StepParams>
+__device__ __forceinline__ void diag_flush(const P &p, DiagLocal &d, int lane) {
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
         d.rmin = fminf(d.rmin, __shfl_xor_sync(FULL, d.rmin, s));
@@ -692,7 +693,9 @@ __device__ __forceinline__ bool div_pair(float jx, float jy, float r, float &vx,
 #ifndef ALB_QUAD_G
 #define ALB_QUAD_G 4
 #endif
-__device__ __forceinline__ unsigned collide_quad(float4 (&o)[9], float tau, float rcp, float rcp_lo) {
+// mac: optional, receives rho/ux/uy of the four cells (what the shader writes to its macro texture)
+__device__ __forceinline__ unsigned collide_quad(float4 (&o)[9], float tau, float rcp, float rcp_lo,
+                                                 float (*mac)[3] = nullptr) {
     constexpr int G = ALB_QUAD_G;
     unsigned hitmask = 0;
 #pragma unroll
@@ -738,6 +741,7 @@ __device__ __forceinline__ unsigned collide_quad(float4 (&o)[9], float tau, floa
             for (int i = 0; i < 9; i++) f[i] = comp(o[i], k0 + kk);
             Moments m;
             m.rho = rho[kk]; m.ux = ux[kk]; m.uy = uy[kk]; m.hit = false;
+            if (mac) { mac[k0 + kk][0] = m.rho; mac[k0 + kk][1] = m.ux; mac[k0 + kk][2] = m.uy; }
             collide(f, m, tau, rcp, rcp_lo);
 #pragma unroll
             for (int i = 0; i < 9; i++) setc(o[i], k0 + kk, f[i]);
@@ -765,6 +769,7 @@ copy_tasks_kernel(const __grid_constant__ StepParams p) {
     for (int i = 0; i < 9; i++) ST4(p.dst + i * plane + c, v[i]);
 }
 
+#if ALB_S2_TMA || ALB_S2_ASYNC
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -787,6 +792,8 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+#endif
+
 // loads that must stay where they are written (issued BEFORE the barrier that ends a super-step)
 __device__ __forceinline__ float4 ld4_pinned(const float *p) {
     float4 r;
@@ -798,14 +805,16 @@ __device__ __forceinline__ float ld1_pinned(const float *p) {
     asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
-constexpr int S2_STG = 4 + 128 + 4;    // floats per population in an A warp's private staging buffer
+[[maybe_unused]] constexpr int S2_STG = 4 + 128 + 4;    // floats per population in an A warp's private staging buffer
 #define LD4P(ptr) (ALB_CHECK_SRC((ptr), 4), ld4_pinned(ptr))
 #define LD1P(ptr) (ALB_CHECK_SRC((ptr), 1), ld1_pinned(ptr))
 
 #ifndef ALB_S2_MINB
 #define ALB_S2_MINB ((16 / (ALB_S2_RB * ALB_S2_K)) >= 1 ? 16 / (ALB_S2_RB * ALB_S2_K) : 1)
 #endif
-template <int RB, int K>
+// DIAG: step 2 also reduces the autoscale statistics of the state it writes (deep cells have no
+// faces), once per tile -- for batches that END with a double step.
+template <int RB, int K, bool DIAG = false>
 __global__ void __launch_bounds__(2 * RB * K * 32, ALB_S2_MINB)
 step2_kernel(const __grid_constant__ Step2Params p) {
     extern __shared__ float4 ring4[];
@@ -1001,6 +1010,7 @@ step2_kernel(const __grid_constant__ Step2Params p) {
             return (g >= 1 && g <= nga && j >= y0 && j < y1 && ownx) ? tfl[(size_t)j * p.tpr] : 0u;
         };
         unsigned tf = 0u, tf1 = flags_of(1);
+        [[maybe_unused]] DiagLocal dl;
         for (int g = 0; g <= nga; g++) {
             const unsigned tf2 = flags_of(g + 2);
             const bool st = (tf & TF_DEEP) != 0;
@@ -1040,18 +1050,24 @@ step2_kernel(const __grid_constant__ Step2Params p) {
                 o[6] = from_right(v6, r6, lane);
                 o[7] = from_right(v7, r7, lane);
                 o[8] = from_left(v8, l8, lane);
-                const unsigned hm = collide_quad(o, p.tau, p.inv_tau, p.inv_tau_lo);
+                float mac[4][3];
+                const unsigned hm = collide_quad(o, p.tau, p.inv_tau, p.inv_tau_lo, DIAG ? mac : nullptr);
                 if (st) {
                     hits += __popc(hm);
                     float *d = p.dst + (size_t)j * p.pitch + gx;
 #pragma unroll
                     for (int i = 0; i < 9; i++) ST4(d + i * plane, o[i]);
+                    if (DIAG) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) diag_cell(p, dl, mac[k][0], mac[k][1], mac[k][2]);
+                    }
                 }
             }
             tf = tf1;
             tf1 = tf2;
             __syncthreads();
         }
+        if (DIAG) diag_flush<false>(p, dl, lane);
     }
     if (hits && p.clamp_hits) atomicAdd(p.clamp_hits, (unsigned long long)hits);
 }
@@ -1430,7 +1446,8 @@ cudaError_t launch_step_unified(const StepParams &p, cudaStream_t s) {
 cudaError_t launch_step_fast_list(const StepParams &p, cudaStream_t s) {
     // at least one CTA even for an empty list: its first thread does the momentum-exchange bookkeeping
     const int nblocks = p.ngen > 0 ? (p.ngen + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK : 1;
-    step_kernel<MODE_STEP, KIND_FAST_LIST><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    if (p.diag) step_kernel<MODE_STEP, KIND_FAST_LIST, true><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    else step_kernel<MODE_STEP, KIND_FAST_LIST><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -1507,11 +1524,14 @@ cudaError_t launch_step2(const Step2Params &p, cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(step2_kernel<RB, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(step2_kernel<RB, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(step2_kernel<RB, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    step2_kernel<RB, K><<<p.ntiles, 2 * RB * K * 32, smem, s>>>(p);
+    if (p.diag) step2_kernel<RB, K, true><<<p.ntiles, 2 * RB * K * 32, smem, s>>>(p);
+    else step2_kernel<RB, K, false><<<p.ntiles, 2 * RB * K * 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 
