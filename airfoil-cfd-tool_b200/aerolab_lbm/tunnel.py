@@ -370,6 +370,17 @@ class WindTunnel:
         self._ck(self._lib.alb_selftest_division(self._h, int(seed), int(pairs), ptr(out)))
         return {"checked": int(out[0]), "accepted": int(out[1]), "wrong": int(out[2])}
 
+    def launch_count(self) -> int:
+        """CUDA kernels launched by this tunnel's step batches so far (graph replays included)."""
+        n = C.c_longlong(0)
+        self._ck(self._lib.alb_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def double_steps_active(self) -> bool:
+        a = C.c_int(0)
+        self._ck(self._lib.alb_get_double_steps(self._h, None, C.byref(a)))
+        return bool(a.value)
+
     def set_double_steps(self, mode: int):
         """-1 automatic, 0 never, 1 always: two steps per pass over HBM (bit-identical results)."""
         self._ck(self._lib.alb_set_double_steps(self._h, int(mode)))

@@ -82,6 +82,8 @@ struct alb_handle {
     bool solid_synced = false;    // both ping-pong buffers hold the same values on the all-solid tasks (lists[4])
     int double_mode = -1;         // -1 automatic, 0 never, 1 whenever possible (AEROLAB_LBM_DOUBLE / alb_set_option)
     int graph_parity = 0;         // h->parity the graph was captured at
+    long long launches = 0;       // kernels launched by step batches so far (graph replays included)
+    long long graph_launches = 0; // kernels inside one replay of the captured graph
     int prev_idx = 1;             // buffer that holds the PREVIOUS state (what the lazy macro pass reads);
                                   // -1 after a batch that ended with a double step: not materialised
     int small_capacity = 0;       // cells the persistent small-lattice kernel can hold on this GPU
@@ -728,7 +730,9 @@ int issue_step(alb_handle *h, int src_idx, int parity, bool halo, long long sync
     if (halo) {
         halo_wait(h, sync_step, h->stream);
         set_peers(h, p, 1 - src_idx);
+        h->launches += 2;       // wait + signal
     }
+    h->launches += (p.ntasks <= UNIFIED_MAX_TASKS || p.ngen == 0) ? 1 : 2;
     if (p.ntasks <= UNIFIED_MAX_TASKS) {
         // small lattice: launch-latency bound, one launch for both paths
         CK(launch_step_unified(p, h->stream));
@@ -778,6 +782,7 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
         p.gen_list = h->lists[2 * pass + 1];
         p.ngen = h->nlist[2 * pass + 1];
         CK(launch_step_general(p, h->aux));
+        h->launches += 1 + (p.ngen > 0 ? 1 : 0) + (halo ? 2 : 0);
         if (pass == 1 && copy_solid && h->nlist[4] > 0) {
             // all-solid tasks return to their state after two steps: copy, unless the destination
             // still holds the same values from the previous double step
@@ -785,6 +790,7 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
             c.gen_list = h->lists[4];
             c.ngen = h->nlist[4];
             CK(launch_copy_tasks(c, h->aux));
+            h->launches++;
         }
         // the second signal also tells the neighbours that they may overwrite the ghost rows of the
         // SOURCE state, which step2_kernel reads: it is given on the main stream after the join
@@ -809,6 +815,7 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
     // the fused kernel reads the ghost rows of the source state (intermediate rows 1 and nyl)
     if (halo) halo_wait(h, sync_step, h->stream);
     CK(launch_step2(q, h->stream));
+    h->launches += (q.ntiles > 0 ? 1 : 0) + (halo ? 1 : 0);
     CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     if (halo) halo_signal(h, sync_step + 2, h->stream);
     return ALB_OK;
@@ -854,6 +861,7 @@ int capture_graph(alb_handle *h, bool doubles) {
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     int r = ALB_OK;
     int cur = 0, parity = h->parity;
+    const long long launches_before = h->launches;
     for (int s = 0; s < GRAPH_STEPS && r == ALB_OK;) {
         if (doubles) {
             r = issue_double(h, cur, parity, false, 0, s == 0);   // replayed after anything: the first one always copies
@@ -878,6 +886,8 @@ int capture_graph(alb_handle *h, bool doubles) {
         return h->fail(ALB_ERR_CUDA, "cudaGraphInstantiate", e);
     }
     h->graph_parity = h->parity;
+    h->graph_launches = h->launches - launches_before;   // captured, not executed
+    h->launches = launches_before;
     return ALB_OK;
 }
 
@@ -902,6 +912,7 @@ static int step_batch(alb_handle *h, int nsteps) {
         h->diag_prearmed = false;
         arm_diag(h, p);
         CK(launch_small_lattice(p, h->f[0], h->f[1], h->cur, nsteps, h->stream));
+        h->launches++;
         h->cur = (h->cur + nsteps) & 1;
         h->parity = h->cur;
         h->prev_idx = 1 - h->cur;
@@ -918,6 +929,7 @@ static int step_batch(alb_handle *h, int nsteps) {
                 if (r) return r;
             }
             CK(cudaGraphLaunch(h->graph, h->stream));
+            h->launches += h->graph_launches;
             h->solid_synced = doubles;
             h->prev_idx = doubles ? -1 : 1;      // the graph starts at cur == 0 and has an even number of steps
             left -= GRAPH_STEPS;           // an even number of steps: cur and parity are unchanged
@@ -1628,6 +1640,19 @@ int alb_selftest_division(alb_handle *h, unsigned long long seed, long long pair
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(d);
     if (e != cudaSuccess) return h->fail(ALB_ERR_CUDA, "alb_selftest_division", e);
+    return ALB_OK;
+}
+
+int alb_launch_count(const alb_handle *h, long long *launches) {
+    if (!h || !launches) return ALB_ERR_INVALID;
+    *launches = h->launches;
+    return ALB_OK;
+}
+
+int alb_get_double_steps(const alb_handle *h, int *mode, int *active) {
+    if (!h) return ALB_ERR_INVALID;
+    if (mode) *mode = h->double_mode;
+    if (active) *active = double_steps_enabled(h) ? 1 : 0;
     return ALB_OK;
 }
 

@@ -183,10 +183,10 @@ __device__ __forceinline__ void moments_plain(const float (&f)[9], float &rho, f
 // HTML:276-281 and 352-356.  feq_i = wt(i)*rho*(1+3eu+4.5eu*eu-1.5uu), left to
 // right; opposite directions share 3*eu and 4.5*eu*eu (negating eu negates the
 // first exactly and leaves the second unchanged, so sharing is bit-neutral).
-__device__ __forceinline__ void collide(float (&f)[9], const Moments &m, float tau, float rcp, float rcp_lo) {
+// uu = ux*ux + uy*uy, passed in by callers that have it already (same operations, same value)
+__device__ __forceinline__ void collide_uu(float (&f)[9], const Moments &m, float uu, float tau, float rcp, float rcp_lo) {
     const float w0 = 4.0f / 9.0f, ws = 1.0f / 9.0f, wd = 1.0f / 36.0f;
     const float rho = m.rho, ux = m.ux, uy = m.uy;
-    const float uu = ux * ux + uy * uy;
     const float c15 = 1.5f * uu;
     const float wr0 = w0 * rho, wrs = ws * rho, wrd = wd * rho;
     {
@@ -208,6 +208,9 @@ __device__ __forceinline__ void collide(float (&f)[9], const Moments &m, float t
     ALB_PAIR(5, 7, ux + uy, wrd)
     ALB_PAIR(6, 8, uy - ux, wrd)
 #undef ALB_PAIR
+}
+__device__ __forceinline__ void collide(float (&f)[9], const Moments &m, float tau, float rcp, float rcp_lo) {
+    collide_uu(f, m, m.ux * m.ux + m.uy * m.uy, tau, rcp, rcp_lo);
 }
 
 __device__ __forceinline__ float comp(const float4 &v, int k) {
@@ -657,8 +660,13 @@ step_kernel(const __grid_constant__ StepParams p) {
 // Everything that is not "deep" (border cells, the body and its surroundings, slab edge rows) is
 // advanced by two passes of the list-driven single-step kernels through a third buffer.
 // jx/r and jy/r with a shared reciprocal: the instruction sequence of nvcc's own div.rn.f32 fast
-// path.  Returns false when the operands are outside the range in which that sequence is known to
-// give the correctly rounded quotient (the caller then uses true division).
+// path (MUFU.RCP, one Newton step, quotient, exact residual, one correction).  It yields the
+// correctly rounded quotient as long as no intermediate leaves the normal range.  The caller only
+// uses the result when quad_accept() holds: rho within the clamp interval [0.5, 2] (so the
+// reciprocal is harmless), |u|^2 <= uMax^2 (which bounds the numerators from above; the negated
+// comparison also catches NaN), and each numerator either +0 or at least 2^-60 in magnitude (the
+// return value; -0 and anything tiny go to true division, which knows about signed zeros and
+// underflow).  tests/test_gpu_div.py compares accepted results with IEEE division.
 __device__ __forceinline__ bool div_pair(float jx, float jy, float r, float &vx, float &vy) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(r));
@@ -668,11 +676,14 @@ __device__ __forceinline__ bool div_pair(float jx, float jy, float r, float &vx,
     const float rx = __fmaf_rn(-r, qx, jx), ry = __fmaf_rn(-r, qy, jy);
     vx = __fmaf_rn(y, rx, qx);
     vy = __fmaf_rn(y, ry, qy);
-    const unsigned bx = __float_as_uint(jx), by = __float_as_uint(jy);
-    const bool den_ok = (__float_as_uint(r) - 0x2B800000u) <= (0x53800000u - 0x2B800000u);                  // 2^-40 .. 2^40
-    const bool nx_ok = ((bx & 0x7fffffffu) - 0x21800000u) <= (0x53800000u - 0x21800000u) || bx == 0u;       // 2^-60 .. 2^40, +0
-    const bool ny_ok = ((by & 0x7fffffffu) - 0x21800000u) <= (0x53800000u - 0x21800000u) || by == 0u;
-    return den_ok && nx_ok && ny_ok;
+    const bool nx_ok = fabsf(jx) >= 0x1p-60f || __float_as_uint(jx) == 0u;
+    const bool ny_ok = fabsf(jy) >= 0x1p-60f || __float_as_uint(jy) == 0u;
+    return nx_ok && ny_ok;
+}
+// true: the fast path's rho/ux/uy ARE the shader's values (no clamp fires, division exact)
+__device__ __forceinline__ bool quad_accept(float r, float spd2, bool nums_ok) {
+    const float rc = fminf(fmaxf(r, 0.5f), 2.0f);
+    return nums_ok && rc == r && spd2 <= 0.35f * 0.35f;
 }
 
 // Four cells at once, written so that the common case is ONE basic block: the generic IEEE
@@ -712,11 +723,9 @@ __device__ __forceinline__ unsigned collide_quad(float4 (&o)[9], float tau, floa
             const float jx = f1 + f5 + f8 - f3 - f6 - f7;
             const float jy = f2 + f5 + f6 - f4 - f7 - f8;
             float vx, vy;
-            const bool div_ok = div_pair(jx, jy, r, vx, vy);
-            const float rc = fminf(fmaxf(r, 0.5f), 2.0f);
+            const bool nums_ok = div_pair(jx, jy, r, vx, vy);
             const float spd2 = vx * vx + vy * vy;
-            const bool clamp = (rc != r) || (spd2 > 0.35f * 0.35f);
-            if (!div_ok || clamp) bad |= 1u << kk;
+            if (!quad_accept(r, spd2, nums_ok)) bad |= 1u << kk;
             rho[kk] = r;          // in [0.5, 2] unless the cell is flagged
             ux[kk] = vx;
             uy[kk] = vy;
@@ -1399,7 +1408,8 @@ __global__ void div_selftest_kernel(unsigned long long seed, int iters, unsigned
             jy = (a >> 36) & 1 ? sp[(a >> 44) & 7] : __uint_as_float(sy | (120u << 23) | mant_y);
         }
         float vx, vy;
-        const bool ok = div_pair(jx, jy, r, vx, vy);
+        const bool nums_ok = div_pair(jx, jy, r, vx, vy);
+        const bool ok = quad_accept(r, vx * vx + vy * vy, nums_ok);
         checked++;
         if (ok) {
             accepted++;

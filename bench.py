@@ -55,12 +55,13 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def committed_traffic(workload):
-    """Per-launch DRAM bytes of the step kernel from the committed ncu capture, if any."""
+def committed_traffic(workload, doubles=False):
+    """DRAM bytes per launch of the dominant step kernel from the committed ncu capture, if any.
+    Single steps: one launch = one step.  Double steps: one launch of step2_kernel = two steps."""
     path = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     try:
         with open(path) as fh:
-            return json.load(fh).get(workload)
+            return json.load(fh).get(workload + (":step2" if doubles else ""))
     except Exception:
         return None
 
@@ -264,12 +265,14 @@ def main():
         sampler.start()
     torch.cuda.synchronize()
     comm.barrier()
+    launches0 = tun.t.launch_count()
     t0 = time.perf_counter()
     tun.step(args.steps)
     ms_dev = tun.last_step_ms()          # CUDA events on the launching stream; synchronises
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
     comm.barrier()
+    launches = tun.t.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_dev = comm.max_float(ms_dev)
     wall_ms = comm.max_float(wall_ms)
@@ -294,16 +297,28 @@ def main():
         except Exception:
             copy_here = None
 
-    # roofline of the dominant kernel: per launch, this rank's cells
+    # roofline of the dominant kernel: per launch, this rank's cells.  Algorithmic traffic is
+    # 72 B per cell update.  With double steps the dominant kernel (step2_kernel)
+    # performs TWO updates per cell and launch while reading and writing the state once, so the
+    # algorithmic rate can exceed the DRAM peak; `traffic` (ncu, per launch) and `dram_frac` show
+    # what actually crosses the HBM interface.
     peak, peak_src = measured_peak()
     cells_local = nx * tun.ny_local
-    launch_ms = ms_dev / args.steps
-    achieved = BYTES_PER_LUP * cells_local / (launch_ms * 1e-3) / 1e9
+    doubles = tun.t.double_steps_active() and args.halo == "p2p"
+    steps_per_launch = 2 if doubles else 1
+    launch_ms = ms_dev / args.steps * steps_per_launch
+    alg_bytes = BYTES_PER_LUP * cells_local * steps_per_launch
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    traffic = committed_traffic(args.workload, doubles)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": committed_traffic(args.workload), "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "copy_gbs_measured_in_this_run": copy_here,
-                "kernel": "alb::step_kernel<MODE_STEP>",
-                "algorithmic_bytes_per_launch": BYTES_PER_LUP * cells_local}
+                "kernel": ("alb::step2_kernel (two steps per launch; + list-driven step_kernel passes for "
+                           "border/body/slab-edge tasks on a second stream)") if doubles else "alb::step_kernel<MODE_STEP>",
+                "steps_per_launch": steps_per_launch,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "launch_ms": launch_ms,
+                "dram_frac": (traffic / (launch_ms * 1e-3) / 1e9 / peak) if (traffic and world == 1) else None}
 
     # ---- end to end through the public API (`e2e`) ----------------------------
     e2e = None
@@ -330,10 +345,9 @@ def main():
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            # per step: fast + general-task kernel (one unified kernel for lattices of <= 2368 tasks),
-            # plus the wait/signal flag kernels when slabs exchange halos
-            "gpu_launches": args.steps * ((1 if (tun.ny_local * ((nx + 127) // 128)) <= 2368 else 2)
-                                          + (2 if world > 1 else 0)),
+            # counted by the library (alb_launch_count): kernels launched on this rank in the timed
+            # region, kernels inside replayed CUDA graphs included
+            "gpu_launches": int(launches),
             "clocks": clocks,
             "check": {"CL_me": forces.get("CL_me"), "CD_me": forces.get("CD_me"),
                       "CL_pressure_raw": forces.get("CL_raw"), "CD_pressure_raw": forces.get("CD_raw"),

@@ -255,6 +255,11 @@ int alb_set_external_halo(alb_handle *h, int on);
  * lattice must use the same mode.  The environment variable AEROLAB_LBM_DOUBLE
  * (0/1) sets the initial mode of new handles. */
 int alb_set_double_steps(alb_handle *h, int mode);
+/* mode as set; active = 1 when step batches of this handle use double steps. */
+int alb_get_double_steps(const alb_handle *h, int *mode, int *active);
+/* Number of CUDA kernels the step batches of this handle have launched so far
+ * (alb_step / alb_run_frames; kernels inside replayed CUDA graphs included). */
+int alb_launch_count(const alb_handle *h, long long *launches);
 
 /* Self-test of the shared-reciprocal division the fused kernels use for
  * u = j / rho: runs it on about `pairs` generated operand

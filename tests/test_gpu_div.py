@@ -16,5 +16,6 @@ def test_shared_reciprocal_division_matches_ieee(built_lib):
                 total[k] += r[k]
     assert total["wrong"] == 0, total
     assert total["checked"] >= 4 * (3 << 30)
-    # most lattice-like and boundary-case operands are accepted; the special values are not
-    assert 0.5 * total["checked"] < total["accepted"] < total["checked"], total
+    # a good part of the lattice-like and boundary-case operands is accepted (rho within [0.5, 2],
+    # |u| below the clamp); special values and out-of-range operands are not
+    assert 0.15 * total["checked"] < total["accepted"] < total["checked"], total
