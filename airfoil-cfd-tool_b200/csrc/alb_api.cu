@@ -328,7 +328,7 @@ int rebuild_info(alb_handle *h) {
     // the host needs the number of general tasks to size that kernel's grid (mask changes are rare)
     CK(cudaMemcpyAsync(&h->ngen, h->gen_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(launch_build_lists(h->info, h->tclass, h->deep_tmp, h->tflags, h->lists, h->list_counts, h->pitch, h->nrows,
-                          h->stream));
+                          h->y0 > 0 ? 1 : 0, h->y0 + h->nyl < h->ny_global ? 1 : 0, h->stream));
     CK(cudaMemcpyAsync(h->nlist, h->list_counts, 5 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     h->solid_synced = false;
     CK(cudaStreamSynchronize(h->stream));
@@ -756,8 +756,8 @@ int issue_step(alb_handle *h, int src_idx, int parity, bool halo, long long sync
 //   aux stream:  the two-pass path for everything else: pass 1 writes the intermediate state of the
 //                shallow tasks and their neighbours into f[2], pass 2 advances the shallow tasks from
 //                f[2] into the destination.  The slab halo (edge rows are always shallow) is pushed
-//                by these passes exactly as by single steps; step2_kernel only has to wait for the
-//                neighbours' previous step (it reads the ghost rows of the source state).
+//                by these passes exactly as by single steps, so step2_kernel needs no flags at all:
+//                next to a neighbouring slab TWO edge rows are shallow and it never reads a ghost row.
 int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sync_step, bool copy_solid,
                  bool diag = false) {
     const int dst_idx = 1 - src_idx;
@@ -792,9 +792,7 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
             CK(launch_copy_tasks(c, h->aux));
             h->launches++;
         }
-        // the second signal also tells the neighbours that they may overwrite the ghost rows of the
-        // SOURCE state, which step2_kernel reads: it is given on the main stream after the join
-        if (halo && pass == 0) halo_signal(h, sync_step + 1, h->aux);
+        if (halo) halo_signal(h, sync_step + pass + 1, h->aux);
     }
     CK(cudaEventRecord(h->ev_join, h->aux));
     Step2Params q;
@@ -812,12 +810,11 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
     q.clamp_hits = h->clamp_hits;
     if (diag) arm_diag2(h, q);
     step2_plan(q, h->nsm);
-    // the fused kernel reads the ghost rows of the source state (intermediate rows 1 and nyl)
-    if (halo) halo_wait(h, sync_step, h->stream);
+    // no flags here: next to a neighbouring slab two edge rows are shallow, the fused kernel never
+    // reads a ghost row, and the GPUs only meet in the short list-driven passes
     CK(launch_step2(q, h->stream));
-    h->launches += (q.ntiles > 0 ? 1 : 0) + (halo ? 1 : 0);
+    h->launches += q.ntiles > 0 ? 1 : 0;
     CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-    if (halo) halo_signal(h, sync_step + 2, h->stream);
     return ALB_OK;
 }
 

@@ -193,7 +193,8 @@ cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tcla
 // lists[5] = pass-1 fast, pass-1 general, pass-2 fast, pass-2 general, all-solid (copied, not stepped);
 // counts = int[5] (device)
 cudaError_t launch_build_lists(const uint16_t *info, const uint8_t *tclass, uint8_t *deep_tmp, uint8_t *tflags,
-                               int *const lists[5], int *counts, int pitch, int nrows, cudaStream_t s);
+                               int *const lists[5], int *counts, int pitch, int nrows, int lo_nb, int hi_nb,
+                               cudaStream_t s);
 
 // alb_diag.cu
 struct DiagScratch {

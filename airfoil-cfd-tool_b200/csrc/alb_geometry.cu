@@ -205,13 +205,15 @@ __global__ void build_tclass_kernel(const uint16_t *__restrict__ info, uint8_t *
 // task to its left, the first cell of the task to its right, in rows j-1, j, j+1) is plain, and
 // the row is neither the first nor the last owned row (those need the neighbouring slab's
 // intermediate state, or are the equilibrium border rows of a whole lattice).
+// With a neighbouring slab below / above (lo_nb / hi_nb) the first / last TWO rows stay shallow, so
+// that the fused kernel never reads a ghost row and needs no synchronisation with the neighbours.
 __global__ void build_deep_kernel(const uint16_t *__restrict__ info, const uint8_t *__restrict__ tclass,
-                                  uint8_t *__restrict__ deep, int pitch, int nrows) {
+                                  uint8_t *__restrict__ deep, int pitch, int nrows, int lo_nb, int hi_nb) {
     const int tpr = pitch / TASK_CELLS;
     const int task = blockIdx.x * blockDim.x + threadIdx.x;
     if (task >= tpr * nrows) return;
     const int j = task / tpr, s = task - j * tpr;
-    bool d = j >= 2 && j <= nrows - 3 && s >= 1 && s <= tpr - 2;
+    bool d = j >= 2 + lo_nb && j <= nrows - 3 - hi_nb && s >= 1 && s <= tpr - 2;
     if (d) {
         for (int jj = j - 1; jj <= j + 1; jj++) {
             d = d && tclass[jj * tpr + s] == TC_FLUID;
@@ -292,9 +294,10 @@ cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tcla
 }
 
 cudaError_t launch_build_lists(const uint16_t *info, const uint8_t *tclass, uint8_t *deep_tmp, uint8_t *tflags,
-                               int *const lists[5], int *counts, int pitch, int nrows, cudaStream_t s) {
+                               int *const lists[5], int *counts, int pitch, int nrows, int lo_nb, int hi_nb,
+                               cudaStream_t s) {
     const int tpr = pitch / TASK_CELLS, ntask = tpr * nrows;
-    build_deep_kernel<<<(ntask + 255) / 256, 256, 0, s>>>(info, tclass, deep_tmp, pitch, nrows);
+    build_deep_kernel<<<(ntask + 255) / 256, 256, 0, s>>>(info, tclass, deep_tmp, pitch, nrows, lo_nb, hi_nb);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(counts, 0, 5 * sizeof(int), s);

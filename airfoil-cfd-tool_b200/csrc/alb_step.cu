@@ -61,6 +61,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef ALB_S2_HS_MAX
 #define ALB_S2_HS_MAX 256
 #endif
+#ifndef ALB_S2_HS_MIN
+#define ALB_S2_HS_MIN 64
+#endif
 // 1: step2t_kernel (TMA-fed staging ring, NST stages), 0: step2_kernel (loads through registers)
 #ifndef ALB_S2_TMA
 #define ALB_S2_TMA 0
@@ -1490,17 +1493,22 @@ void step2_plan(Step2Params &p, int nsm) {
     if (hs_env > 0) {
         p.hs = hs_env;
     } else {
-        // Whole waves: every tile costs the same, one CTA per SM, so the number of tiles should be
-        // just under a multiple of the SM count.  Taller segments recompute fewer rows, but the
-        // list-driven passes on the aux stream only get SMs when a tile retires: measured on
-        // 32768x16384, 128..256 rows are equally good (125 GLUPS), 443 rows 123, 1024 rows 115.
-        int best = rows;
-        for (int waves = 1; waves <= 4096; waves++) {
-            int nsegs = (int)((long long)waves * nsm / p.nstrips);
-            if (nsegs < 1) continue;
-            if (nsegs > rows) nsegs = rows;
-            best = (rows + nsegs - 1) / nsegs;
-            if (best <= ALB_S2_HS_MAX) break;
+        // Every tile costs about (rows + 6) row-group times (two recomputed rows, pipeline fill and
+        // drain) and one CTA runs per SM, so the step takes ceil(tiles / SMs) * (hs + 6): pick the
+        // segment height in [ALB_S2_HS_MIN, ALB_S2_HS_MAX] that minimises it.  Taller segments are not
+        // better per se: the list-driven passes on the aux stream only get SMs when a tile retires
+        // (measured on 32768x16384: 128..256 rows 125 GLUPS, 443 rows 123, 1024 rows 115).
+        long long best_cost = -1;
+        int best = rows < ALB_S2_HS_MAX ? rows : ALB_S2_HS_MAX;
+        for (int nsegs = (rows + ALB_S2_HS_MAX - 1) / ALB_S2_HS_MAX; nsegs <= rows; nsegs++) {
+            const int hs = (rows + nsegs - 1) / nsegs;
+            if (hs < ALB_S2_HS_MIN && best_cost >= 0) break;
+            const long long tiles = (long long)p.nstrips * ((rows + hs - 1) / hs);
+            const long long cost = ((tiles + nsm - 1) / nsm) * (hs + 6);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                best = hs;
+            }
         }
         p.hs = best;
     }
