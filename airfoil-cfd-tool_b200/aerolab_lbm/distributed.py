@@ -75,6 +75,12 @@ class Comm:
         self._dist.all_reduce(t, op=ops[op])
         return t.cpu().numpy()
 
+    def allgather_float(self, x: float) -> List[float]:
+        """One float per rank, known to every rank afterwards."""
+        v = np.zeros(self.world)
+        v[self.rank] = float(x)
+        return [float(a) for a in self.allreduce(v, "sum")]
+
     def all_gather_bytes(self, b: bytes) -> List[bytes]:
         if not self._dist:
             return [b]
@@ -152,34 +158,94 @@ class _DevRow:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (addr, False), "version": 2}
 
 
+def resplit_rows(rows: Sequence[int], times: Sequence[float], ny: int, min_rows: int = 8) -> List[int]:
+    """New rows per slab from the measured time of each slab: proportional to the measured speed
+    (rows per millisecond), damped by averaging with the old split (the cost is not uniform inside
+    a slab, so one proportional step overshoots), at least ``min_rows`` each, adding up to ``ny``."""
+    speed = [r / max(t, 1e-9) for r, t in zip(rows, times)]
+    tot = sum(speed)
+    new = [max(min_rows, int(round(ny * sp / tot))) for sp in speed]
+    out = [max(min_rows, (a + b) // 2) for a, b in zip(rows, new)]
+    out[out.index(max(out))] += ny - sum(out)
+    if min(out) < 1:
+        raise ValueError("cannot split %d rows over %d slabs with at least %d rows each" % (ny, len(rows), min_rows))
+    return out
+
+
 class DistributedTunnel:
     """A lattice split into one y-slab per rank; same control surface as WindTunnel."""
 
     def __init__(self, nx: int, ny: int, comm: Optional[Comm] = None, device: int = 0, halo: str = "p2p",
-                 u0: float = 0.06, tau: float = 0.58):
-        from .tunnel import WindTunnel
+                 u0: float = 0.06, tau: float = 0.58, rows: Optional[Sequence[int]] = None):
+        """``rows``: rows per rank (bottom slab first); default: as equal as possible."""
         self.comm = comm or Comm()
         self.nx, self.ny = nx, ny
-        self.y0, self.ny_local = slab_rows(ny, self.comm.world, self.comm.rank)
-        if self.ny_local < 1:
-            raise ValueError("more ranks than lattice rows")
-        self.t = WindTunnel(nx, ny, device, u0=u0, tau=tau, y0=self.y0, ny_local=self.ny_local)
-        self.halo = halo if self.comm.world > 1 else "none"
-        self._xchg = None
-        self._row_cache = {}
         self.device = device
+        self._u0, self._tau = u0, tau
+        self.halo = halo if self.comm.world > 1 else "none"
         self.cl_smooth = None
         self.cd_smooth = None
         self.sep_frac = 0.0
         self.max_s, self.cp_min, self.cp_max = 0.6, -1.0, 1.0
+        self.t = None
+        self._build(rows, connect=True)
+
+    def _build(self, rows, connect: bool):
+        """(Re-)create this rank's slab; ``connect=False`` leaves it isolated (timing runs)."""
+        from .tunnel import WindTunnel
+        if self.t is not None:
+            self.t.sync()
+            self.t.close()
+        w, r = self.comm.world, self.comm.rank
+        if rows is None:
+            self.rows = [slab_rows(self.ny, w, k)[1] for k in range(w)]
+        else:
+            self.rows = [int(v) for v in rows]
+            if len(self.rows) != w or sum(self.rows) != self.ny or min(self.rows) < 1:
+                raise ValueError("rows must give every rank at least one row and add up to ny")
+        self.y0, self.ny_local = sum(self.rows[:r]), self.rows[r]
+        if self.ny_local < 1:
+            raise ValueError("more ranks than lattice rows")
+        self.t = WindTunnel(self.nx, self.ny, self.device, u0=self._u0, tau=self._tau, y0=self.y0,
+                            ny_local=self.ny_local)
+        self._xchg = None
+        self._row_cache = {}
+        if not connect:
+            return
         if self.halo == "p2p":
             blobs = self.comm.all_gather_bytes(self.t.ipc_export())
-            r, w = self.comm.rank, self.comm.world
             self.t.ipc_connect(blobs[r - 1] if r > 0 else None, blobs[r + 1] if r < w - 1 else None)
             self.comm.barrier()
         elif self.halo == "nccl":
             self.t.set_external_halo(True)
             self._xchg = TorchHaloExchange(self.comm, self._torch_rows)
+
+    def rebalance(self, calib_steps: int = 12, rounds: int = 2, min_rows: int = 8):
+        """Static load balancing of the slabs, before the run starts (the flow is reset).
+
+        Rows are not equally expensive: slabs that contain the body spend extra time in the
+        general-task kernels, and with equal slabs everybody waits for them every step.  Each round
+        times ``calib_steps`` steps of every slab in isolation (unconnected, so no slab waits for
+        another), all-gathers the times and re-splits the rows in proportion to the measured speed.
+        Returns the final rows per rank.  No-op on one rank."""
+        if self.comm.world == 1 or self.t.coords is None:
+            return list(self.rows)
+        coords, name, alpha = self.t.coords, self.t.name, self.t.alpha
+        rows = list(self.rows)
+        for _ in range(rounds):
+            self._build(rows, connect=False)
+            self.t.load_coords(coords, name=name, alpha=alpha)
+            self.t.step(calib_steps)            # warm-up: graph capture, first-touch
+            self.t.sync()
+            self.t.step(calib_steps)
+            ms = self.t.last_step_ms()
+            times = self.comm.allgather_float(ms)
+            rows = resplit_rows(rows, times, self.ny, min_rows)
+            self.calib_ms = times
+        self._build(rows, connect=True)
+        self.t.load_coords(coords, name=name, alpha=alpha)
+        self.comm.barrier()
+        return list(self.rows)
 
     # -- halo rows as torch tensors (nccl transport) ---------------------------------
     def _torch_rows(self):

@@ -1640,6 +1640,21 @@ int alb_selftest_division(alb_handle *h, unsigned long long seed, long long pair
     return ALB_OK;
 }
 
+int alb_debug_step2_plan(int nx, int ny_local, int nsm, int *out5) {
+    if (!out5 || nx < 1 || ny_local < 1 || nsm < 1) return ALB_ERR_INVALID;
+    Step2Params q;
+    memset(&q, 0, sizeof q);
+    q.pitch = (nx + TASK_CELLS - 1) / TASK_CELLS * TASK_CELLS;
+    q.nyl = ny_local;
+    step2_plan(q, nsm);
+    out5[0] = q.nstrips;
+    out5[1] = q.wo;
+    out5[2] = q.hs;
+    out5[3] = q.ntiles;
+    out5[4] = step2_strip_width();
+    return ALB_OK;
+}
+
 int alb_launch_count(const alb_handle *h, long long *launches) {
     if (!h || !launches) return ALB_ERR_INVALID;
     *launches = h->launches;

@@ -176,6 +176,7 @@ cudaError_t launch_step_fast_list(const StepParams &p, cudaStream_t s);   // p.g
 cudaError_t launch_copy_tasks(const StepParams &p, cudaStream_t s);       // dst = src on the listed tasks
 // geometry of the fused two-step kernel for a pitch x nyl slab: fills wo/hs/nstrips/ntiles
 void step2_plan(Step2Params &p, int nsm);
+int step2_strip_width();   // 128 * K of the compiled kernel shape
 cudaError_t launch_step2(const Step2Params &p, cudaStream_t s);
 cudaError_t launch_div_selftest(unsigned long long seed, int nblocks, int iters, unsigned long long *d_out3, cudaStream_t s);
 int small_lattice_capacity(int device);

@@ -1470,6 +1470,8 @@ cudaError_t launch_copy_tasks(const StepParams &p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+int step2_strip_width() { return 128 * ALB_S2_K; }
+
 void step2_plan(Step2Params &p, int nsm) {
     constexpr int WI = 128 * ALB_S2_K;
     const int wo_max = WI - 8;

@@ -222,6 +222,9 @@ def main():
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="weak: configs[3] width, 2048 rows per GPU (32768 x 2048*N), fixed work per GPU")
+    ap.add_argument("--balance", default="auto", choices=["auto", "equal", "measured"],
+                    help="rows per GPU: equal, or re-split before the run in proportion to the measured speed of "
+                         "each slab (auto: measured for strong scaling on more than one GPU with the p2p halo)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -254,6 +257,13 @@ def main():
     tun.load_shape(shape, alpha=alpha)
     tun.sync()
     comm.barrier()
+    balance = args.balance
+    if balance == "auto":
+        balance = "measured" if (world > 1 and args.halo == "p2p" and args.scaling == "strong") else "equal"
+    if balance == "measured" and world > 1:
+        tun.rebalance()          # set-up, outside every timed region; the flow starts from rest afterwards
+        tun.sync()
+        comm.barrier()
 
     cells_global = nx * ny
     # ---- device-resident throughput (`value`) ---------------------------------
@@ -339,7 +349,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {shape} alpha={alpha} on {nx}x{ny}, U0={U0}, tau={TAU}",
-                       "decomposition": f"{world} y-slab(s), one-row population halo ({args.halo})",
+                       "decomposition": f"{world} y-slab(s), one-row population halo ({args.halo}), rows per GPU "
+                                        f"{balance}: {tun.rows}",
                        "l2": "populations (2 x %.1f GB per GPU) are far larger than the 126 MB L2; no flush needed"
                              % (36.0 * cells_local / 1e9),
                        "timing": "CUDA events on the launching stream, max over ranks"},

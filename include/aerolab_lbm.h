@@ -257,6 +257,10 @@ int alb_set_external_halo(alb_handle *h, int on);
 int alb_set_double_steps(alb_handle *h, int mode);
 /* mode as set; active = 1 when step batches of this handle use double steps. */
 int alb_get_double_steps(const alb_handle *h, int *mode, int *active);
+/* Host-only (no device needed): the tiling the fused two-step kernel would use for
+ * an nx-wide slab of ny_local rows on a GPU with nsm SMs.  out5 = {strips, output
+ * columns per strip, rows per segment, tiles, strip width of the kernel}. */
+int alb_debug_step2_plan(int nx, int ny_local, int nsm, int *out5);
 /* Number of CUDA kernels the step batches of this handle have launched so far
  * (alb_step / alb_run_frames; kernels inside replayed CUDA graphs included). */
 int alb_launch_count(const alb_handle *h, long long *launches);

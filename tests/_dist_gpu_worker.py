@@ -17,12 +17,18 @@ from aerolab_lbm import distributed as dm  # noqa: E402
 def main():
     halo = sys.argv[1]
     nx, ny, nsteps = 512, 250, 48
+    balanced = False
     if halo.endswith("-double"):
         halo, nx = halo[:-len("-double")], 1400
+    if halo.endswith("-balanced"):
+        halo, balanced = halo[:-len("-balanced")], True
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     comm = dm.init_comm(world, rank, local)
     tun = dm.DistributedTunnel(nx, ny, comm, device=local, halo=halo)
     tun.load_shape("naca4412", alpha=9.0)
+    if balanced:
+        rows = tun.rebalance(calib_steps=4)      # measured re-split of the slabs; the flow starts from rest again
+        assert sum(rows) == ny and len(rows) == world
     tun.step(nsteps // 2)
     tun.step(nsteps - nsteps // 2)
     tun.sync()

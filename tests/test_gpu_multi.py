@@ -43,7 +43,7 @@ def test_two_device_slabs_bitwise(al, nx, ny, double):
     assert np.array_equal(me, whole.me_history(1)[0])
 
 
-@pytest.mark.parametrize("halo", ["p2p", "nccl", "p2p-double"])
+@pytest.mark.parametrize("halo", ["p2p", "nccl", "p2p-double", "p2p-balanced-double"])
 def test_distributed_tunnel_torchrun(al, halo):
     """One process per GPU (torchrun, NCCL plumbing): IPC/NVLink halo push and the NCCL fallback
     must both reproduce the single-GPU run bit for bit."""
@@ -53,7 +53,7 @@ def test_distributed_tunnel_torchrun(al, halo):
     from conftest import ROOT
     n = min(al.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
-           "--master-addr", "127.0.0.1", "--master-port", {"p2p": "29577", "nccl": "29578"}.get(halo, "29579"),
+           "--master-addr", "127.0.0.1", "--master-port", {"p2p": "29577", "nccl": "29578", "p2p-double": "29579"}.get(halo, "29580"),
            os.path.join(ROOT, "tests", "_dist_gpu_worker.py"), halo]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -74,3 +74,20 @@ def test_resolve_parser_error_message(monkeypatch):
         dat.resolve_parser(None)
     assert "parse_dat_file" in str(e.value)
     assert dat.resolve_parser(dat.read_plain_dat) is dat.read_plain_dat
+
+
+def test_resplit_rows_balances_and_conserves():
+    """Static slab balancing (DistributedTunnel.rebalance): pure host arithmetic."""
+    from aerolab_lbm.distributed import resplit_rows
+    rows = [2048] * 8
+    times = [1.0, 1.0, 1.0, 1.15, 1.15, 1.0, 1.0, 1.0]      # the slabs with the body are slower
+    new = resplit_rows(rows, times, 16384)
+    assert sum(new) == 16384 and min(new) >= 8
+    assert new[3] < 2048 and new[4] < 2048 and new[0] > 2048
+    # equal times: nothing changes
+    assert resplit_rows(rows, [2.0] * 8, 16384) == rows
+    # a fixed point of the iteration: time proportional to rows
+    r2 = resplit_rows(new, [t * n / 2048 for t, n in zip(times, new)], 16384)
+    assert sum(r2) == 16384 and all(abs(a - b) < 120 for a, b in zip(r2, new))
+    # tiny lattices keep at least min_rows per slab
+    assert min(resplit_rows([10, 10, 10], [1.0, 50.0, 1.0], 30, min_rows=4)) >= 4
