@@ -82,6 +82,11 @@ struct alb_handle {
     bool solid_synced = false;    // both ping-pong buffers hold the same values on the all-solid tasks (lists[4])
     int double_mode = -1;         // -1 automatic, 0 never, 1 whenever possible (AEROLAB_LBM_DOUBLE / alb_set_option)
     int graph_parity = 0;         // h->parity the graph was captured at
+    // AEROLAB_LBM_TRACE=<step>: CUDA events around the parts of the double step that starts at that
+    // step count, printed by the next alb_sync()/alb_last_step_ms() (a measurement aid, see tools/)
+    long long trace_step = -1;
+    bool trace_armed = false;
+    cudaEvent_t tev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     long long launches = 0;       // kernels launched by step batches so far (graph replays included)
     long long graph_launches = 0; // kernels inside one replay of the captured graph
     int prev_idx = 1;             // buffer that holds the PREVIOUS state (what the lazy macro pass reads);
@@ -375,7 +380,22 @@ int copy_out_rows(alb_handle *h, void *dst_host, const void *src_dev_row1, size_
     return ALB_OK;
 }
 
+void print_trace(alb_handle *h) {
+    if (!h->trace_armed) return;
+    h->trace_armed = false;
+    if (cudaEventSynchronize(h->tev[6]) != cudaSuccess) return;
+    const char *names[7] = {"fork", "pass1 flags in", "pass1 done", "pass2 flags in", "pass2 done", "step2_kernel done", "joined"};
+    fprintf(stderr, "[alb trace] device %d rows %d..%d, double step at step %lld:", h->device, h->y0, h->y0 + h->nyl - 1,
+            h->trace_step);
+    for (int k = 1; k < 7; k++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->tev[0], h->tev[k]) == cudaSuccess) fprintf(stderr, "  %s %.3f ms", names[k], ms);
+    }
+    fprintf(stderr, "\n");
+}
+
 int check_wait_error(alb_handle *h) {
+    print_trace(h);
     if (h->h_err && *h->h_err) {
         *h->h_err = 0;
         return h->fail(ALB_ERR_TIMEOUT, "timed out waiting for a neighbouring slab's halo");
@@ -414,6 +434,8 @@ void free_handle(alb_handle *h) {
     cudaFree(h->d_yp);
     cudaFree(h->d_part);
     for (auto &t : h->d_tmp) cudaFree(t);
+    for (auto &ev : h->tev)
+        if (ev) cudaEventDestroy(ev);
     if (h->h_part) cudaFreeHost(h->h_part);
     if (h->h_err) cudaFreeHost(h->h_err);
     if (h->h_diag) cudaFreeHost(h->h_diag);
@@ -503,8 +525,15 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        // general-task kernel: high priority (measured: priority makes no difference)
-        CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, prio_hi));
+        // The aux stream runs the general-task kernel of single steps and the list-driven passes of
+        // double steps.  NORMAL priority: with a high-priority aux stream the passes cut into the fused
+        // step2_kernel at its wave boundaries and every double step of a slab costs 2.47 instead of
+        // 2.23 ms (measured on one GPU with AEROLAB_LBM_FAKE_HALO=1; 434 -> see DESIGN.md section 7 at 4
+        // GPUs).  At normal priority they run before the fused kernel's CTAs when they are ready first,
+        // else in its tail.  AEROLAB_LBM_AUX_PRIO=1 restores the high priority for measurements.
+        (void)prio_lo;
+        CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking,
+                                        getenv("AEROLAB_LBM_AUX_PRIO") && atoi(getenv("AEROLAB_LBM_AUX_PRIO")) == 1 ? prio_hi : prio_lo));
         CK(cudaEventCreate(&h->ev0));
         CK(cudaEventCreate(&h->ev1));
         CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -559,6 +588,10 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device));
         h->use_graph = getenv("AEROLAB_LBM_NO_GRAPH") == nullptr;   // A/B switch for measurements
         if (const char *e = getenv("AEROLAB_LBM_DOUBLE")) h->double_mode = atoi(e) != 0 ? 1 : 0;
+        if (const char *e = getenv("AEROLAB_LBM_TRACE")) {
+            h->trace_step = atoll(e);
+            for (auto &ev : h->tev) CK(cudaEventCreate(&ev));
+        }
         return ALB_OK;
     };
     rc = body();
@@ -767,6 +800,8 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
             CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc) * DIAG_SLOTS, cudaMemcpyHostToDevice, h->stream));
         h->diag_prearmed = false;
     }
+    const bool trace = h->trace_step >= 0 && sync_step == h->trace_step && h->tev[0];
+    if (trace) CK(cudaEventRecord(h->tev[0], h->stream));
     CK(cudaEventRecord(h->ev_fork, h->stream));
     CK(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
     for (int pass = 0; pass < 2; pass++) {
@@ -776,6 +811,7 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
             set_peers(h, p, pass == 0 ? 2 : dst_idx);
         }
         if (diag && pass == 1) arm_diag(h, p);
+        if (trace) CK(cudaEventRecord(h->tev[1 + 2 * pass], h->aux));      // the neighbours' flags have arrived
         p.gen_list = h->lists[2 * pass];
         p.ngen = h->nlist[2 * pass];
         CK(launch_step_fast_list(p, h->aux));
@@ -793,6 +829,7 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
             h->launches++;
         }
         if (halo) halo_signal(h, sync_step + pass + 1, h->aux);
+        if (trace) CK(cudaEventRecord(h->tev[2 + 2 * pass], h->aux));      // pass finished and signalled
     }
     CK(cudaEventRecord(h->ev_join, h->aux));
     Step2Params q;
@@ -814,7 +851,12 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
     // reads a ghost row, and the GPUs only meet in the short list-driven passes
     CK(launch_step2(q, h->stream));
     h->launches += q.ntiles > 0 ? 1 : 0;
+    if (trace) CK(cudaEventRecord(h->tev[5], h->stream));                  // fused kernel finished
     CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    if (trace) {
+        CK(cudaEventRecord(h->tev[6], h->stream));                         // joined
+        h->trace_armed = true;
+    }
     return ALB_OK;
 }
 
@@ -894,7 +936,10 @@ extern "C" {
 
 // nsteps >= 1 steps; the last one also reduces the new state's statistics / face sums
 static int step_batch(alb_handle *h, int nsteps) {
-    const bool halo = !h->external_halo && (h->lo.base || h->hi.base);
+    // AEROLAB_LBM_FAKE_HALO=1 (measurement aid): issue the wait/signal kernels of the slab protocol even
+    // without neighbours (they return at once), to see what the protocol itself costs on one GPU
+    static const bool fake_halo = getenv("AEROLAB_LBM_FAKE_HALO") != nullptr;
+    const bool halo = !h->external_halo && (h->lo.base || h->hi.base || fake_halo);
     int left = nsteps;
     const bool doubles = double_steps_enabled(h);
     const bool persistent = !doubles && h->whole() && !halo && !h->external_halo && nsteps >= 2 &&

@@ -176,3 +176,27 @@ def test_double_steps_local_slabs(al, splits):
         assert_bitwise(np.concatenate([s.macro()[k] for s in slabs], 0), wm[k], f"slab macro {k}")
     me = sum(s.me_history(1)[0] for s in slabs)
     assert np.array_equal(me, whole.me_history(1)[0])
+
+
+def test_double_steps_restart(al):
+    """dump_state / load_state in the middle of a double-step run (the all-solid tasks of the other
+    ping-pong buffer are stale after set_populations and must be copied again)."""
+    nx, ny = 1300, 220
+    t = al.WindTunnel(nx, ny, 0)
+    t.set_double_steps(1)
+    t.load_shape("naca4412", alpha=12.0)
+    o = olbm.OracleTunnel(nx, ny)
+    o.apply_geometry(ogeo.SHAPES["naca4412"](), 12.0)
+    t.step(10); o.step(10)
+    st = t.dump_state()
+    t.step(6)                      # diverge ...
+    t.load_state(st)               # ... and come back
+    t.step(8); o.step(8)
+    compare_state(t, o, "restart in double mode")
+    t2 = al.WindTunnel(nx, ny, 0)
+    t2.set_double_steps(1)
+    t2.load_shape("naca4412", alpha=12.0)
+    t2.load_state(st)
+    t2.step(8)
+    assert_bitwise(t2.populations(), o.F, "fresh tunnel restarted from the dump")
+    t.close(); t2.close()
