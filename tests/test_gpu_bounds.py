@@ -59,12 +59,16 @@ def test_bounds_checked_build_runs_clean(tmp_path):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     lib = os.path.join(ROOT, "variants", "lib_bounds.so")
-    if not os.path.exists(lib):
+    srcs = [os.path.join(mod.CSRC, d) for d in mod.DEPS]
+    stale = not os.path.exists(lib) or any(os.path.getmtime(p) > os.path.getmtime(lib) for p in srcs)
+    if stale:
         try:
             mod.nvcc_path()
         except RuntimeError:
-            pytest.skip("no nvcc and no prebuilt variants/lib_bounds.so")
-        mod.build(defines=["ALB_DEBUG_BOUNDS=1"], out=lib)
+            if not os.path.exists(lib):
+                pytest.skip("no nvcc and no prebuilt variants/lib_bounds.so")
+        else:
+            mod.build(defines=["ALB_DEBUG_BOUNDS=1"], out=lib)
     r = subprocess.run([sys.executable, "-c", SCRIPT], env=dict(os.environ, AEROLAB_LBM_LIB=lib),
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "BOUNDS_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
