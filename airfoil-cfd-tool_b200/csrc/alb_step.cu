@@ -78,6 +78,16 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef ALB_S2_ASYNC
 #define ALB_S2_ASYNC 0
 #endif
+// step2_kernel, experimental: re-split the register file between the roles after launch (setmaxnreg)
+#ifndef ALB_S2_SETMAXNREG
+#define ALB_S2_SETMAXNREG 0
+#endif
+#ifndef ALB_S2_REGS_A
+#define ALB_S2_REGS_A 96
+#endif
+#ifndef ALB_S2_REGS_B
+#define ALB_S2_REGS_B 64
+#endif
 
 
 // ALB_DEBUG_BOUNDS=1 (compute-sanitizer is not available on the pool): every population load and
@@ -707,10 +717,13 @@ __device__ __forceinline__ bool quad_accept(float r, float spd2, bool nums_ok) {
 #ifndef ALB_QUAD_G
 #define ALB_QUAD_G 4
 #endif
+#ifndef ALB_QUAD_GB          // the same for the step-2 warps of step2_kernel
+#define ALB_QUAD_GB ALB_QUAD_G
+#endif
 // mac: optional, receives rho/ux/uy of the four cells (what the shader writes to its macro texture)
+template <int G = ALB_QUAD_G>
 __device__ __forceinline__ unsigned collide_quad(float4 (&o)[9], float tau, float rcp, float rcp_lo,
                                                  float (*mac)[3] = nullptr) {
-    constexpr int G = ALB_QUAD_G;
     unsigned hitmask = 0;
 #pragma unroll
     for (int k0 = 0; k0 < 4; k0 += G) {
@@ -851,6 +864,14 @@ step2_kernel(const __grid_constant__ Step2Params p) {
     [[maybe_unused]] float *const dst_base = p.dst;
     const uint8_t *tfl = p.tflags + (inx ? (gx >> 7) : 0);
     unsigned hits = 0;
+#if ALB_S2_SETMAXNREG
+    // Experimental: the step-1 warps need ~100 registers (36 of them hold the next task's loads across
+    // the barrier), the step-2 warps far fewer; with warpgroup-aligned roles the register file can be
+    // re-split after launch, so that 24 warps fit without spills (compile with RB*K a multiple of 4).
+    static_assert(!ALB_S2_SETMAXNREG || (RB * K) % 4 == 0, "roles must be whole warpgroups");
+    if (!role_b) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ALB_S2_REGS_A));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ALB_S2_REGS_B));
+#endif
 
     if (!role_b) {
         // ---- A warps: step 1, HBM -> ring.  The loads of the NEXT row group are issued before the
@@ -1063,7 +1084,7 @@ step2_kernel(const __grid_constant__ Step2Params p) {
                 o[7] = from_right(v7, r7, lane);
                 o[8] = from_left(v8, l8, lane);
                 float mac[4][3];
-                const unsigned hm = collide_quad(o, p.tau, p.inv_tau, p.inv_tau_lo, DIAG ? mac : nullptr);
+                const unsigned hm = collide_quad<ALB_QUAD_GB>(o, p.tau, p.inv_tau, p.inv_tau_lo, DIAG ? mac : nullptr);
                 if (st) {
                     hits += __popc(hm);
                     float *d = p.dst + (size_t)j * p.pitch + gx;
