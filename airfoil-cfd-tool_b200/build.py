@@ -18,8 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "aerolab_lbm", "_lib")
 OUT = os.path.join(OUT_DIR, "libaerolab_lbm.so")
-SOURCES = ["alb_api.cu", "alb_step.cu", "alb_geometry.cu", "alb_diag.cu", "alb_particles.cu"]
-DEPS = SOURCES + ["alb_common.cuh", os.path.join("..", "..", "include", "aerolab_lbm.h")]
+SOURCES = ["alb_api.cu", "alb_step.cu", "alb_step2.cu", "alb_geometry.cu", "alb_diag.cu", "alb_particles.cu"]
+DEPS = SOURCES + ["alb_common.cuh", "alb_lbm.cuh", os.path.join("..", "..", "include", "aerolab_lbm.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -22,361 +22,13 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include "alb_common.cuh"
+#include "alb_lbm.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace alb {
 
 namespace {
-
-constexpr unsigned FULL = 0xffffffffu;
-
-// Tuning knobs (defaults chosen from B200 measurements, see DESIGN.md / profiles/):
-//   ALB_LD_HINT  0 ld.global.nc   1 ld.global.cs (evict first)   2 ld.global.nc.L1::no_allocate
-//   ALB_ST_HINT  0 st.global      1 st.global.cs (evict first)
-//   ALB_FAST_MINBLOCKS  resident CTAs per SM the fast kernel is compiled for
-#ifndef ALB_LD_HINT
-#define ALB_LD_HINT 0
-#endif
-#ifndef ALB_ST_HINT
-#define ALB_ST_HINT 0
-#endif
-//   ALB_EDGE_IN_FAST  (alb_common.cuh) inlet/outlet cells of otherwise all-fluid tasks patched in the fast kernel
-//   ALB_DIAG_MINBLOCKS  resident CTAs per SM the DIAG variant of the fast kernel is compiled for
-#ifndef ALB_DIAG_MINBLOCKS
-#define ALB_DIAG_MINBLOCKS 4
-#endif
-#ifndef ALB_FAST_MINBLOCKS
-#define ALB_FAST_MINBLOCKS 4
-#endif
-
-// Shape of the fused two-step kernel: RB rows per group, K 128-cell segments per strip.
-#ifndef ALB_S2_RB
-#define ALB_S2_RB 2
-#endif
-#ifndef ALB_S2_K
-#define ALB_S2_K 5
-#endif
-#ifndef ALB_S2_HS_MAX
-#define ALB_S2_HS_MAX 256
-#endif
-#ifndef ALB_S2_HS_MIN
-#define ALB_S2_HS_MIN 64
-#endif
-// 1: step2t_kernel (TMA-fed staging ring, NST stages), 0: step2_kernel (loads through registers)
-#ifndef ALB_S2_TMA
-#define ALB_S2_TMA 0
-#endif
-#ifndef ALB_S2_NST
-#define ALB_S2_NST 3
-#endif
-// step2_kernel: 1 = the A warps prefetch their next task with TMA bulk copies into private shared-memory
-// staging instead of loading it into registers just before the barrier.  Measured on 32768x16384:
-// long_scoreboard stalls drop from 15 % to 3 % of the samples, but the step is SLOWER (116 vs 125 GLUPS;
-// a cp.async version: 116-123) -- see DESIGN.md section 4.2.
-#ifndef ALB_S2_ASYNC
-#define ALB_S2_ASYNC 0
-#endif
-// step2_kernel, experimental: re-split the register file between the roles after launch (setmaxnreg)
-#ifndef ALB_S2_SETMAXNREG
-#define ALB_S2_SETMAXNREG 0
-#endif
-#ifndef ALB_S2_REGS_A
-#define ALB_S2_REGS_A 96
-#endif
-#ifndef ALB_S2_REGS_B
-#define ALB_S2_REGS_B 64
-#endif
-
-
-// ALB_DEBUG_BOUNDS=1 (compute-sanitizer is not available on the pool): every population load and
-// store of the step kernels is checked against the source / destination allocation; a violation
-// prints the address and traps, which the C ABI reports as a CUDA error.
-#ifndef ALB_DEBUG_BOUNDS
-#define ALB_DEBUG_BOUNDS 0
-#endif
-#if ALB_DEBUG_BOUNDS
-// the kernels keep the bases in locals named src / dst_base / plane
-#define ALB_CHECK_SRC(ptr, n) alb_check((ptr), (n), src, 9 * plane, "load")
-#define ALB_CHECK_DST(ptr, n) alb_check((ptr), (n), dst_base, 9 * plane, "store")
-__device__ __noinline__ void alb_check(const float *ptr, int n, const float *base, size_t len, const char *what) {
-    if (ptr < base || ptr + n > base + len || (n == 4 && (reinterpret_cast<uintptr_t>(ptr) & 15))) {
-        printf("alb bounds violation: %s of %d floats at offset %lld (allocation %llu floats)\n", what, n,
-               (long long)(ptr - base), (unsigned long long)len);
-        __trap();
-    }
-}
-#else
-#define ALB_CHECK_SRC(ptr, n) ((void)0)
-#define ALB_CHECK_DST(ptr, n) ((void)0)
-#endif
-#define LD4(ptr) (ALB_CHECK_SRC((ptr), 4), ld4(ptr))
-#define LD1(ptr) (ALB_CHECK_SRC((ptr), 1), __ldg(ptr))
-#define LD1CG(ptr) (ALB_CHECK_SRC((ptr), 1), __ldcg(ptr))
-#define ST4(ptr, v) (ALB_CHECK_DST((ptr), 4), st4((ptr), (v)))
-
-__device__ __forceinline__ float4 ld4(const float *p) {
-#if ALB_LD_HINT == 1
-    return __ldcs(reinterpret_cast<const float4 *>(p));
-#elif ALB_LD_HINT == 2
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-#else
-    return __ldg(reinterpret_cast<const float4 *>(p));
-#endif
-}
-__device__ __forceinline__ void st4(float *p, const float4 &v) {
-#if ALB_ST_HINT == 1
-    __stcs(reinterpret_cast<float4 *>(p), v);
-#else
-    *reinterpret_cast<float4 *>(p) = v;
-#endif
-}
-
-// x / tau, correctly rounded (== IEEE division), for the uniform divisor tau.
-// rcp = RN(1/tau) and rcp_lo = RN(1/tau - rcp) are computed once on the host.  x*(rcp + rcp_lo),
-// rounded once by the FMA, is a faithful estimate of the quotient; by Markstein's theorem one
-// correction with the exact residual (FMA) and the correctly rounded reciprocal then yields
-// RN(x/tau).  4 instructions instead of the ~10 + slow path of the generic division.  (Operands
-// here are differences of populations: 0 or >= 2^-30 in magnitude, far from underflow.)  Checked
-// exhaustively against true division in tests/test_div_by_tau.py.
-__device__ __forceinline__ float div_by_tau(float x, float tau, float rcp, float rcp_lo) {
-    const float t = __fmul_rn(x, rcp_lo);
-    float q = __fmaf_rn(x, rcp, t);
-    const float r = __fmaf_rn(-tau, q, x);
-    q = __fmaf_rn(r, rcp, q);
-    return q;
-}
-
-struct Moments {
-    float rho, ux, uy;
-    bool hit;
-};
-
-// HTML:335-350: moments of the streamed populations, then the stability clamps.
-__device__ __forceinline__ Moments moments_clamped(const float (&f)[9]) {
-    Moments m;
-    float rho = f[0];
-    rho = rho + f[1];
-    rho = rho + f[2];
-    rho = rho + f[3];
-    rho = rho + f[4];
-    rho = rho + f[5];
-    rho = rho + f[6];
-    rho = rho + f[7];
-    rho = rho + f[8];
-    float ux = (f[1] + f[5] + f[8] - f[3] - f[6] - f[7]) / rho;
-    float uy = (f[2] + f[5] + f[6] - f[4] - f[7] - f[8]) / rho;
-    const float uMax = 0.35f, rhoMin = 0.5f, rhoMax = 2.0f;
-    float rc = fminf(fmaxf(rho, rhoMin), rhoMax);
-    m.hit = (rc != rho);
-    float spd2 = ux * ux + uy * uy;
-    if (spd2 > uMax * uMax) {
-        float k = uMax / sqrtf(spd2);
-        ux *= k;
-        uy *= k;
-        m.hit = true;
-    }
-    m.rho = rc;
-    m.ux = ux;
-    m.uy = uy;
-    return m;
-}
-
-// plain moments of the outlet rule (HTML:305-307): no clamp
-__device__ __forceinline__ void moments_plain(const float (&f)[9], float &rho, float &ux, float &uy) {
-    rho = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8];
-    ux = (f[1] + f[5] + f[8] - f[3] - f[6] - f[7]) / rho;
-    uy = (f[2] + f[5] + f[6] - f[4] - f[7] - f[8]) / rho;
-}
-
-// HTML:276-281 and 352-356.  feq_i = wt(i)*rho*(1+3eu+4.5eu*eu-1.5uu), left to
-// right; opposite directions share 3*eu and 4.5*eu*eu (negating eu negates the
-// first exactly and leaves the second unchanged, so sharing is bit-neutral).
-// uu = ux*ux + uy*uy, passed in by callers that have it already (same operations, same value)
-__device__ __forceinline__ void collide_uu(float (&f)[9], const Moments &m, float uu, float tau, float rcp, float rcp_lo) {
-    const float w0 = 4.0f / 9.0f, ws = 1.0f / 9.0f, wd = 1.0f / 36.0f;
-    const float rho = m.rho, ux = m.ux, uy = m.uy;
-    const float c15 = 1.5f * uu;
-    const float wr0 = w0 * rho, wrs = ws * rho, wrd = wd * rho;
-    {
-        float eq = wr0 * (1.0f - c15);
-        f[0] = f[0] - div_by_tau(f[0] - eq, tau, rcp, rcp_lo);
-    }
-#define ALB_PAIR(A, B, EU, WR)                                      \
-    {                                                               \
-        const float eu = (EU);                                      \
-        const float t1 = 3.0f * eu;                                 \
-        const float t2 = (4.5f * eu) * eu;                          \
-        const float ea = (WR) * (((1.0f + t1) + t2) - c15);         \
-        const float eb = (WR) * (((1.0f - t1) + t2) - c15);         \
-        f[A] = f[A] - div_by_tau(f[A] - ea, tau, rcp, rcp_lo);              \
-        f[B] = f[B] - div_by_tau(f[B] - eb, tau, rcp, rcp_lo);              \
-    }
-    ALB_PAIR(1, 3, ux, wrs)
-    ALB_PAIR(2, 4, uy, wrs)
-    ALB_PAIR(5, 7, ux + uy, wrd)
-    ALB_PAIR(6, 8, uy - ux, wrd)
-#undef ALB_PAIR
-}
-__device__ __forceinline__ void collide(float (&f)[9], const Moments &m, float tau, float rcp, float rcp_lo) {
-    collide_uu(f, m, m.ux * m.ux + m.uy * m.uy, tau, rcp, rcp_lo);
-}
-
-__device__ __forceinline__ float comp(const float4 &v, int k) {
-    return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
-}
-__device__ __forceinline__ void setc(float4 &v, int k, float a) {
-    if (k == 0) v.x = a;
-    else if (k == 1) v.y = a;
-    else if (k == 2) v.z = a;
-    else v.w = a;
-}
-
-// populations arriving from x-1: own aligned vector shifted right by one cell
-__device__ __forceinline__ float4 from_left(const float4 &v, float edge, int lane) {
-    float t = __shfl_up_sync(FULL, v.w, 1);
-    if (lane == 0) t = edge;
-    return make_float4(t, v.x, v.y, v.z);
-}
-// populations arriving from x+1
-__device__ __forceinline__ float4 from_right(const float4 &v, float edge, int lane) {
-    float t = __shfl_down_sync(FULL, v.x, 1);
-    if (lane == 31) t = edge;
-    return make_float4(v.y, v.z, v.w, t);
-}
-
-constexpr int MODE_STEP = 0, MODE_MACRO = 1;
-
-// first thread of a step: commit the previous step's momentum-exchange sums, clear that accumulator
-__device__ __forceinline__ void me_begin_step(MeState *m, int parity) {
-    const int prev = parity ^ 1;
-    if (m->pending) {
-        const long long c = m->count;
-        m->ring[c % ME_RING][0] = m->acc[prev][0];
-        m->ring[c % ME_RING][1] = m->acc[prev][1];
-        m->count = c + 1;
-    }
-    m->acc[prev][0] = 0;
-    m->acc[prev][1] = 0;
-    m->pending = 1;
-}
-
-// ---- fused diagnostics of the macro pass (HTML:596-614 statistics, HTML:649-700 faces) ----------
-struct DiagLocal {
-    float rmin = INFINITY, rmax = -INFINITY;
-    float m2f = -1.0f;       // fp32 pre-filter: largest fp32 ux^2+uy^2 among the cells accepted so far
-    double m2 = -1.0;        // largest ux^2+uy^2 among cells with s < 4
-    float bux = 0.f, buy = 0.f;
-    long long fx = 0, fy = 0;
-    unsigned surf = 0, rev = 0;
-};
-
-__device__ __forceinline__ double speed_ratio(float ux, float uy, double U0) {
-    return hypot(__ddiv_rn((double)ux, U0), __ddiv_rn((double)uy, U0));   // Math.hypot(ux/U0, uy/U0)
-}
-
-// One non-solid lattice cell.  s is monotone in ux^2+uy^2 (exact in double), so only the arg-max
-// candidate ever needs the hypot; cells within 1e-9 of the s < 4 cut are decided exactly.
-template <class P>
-__device__ __forceinline__ void diag_cell(const P &p, DiagLocal &d, float rho, float ux, float uy) {
-    if (rho >= p.rho_lo && rho <= p.rho_hi) {
-        d.rmin = fminf(d.rmin, rho);
-        d.rmax = fmaxf(d.rmax, rho);
-    }
-    // fp32 pre-filter (relative error of m2f < 2e-7): a cell can only be the arg-max if its fp32
-    // value is within 1e-6 of the largest fp32 value seen so far; everything else skips the fp64 part
-    const float m2f = ux * ux + uy * uy;
-    if (!(m2f >= d.m2f * (1.0f - 1e-6f)) || m2f > p.m2f_cap) return;   // also drops NaN and s >= 4 for sure
-    const double m2 = __dadd_rn(__dmul_rn((double)ux, (double)ux), __dmul_rn((double)uy, (double)uy));
-    if (m2 > d.m2 && m2 < p.m2_hi) {
-        if (m2 >= p.m2_lo && !(speed_ratio(ux, uy, p.U0d) < 4.0)) return;
-        d.m2f = fmaxf(d.m2f, m2f);   // only ACCEPTED cells (s < 4) may raise the pre-filter level
-        d.m2 = m2;
-        d.bux = ux;
-        d.buy = uy;
-    }
-}
-
-// faces of a non-solid cell: bit i-1 of `links` (i = 1..4) says the cell at x - e_i is solid
-__device__ __forceinline__ void diag_faces(DiagLocal &d, unsigned links, float rho, float ux) {
-    const unsigned faces = links & 0xfu;
-    if (!faces) return;
-    const long long q = __double2ll_rn((double)rho * 0x1p40);
-    const int n = __popc(faces);
-    if (faces & 1u) d.fx -= q;   // solid at x-1: force on the body points to -x
-    if (faces & 4u) d.fx += q;   // solid at x+1
-    if (faces & 2u) d.fy -= q;   // solid at y-1
-    if (faces & 8u) d.fy += q;   // solid at y+1
-    d.surf += n;
-    if (ux < 0.0f) d.rev += n;
-}
-
-__device__ __forceinline__ void atomic_min_float(float *a, float v) {
-    int *ai = reinterpret_cast<int *>(a);
-    int old = *ai;
-    while (v < __int_as_float(old)) {
-        const int assumed = old;
-        old = atomicCAS(ai, assumed, __float_as_int(v));
-        if (old == assumed) break;
-    }
-}
-__device__ __forceinline__ void atomic_max_float(float *a, float v) {
-    int *ai = reinterpret_cast<int *>(a);
-    int old = *ai;
-    while (v > __int_as_float(old)) {
-        const int assumed = old;
-        old = atomicCAS(ai, assumed, __float_as_int(v));
-        if (old == assumed) break;
-    }
-}
-
-// warp tree, then at most a handful of atomics per warp -- and none at all once the global
-// extrema have settled (plain-load pre-check)
-// FACES = false for tasks that cannot have fluid/solid faces (all-fluid, all-equilibrium): the
-// four face sums are known to be zero and are left out of the shuffle tree.
-template <bool FACES = true, class P = StepParams>
-__device__ __forceinline__ void diag_flush(const P &p, DiagLocal &d, int lane) {
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-        d.rmin = fminf(d.rmin, __shfl_xor_sync(FULL, d.rmin, s));
-        d.rmax = fmaxf(d.rmax, __shfl_xor_sync(FULL, d.rmax, s));
-        const double om = __shfl_xor_sync(FULL, d.m2, s);
-        const float ox = __shfl_xor_sync(FULL, d.bux, s), oy = __shfl_xor_sync(FULL, d.buy, s);
-        if (om > d.m2) { d.m2 = om; d.bux = ox; d.buy = oy; }
-        if (FACES) {
-            d.fx += __shfl_xor_sync(FULL, d.fx, s);
-            d.fy += __shfl_xor_sync(FULL, d.fy, s);
-            d.surf += __shfl_xor_sync(FULL, d.surf, s);
-            d.rev += __shfl_xor_sync(FULL, d.rev, s);
-        }
-    }
-    if (lane != 0) return;
-    DiagAcc *g = p.diag + ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (DIAG_SLOTS - 1));
-    // pre-checks through L1 (ld.global.ca): a stale value only makes the filter less tight, the
-    // atomics below re-check against the true value
-    if (d.rmin < __ldca(&g->rho_min)) atomic_min_float(&g->rho_min, d.rmin);
-    if (d.rmax > __ldca(&g->rho_max)) atomic_max_float(&g->rho_max, d.rmax);
-    if (d.m2 >= 0.0) {
-        const double cur = __longlong_as_double((long long)__ldca(&g->m2max_bits));
-        if (d.m2 >= cur * (1.0 - 1e-12)) {
-            const double sr = speed_ratio(d.bux, d.buy, p.U0d);
-            if (sr < 4.0) {
-                atomicMax(&g->smax_bits, (unsigned long long)__double_as_longlong(sr));
-                atomicMax(&g->m2max_bits, (unsigned long long)__double_as_longlong(d.m2));
-            }
-        }
-    }
-    if (FACES && d.surf) {
-        atomicAdd(reinterpret_cast<unsigned long long *>(&g->fx), (unsigned long long)d.fx);
-        atomicAdd(reinterpret_cast<unsigned long long *>(&g->fy), (unsigned long long)d.fy);
-        atomicAdd(&g->surf, (unsigned long long)d.surf);
-        atomicAdd(&g->rev, (unsigned long long)d.rev);
-    }
-}
 
 // KIND_FAST: every task of the slab, but tasks of class TC_GENERAL are skipped -- 64 registers,
 // 4 CTAs per SM.  KIND_GENERAL: only the compacted list of TC_GENERAL tasks (tasks that mix cell
@@ -658,649 +310,6 @@ step_kernel(const __grid_constant__ StepParams p) {
 }
 
 
-// ---- two steps per pass over HBM (temporal blocking) ---------------------------------------------
-// The single-step kernel already moves exactly the algorithmic 72 B per cell update and runs at the
-// DRAM ceiling, so the only way up is to touch HBM less often: step2_kernel advances the deep
-// interior of the lattice by TWO steps while reading the state once and writing it once (36 B per
-// cell update).  A CTA owns a column strip of WI = 128*K cells and marches up the rows.  Half of
-// its warps ("A") run step 1 exactly like the fast kernel (aligned 128-bit loads from HBM, shuffle
-// shifts) but store the result into a ring of 3*RB rows in shared memory; the other half ("B")
-// run step 2 out of that ring, one row group behind, and store to HBM.  While the A warps wait
-// for their loads the B warps compute, so one __syncthreads per row group is all the coordination
-// needed.  Step 2 of a cell needs step 1 of its 8 neighbours, hence the strip's outermost 4
-// columns and the rows above/below a segment are computed redundantly (A only) and never stored.
-// Same moments_clamped()/collide() as everywhere else -> bit-identical to two single steps.
-// Everything that is not "deep" (border cells, the body and its surroundings, slab edge rows) is
-// advanced by two passes of the list-driven single-step kernels through a third buffer.
-// jx/r and jy/r with a shared reciprocal: the instruction sequence of nvcc's own div.rn.f32 fast
-// path (MUFU.RCP, one Newton step, quotient, exact residual, one correction).  It yields the
-// correctly rounded quotient as long as no intermediate leaves the normal range.  The caller only
-// uses the result when quad_accept() holds: rho within the clamp interval [0.5, 2] (so the
-// reciprocal is harmless), |u|^2 <= uMax^2 (which bounds the numerators from above; the negated
-// comparison also catches NaN), and each numerator either +0 or at least 2^-60 in magnitude (the
-// return value; -0 and anything tiny go to true division, which knows about signed zeros and
-// underflow).  tests/test_gpu_div.py compares accepted results with IEEE division.
-__device__ __forceinline__ bool div_pair(float jx, float jy, float r, float &vx, float &vy) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(r));
-    const float e = __fmaf_rn(-r, y, 1.0f);
-    y = __fmaf_rn(y, e, y);
-    const float qx = __fmaf_rn(jx, y, 0.0f), qy = __fmaf_rn(jy, y, 0.0f);
-    const float rx = __fmaf_rn(-r, qx, jx), ry = __fmaf_rn(-r, qy, jy);
-    vx = __fmaf_rn(y, rx, qx);
-    vy = __fmaf_rn(y, ry, qy);
-    const bool nx_ok = fabsf(jx) >= 0x1p-60f || __float_as_uint(jx) == 0u;
-    const bool ny_ok = fabsf(jy) >= 0x1p-60f || __float_as_uint(jy) == 0u;
-    return nx_ok && ny_ok;
-}
-// true: the fast path's rho/ux/uy ARE the shader's values (no clamp fires, division exact)
-__device__ __forceinline__ bool quad_accept(float r, float spd2, bool nums_ok) {
-    const float rc = fminf(fmaxf(r, 0.5f), 2.0f);
-    return nums_ok && rc == r && spd2 <= 0.35f * 0.35f;
-}
-
-// Four cells at once, written so that the common case is ONE basic block: the generic IEEE
-// division (range check + branch to a slow path) and the |u| clamp (branch) would otherwise cut
-// the code of every cell into pieces that the scheduler cannot interleave, and a warp then crawls
-// along one dependent chain at a time (ncu: ~7 cycles between issues of a warp).
-//   * ux = jx/rho and uy = jy/rho use the very sequence nvcc emits for the fast path of
-//     div.rn.f32 (MUFU.RCP, one Newton step, quotient, exact residual, one correction -- see the
-//     SASS of moments_clamped), sharing the reciprocal of rho.  It is valid when no intermediate
-//     leaves the normal range; here: 2^-40 <= rho <= 2^40 and the numerator is +0 or has
-//     2^-60 <= |j| <= 2^40 (checked on the bit patterns).  tests/test_gpu_div.py compares it with
-//     true division for ~10^10 operand pairs.
-//   * anything else -- operands outside that range, a rho or |u| clamp that fires -- sets a bit
-//     in `bad`; those cells are redone by moments_clamped(), the literal transcription of the
-//     shader, in a cold branch.  Clamp hits can only occur there.
-// ALB_QUAD_G cells are worked on together (4: all in one basic block, most ILP, most registers;
-// 2: two pairs; 1: one cell at a time).
-#ifndef ALB_QUAD_G
-#define ALB_QUAD_G 4
-#endif
-#ifndef ALB_QUAD_GB          // the same for the step-2 warps of step2_kernel
-#define ALB_QUAD_GB ALB_QUAD_G
-#endif
-// mac: optional, receives rho/ux/uy of the four cells (what the shader writes to its macro texture)
-template <int G = ALB_QUAD_G>
-__device__ __forceinline__ unsigned collide_quad(float4 (&o)[9], float tau, float rcp, float rcp_lo,
-                                                 float (*mac)[3] = nullptr) {
-    unsigned hitmask = 0;
-#pragma unroll
-    for (int k0 = 0; k0 < 4; k0 += G) {
-        float rho[G], ux[G], uy[G];
-        unsigned bad = 0;
-#pragma unroll
-        for (int kk = 0; kk < G; kk++) {
-            const int k = k0 + kk;
-            const float f0 = comp(o[0], k), f1 = comp(o[1], k), f2 = comp(o[2], k), f3 = comp(o[3], k), f4 = comp(o[4], k);
-            const float f5 = comp(o[5], k), f6 = comp(o[6], k), f7 = comp(o[7], k), f8 = comp(o[8], k);
-            float r = f0;
-            r = r + f1; r = r + f2; r = r + f3; r = r + f4; r = r + f5; r = r + f6; r = r + f7; r = r + f8;
-            const float jx = f1 + f5 + f8 - f3 - f6 - f7;
-            const float jy = f2 + f5 + f6 - f4 - f7 - f8;
-            float vx, vy;
-            const bool nums_ok = div_pair(jx, jy, r, vx, vy);
-            const float spd2 = vx * vx + vy * vy;
-            if (!quad_accept(r, spd2, nums_ok)) bad |= 1u << kk;
-            rho[kk] = r;          // in [0.5, 2] unless the cell is flagged
-            ux[kk] = vx;
-            uy[kk] = vy;
-        }
-        if (bad) {
-#pragma unroll
-            for (int kk = 0; kk < G; kk++) {
-                if (bad & (1u << kk)) {
-                    float f[9];
-#pragma unroll
-                    for (int i = 0; i < 9; i++) f[i] = comp(o[i], k0 + kk);
-                    const Moments m = moments_clamped(f);
-                    rho[kk] = m.rho; ux[kk] = m.ux; uy[kk] = m.uy;
-                    if (m.hit) hitmask |= 1u << (k0 + kk);
-                }
-            }
-        }
-#pragma unroll
-        for (int kk = 0; kk < G; kk++) {
-            float f[9];
-#pragma unroll
-            for (int i = 0; i < 9; i++) f[i] = comp(o[i], k0 + kk);
-            Moments m;
-            m.rho = rho[kk]; m.ux = ux[kk]; m.uy = uy[kk]; m.hit = false;
-            if (mac) { mac[k0 + kk][0] = m.rho; mac[k0 + kk][1] = m.ux; mac[k0 + kk][2] = m.uy; }
-            collide(f, m, tau, rcp, rcp_lo);
-#pragma unroll
-            for (int i = 0; i < 9; i++) setc(o[i], k0 + kk, f[i]);
-        }
-    }
-    return hitmask;
-}
-
-// dst = src on the listed tasks (all-solid tasks over a double step, see build_lists_kernel)
-__global__ void __launch_bounds__(BLOCK_THREADS)
-copy_tasks_kernel(const __grid_constant__ StepParams p) {
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * TASKS_PER_BLOCK + (threadIdx.x >> 5);
-    if (t >= p.ngen) return;
-    const int task = p.gen_list[t] & LIST_ID_MASK;
-    const int j = task / p.tpr + 1;
-    const size_t c = (size_t)j * p.pitch + (task - (j - 1) * p.tpr) * TASK_CELLS + lane * 4;
-    const size_t plane = p.plane;
-    [[maybe_unused]] const float *const src = p.src;
-    [[maybe_unused]] float *const dst_base = p.dst;
-    float4 v[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) v[i] = LD4(p.src + i * plane + c);
-#pragma unroll
-    for (int i = 0; i < 9; i++) ST4(p.dst + i * plane + c, v[i]);
-}
-
-#if ALB_S2_TMA || ALB_S2_ASYNC
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-#endif
-
-// loads that must stay where they are written (issued BEFORE the barrier that ends a super-step)
-__device__ __forceinline__ float4 ld4_pinned(const float *p) {
-    float4 r;
-    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float ld1_pinned(const float *p) {
-    float r;
-    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
-    return r;
-}
-[[maybe_unused]] constexpr int S2_STG = 4 + 128 + 4;    // floats per population in an A warp's private staging buffer
-#define LD4P(ptr) (ALB_CHECK_SRC((ptr), 4), ld4_pinned(ptr))
-#define LD1P(ptr) (ALB_CHECK_SRC((ptr), 1), ld1_pinned(ptr))
-
-#ifndef ALB_S2_MINB
-#define ALB_S2_MINB ((16 / (ALB_S2_RB * ALB_S2_K)) >= 1 ? 16 / (ALB_S2_RB * ALB_S2_K) : 1)
-#endif
-// DIAG: step 2 also reduces the autoscale statistics of the state it writes (deep cells have no
-// faces), once per tile -- for batches that END with a double step.
-template <int RB, int K, bool DIAG = false>
-__global__ void __launch_bounds__(2 * RB * K * 32, ALB_S2_MINB)
-step2_kernel(const __grid_constant__ Step2Params p) {
-    extern __shared__ float4 ring4[];
-    float *ring = reinterpret_cast<float *>(ring4);   // [RS][9][WI]
-    constexpr int WI = 128 * K, NW = RB * K, RS = 2 * RB + 2;
-    [[maybe_unused]] float *stage_all = ring + (size_t)RS * 9 * WI;   // ALB_S2_ASYNC: [NW][9][S2_STG]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool role_b = warp >= NW;
-    const int w = role_b ? warp - NW : warp;
-    const int r = w / K, seg = w - r * K;
-    const int strip = blockIdx.x % p.nstrips, sgm = blockIdx.x / p.nstrips;
-    const int y0 = 2 + sgm * p.hs;                 // owned output rows [y0, y1)
-    const int y1 = min(y0 + p.hs, p.nyl);
-    const int a0 = y0 - 1;                         // first intermediate row
-    const int nga = (y1 - y0 + 2 + RB - 1) / RB;   // row groups of step 1
-    const int col = seg * 128 + lane * 4;          // column of this lane's quad inside the strip
-    const int gx = strip * p.wo - 4 + col;         // and on the lattice
-    const bool inx = gx >= 0 && gx < p.pitch;
-    const bool ownx = col >= 4 && col < min(p.wo, p.pitch - strip * p.wo) + 4;
-    const size_t plane = p.plane;
-    const float *__restrict__ src = p.src;
-    [[maybe_unused]] float *const dst_base = p.dst;
-    const uint8_t *tfl = p.tflags + (inx ? (gx >> 7) : 0);
-    unsigned hits = 0;
-#if ALB_S2_SETMAXNREG
-    // Experimental: the step-1 warps need ~100 registers (36 of them hold the next task's loads across
-    // the barrier), the step-2 warps far fewer; with warpgroup-aligned roles the register file can be
-    // re-split after launch, so that 24 warps fit without spills (compile with RB*K a multiple of 4).
-    static_assert(!ALB_S2_SETMAXNREG || (RB * K) % 4 == 0, "roles must be whole warpgroups");
-    if (!role_b) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ALB_S2_REGS_A));
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ALB_S2_REGS_B));
-#endif
-
-    if (!role_b) {
-        // ---- A warps: step 1, HBM -> ring.  The loads of the NEXT row group are issued before the
-        // barrier that ends the current one (their 36 registers are dead by then), so HBM latency
-        // overlaps the barrier wait and the B warps' work instead of heading every task; the task
-        // flags are fetched two groups ahead for the same reason.
-        auto flags_of = [&](int g) -> unsigned {
-            const int j = a0 + g * RB + r;
-            return (g < nga && j <= y1 && inx) ? tfl[(size_t)j * p.tpr] : 0u;
-        };
-#if ALB_S2_ASYNC
-        // Each A warp owns a private staging buffer of one task, 9 rows of 4 + 128 + 4 floats (the
-        // task's 128 cells plus the quad to its left and right, so the x-neighbours come along).
-        // As soon as the populations of the current task are in registers, one lane starts nine
-        // 1-D bulk copies (TMA, completion on the warp's own mbarrier) of the NEXT task into the
-        // same buffer: HBM latency is covered by a whole task of arithmetic plus the barrier, no
-        // registers are held, and the per-lane address arithmetic of nine LDG.128 disappears.
-        float *const stg_row = stage_all + (size_t)w * 9 * S2_STG;
-        unsigned long long *const bar = reinterpret_cast<unsigned long long *>(stage_all + (size_t)NW * 9 * S2_STG) + w;
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-        // lattice columns [c_lo, c_hi) of this warp's segment incl. the two extra quads, clipped to the row
-        const int seg_x = strip * p.wo - 4 + seg * 128;
-        const int c_lo = max(seg_x - 4, 0), c_hi = min(seg_x + 132, p.pitch);
-        const bool seg_in = c_hi > c_lo;
-        const float *stg = stg_row + 4 + lane * 4;
-        auto issue_loads = [&](int g) {
-            if (lane == 0 && seg_in) {
-                const int j = a0 + g * RB + r;
-                const unsigned bytes = (unsigned)(c_hi - c_lo) * 4u;
-                mbar_arrive_expect_tx(bar, 9u * bytes);
-                const float *g0 = src + (size_t)j * p.pitch + c_lo;
-                float *s0 = stg_row + (c_lo - (seg_x - 4));
-                const int ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
-#pragma unroll
-                for (int i = 0; i < 9; i++) {
-                    const float *gs = g0 + i * plane - (ptrdiff_t)ey[i] * p.pitch;
-                    ALB_CHECK_SRC(gs, c_hi - c_lo);
-                    tma_load_1d(s0 + i * S2_STG, gs, bytes, bar);
-                }
-            }
-        };
-        unsigned tf = flags_of(0), tf1 = flags_of(1), phase = 0;
-        bool have = __any_sync(FULL, tf & TF_NEED);
-        if (have) issue_loads(0);
-        for (int g = 0; g <= nga; g++) {
-            const unsigned tf2 = flags_of(g + 2);
-            const bool have_next = __any_sync(FULL, tf1 & TF_NEED);
-            float4 o[9];
-            if (have) {
-                if (seg_in) mbar_wait(bar, phase);
-                phase ^= 1u;
-                const float4 v0 = *reinterpret_cast<const float4 *>(stg + 0 * S2_STG);
-                const float4 v1 = *reinterpret_cast<const float4 *>(stg + 1 * S2_STG);
-                const float4 v2 = *reinterpret_cast<const float4 *>(stg + 2 * S2_STG);
-                const float4 v3 = *reinterpret_cast<const float4 *>(stg + 3 * S2_STG);
-                const float4 v4 = *reinterpret_cast<const float4 *>(stg + 4 * S2_STG);
-                const float4 v5 = *reinterpret_cast<const float4 *>(stg + 5 * S2_STG);
-                const float4 v6 = *reinterpret_cast<const float4 *>(stg + 6 * S2_STG);
-                const float4 v7 = *reinterpret_cast<const float4 *>(stg + 7 * S2_STG);
-                const float4 v8 = *reinterpret_cast<const float4 *>(stg + 8 * S2_STG);
-                float l1 = 0.f, l5 = 0.f, l8 = 0.f, r3 = 0.f, r6 = 0.f, r7 = 0.f;
-                if (lane == 0) {
-                    l1 = stg[1 * S2_STG - 1];
-                    l5 = stg[5 * S2_STG - 1];
-                    l8 = stg[8 * S2_STG - 1];
-                }
-                if (lane == 31) {
-                    r3 = stg[3 * S2_STG + 4];
-                    r6 = stg[6 * S2_STG + 4];
-                    r7 = stg[7 * S2_STG + 4];
-                }
-                o[0] = v0;
-                o[1] = from_left(v1, l1, lane);
-                o[2] = v2;
-                o[3] = from_right(v3, r3, lane);
-                o[4] = v4;
-                o[5] = from_left(v5, l5, lane);
-                o[6] = from_right(v6, r6, lane);
-                o[7] = from_right(v7, r7, lane);
-                o[8] = from_left(v8, l8, lane);
-            }
-            // the staged values are in registers (the shuffles consumed them): refill the buffer
-            if (have_next) {
-                __syncwarp();
-                issue_loads(g + 1);
-            }
-            if (have) {
-                const int j = a0 + g * RB + r;
-                const unsigned hm = collide_quad(o, p.tau, p.inv_tau, p.inv_tau_lo);
-                if ((tf & TF_DEEP) && ownx && j >= y0 && j < y1) hits += __popc(hm);
-                float *slot = ring + ((size_t)((j - a0) % RS) * 9) * WI + col;
-#pragma unroll
-                for (int i = 0; i < 9; i++) *reinterpret_cast<float4 *>(slot + i * WI) = o[i];
-            }
-            tf = tf1;
-            tf1 = tf2;
-            have = have_next;
-            __syncthreads();
-        }
-#else
-        float4 v0, v1, v2, v3, v4, v5, v6, v7, v8;
-        float l1 = 0.f, l5 = 0.f, l8 = 0.f, r3 = 0.f, r6 = 0.f, r7 = 0.f;
-        v0 = v1 = v2 = v3 = v4 = v5 = v6 = v7 = v8 = make_float4(0.f, 0.f, 0.f, 0.f);
-        auto issue_loads = [&](int g) {
-            const int j = a0 + g * RB + r;
-            const size_t c = (size_t)j * p.pitch + gx;
-            const size_t cm = c - p.pitch, cp = c + p.pitch;
-            if (inx) {
-                v0 = LD4P(src + 0 * plane + c);
-                v1 = LD4P(src + 1 * plane + c);
-                v2 = LD4P(src + 2 * plane + cm);
-                v3 = LD4P(src + 3 * plane + c);
-                v4 = LD4P(src + 4 * plane + cp);
-                v5 = LD4P(src + 5 * plane + cm);
-                v6 = LD4P(src + 6 * plane + cm);
-                v7 = LD4P(src + 7 * plane + cp);
-                v8 = LD4P(src + 8 * plane + cp);
-            }
-            if (lane == 0 && gx > 0) {
-                l1 = LD1P(src + 1 * plane + c - 1);
-                l5 = LD1P(src + 5 * plane + cm - 1);
-                l8 = LD1P(src + 8 * plane + cp - 1);
-            }
-            if (lane == 31 && gx + 4 < p.pitch) {
-                r3 = LD1P(src + 3 * plane + c + 4);
-                r6 = LD1P(src + 6 * plane + cm + 4);
-                r7 = LD1P(src + 7 * plane + cp + 4);
-            }
-        };
-        unsigned tf = flags_of(0), tf1 = flags_of(1);
-        bool have = __any_sync(FULL, tf & TF_NEED);
-        if (have) issue_loads(0);
-        for (int g = 0; g <= nga; g++) {
-            const unsigned tf2 = flags_of(g + 2);
-            if (have) {
-                const int j = a0 + g * RB + r;
-                float4 o[9];
-                o[0] = v0;
-                o[1] = from_left(v1, l1, lane);
-                o[2] = v2;
-                o[3] = from_right(v3, r3, lane);
-                o[4] = v4;
-                o[5] = from_left(v5, l5, lane);
-                o[6] = from_right(v6, r6, lane);
-                o[7] = from_right(v7, r7, lane);
-                o[8] = from_left(v8, l8, lane);
-                const unsigned hm = collide_quad(o, p.tau, p.inv_tau, p.inv_tau_lo);
-                // clamp hits of step 1: every deep cell is owned by exactly one tile
-                if ((tf & TF_DEEP) && ownx && j >= y0 && j < y1) hits += __popc(hm);
-                float *slot = ring + ((size_t)((j - a0) % RS) * 9) * WI + col;
-#pragma unroll
-                for (int i = 0; i < 9; i++) *reinterpret_cast<float4 *>(slot + i * WI) = o[i];
-            }
-            tf = tf1;
-            tf1 = tf2;
-            have = __any_sync(FULL, tf & TF_NEED);
-            if (have) issue_loads(g + 1);
-            __syncthreads();
-        }
-#endif  // ALB_S2_ASYNC
-    } else {
-        // ---- B warps: step 2, ring -> HBM, one row group behind ----
-        auto flags_of = [&](int g) -> unsigned {
-            const int j = y0 - 2 + (g - 1) * RB + r;
-            return (g >= 1 && g <= nga && j >= y0 && j < y1 && ownx) ? tfl[(size_t)j * p.tpr] : 0u;
-        };
-        unsigned tf = 0u, tf1 = flags_of(1);
-        [[maybe_unused]] DiagLocal dl;
-        for (int g = 0; g <= nga; g++) {
-            const unsigned tf2 = flags_of(g + 2);
-            const bool st = (tf & TF_DEEP) != 0;
-            if (__any_sync(FULL, st)) {
-                const int j = y0 - 2 + (g - 1) * RB + r;
-                const int q = j - a0;
-                const float *s0 = ring + ((size_t)(q % RS) * 9) * WI + col;
-                const float *sm = ring + ((size_t)((q - 1) % RS) * 9) * WI + col;
-                const float *sp = ring + ((size_t)((q + 1) % RS) * 9) * WI + col;
-                float4 o[9];
-                const float4 v0 = *reinterpret_cast<const float4 *>(s0 + 0 * WI);
-                const float4 v1 = *reinterpret_cast<const float4 *>(s0 + 1 * WI);
-                const float4 v2 = *reinterpret_cast<const float4 *>(sm + 2 * WI);
-                const float4 v3 = *reinterpret_cast<const float4 *>(s0 + 3 * WI);
-                const float4 v4 = *reinterpret_cast<const float4 *>(sp + 4 * WI);
-                const float4 v5 = *reinterpret_cast<const float4 *>(sm + 5 * WI);
-                const float4 v6 = *reinterpret_cast<const float4 *>(sm + 6 * WI);
-                const float4 v7 = *reinterpret_cast<const float4 *>(sp + 7 * WI);
-                const float4 v8 = *reinterpret_cast<const float4 *>(sp + 8 * WI);
-                float l1 = 0.f, l5 = 0.f, l8 = 0.f, r3 = 0.f, r6 = 0.f, r7 = 0.f;
-                if (lane == 0 && col > 0) {
-                    l1 = s0[1 * WI - 1];
-                    l5 = sm[5 * WI - 1];
-                    l8 = sp[8 * WI - 1];
-                }
-                if (lane == 31 && col + 4 < WI) {
-                    r3 = s0[3 * WI + 4];
-                    r6 = sm[6 * WI + 4];
-                    r7 = sp[7 * WI + 4];
-                }
-                o[0] = v0;
-                o[1] = from_left(v1, l1, lane);
-                o[2] = v2;
-                o[3] = from_right(v3, r3, lane);
-                o[4] = v4;
-                o[5] = from_left(v5, l5, lane);
-                o[6] = from_right(v6, r6, lane);
-                o[7] = from_right(v7, r7, lane);
-                o[8] = from_left(v8, l8, lane);
-                float mac[4][3];
-                const unsigned hm = collide_quad<ALB_QUAD_GB>(o, p.tau, p.inv_tau, p.inv_tau_lo, DIAG ? mac : nullptr);
-                if (st) {
-                    hits += __popc(hm);
-                    float *d = p.dst + (size_t)j * p.pitch + gx;
-#pragma unroll
-                    for (int i = 0; i < 9; i++) ST4(d + i * plane, o[i]);
-                    if (DIAG) {
-#pragma unroll
-                        for (int k = 0; k < 4; k++) diag_cell(p, dl, mac[k][0], mac[k][1], mac[k][2]);
-                    }
-                }
-            }
-            tf = tf1;
-            tf1 = tf2;
-            __syncthreads();
-        }
-        if (DIAG) diag_flush<false>(p, dl, lane);
-    }
-    if (hits && p.clamp_hits) atomicAdd(p.clamp_hits, (unsigned long long)hits);
-}
-
-#if ALB_S2_TMA
-// ---- the same two-step scheme, fed by TMA ----------------------------------------------------------
-// step2_kernel's A warps still sit on HBM latency (ncu: long_scoreboard + barrier stalls, issue slots
-// 62 % busy).  Here a producer warp streams the source rows of row group g+NST-1 into a shared-memory
-// staging ring with 1-D bulk copies (cp.async.bulk, completion on an mbarrier) while the A warps run
-// step 1 of group g out of staging and the B warps run step 2 of group g-1 out of the intermediate
-// ring: every compute warp works from shared memory, nothing waits on HBM, and the 18 copies per group
-// cost one thread a few dozen instructions instead of nine LDG.128 per lane.
-//   staging  [NST][RB][9][WI+8]   source populations as the pull needs them (population i of the row
-//                                 j - ey_i), 4 cells of padding left and right for the x-neighbours
-//   ring     [2RB+2][9][WI]       intermediate state (one step ahead)
-template <int RB, int K, int NST>
-__global__ void __launch_bounds__((2 * RB * K + 1) * 32, 1)
-step2t_kernel(const __grid_constant__ Step2Params p) {
-    constexpr int WI = 128 * K, WS = WI + 8, NW = RB * K, RS = 2 * RB + 2;
-    extern __shared__ float4 smem4[];
-    float *stage = reinterpret_cast<float *>(smem4);                 // [NST][RB][9][WS]
-    float *ring = stage + (size_t)NST * RB * 9 * WS;                  // [RS][9][WI]
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(ring + (size_t)RS * 9 * WI);   // [NST]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int strip = blockIdx.x % p.nstrips, sgm = blockIdx.x / p.nstrips;
-    const int y0 = 2 + sgm * p.hs;                 // owned output rows [y0, y1)
-    const int y1 = min(y0 + p.hs, p.nyl);
-    const int a0 = y0 - 1;                         // first intermediate row
-    const int nga = (y1 - y0 + 2 + RB - 1) / RB;   // row groups of step 1
-    const int xs = strip * p.wo - 4;               // lattice x of intermediate column 0
-    const size_t plane = p.plane;
-    [[maybe_unused]] const float *const src = p.src;
-    [[maybe_unused]] float *const dst_base = p.dst;
-
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < NST; k++) mbar_init(full + k, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (warp == 2 * NW) {
-        // ---- producer: one lane issues the bulk copies of group gg, NST-1 super-steps ahead ----
-        // staged columns [xs-4, xs+WI+4) clipped to the lattice row
-        const int c_lo = max(xs - 4, 0), c_hi = min(xs + WI + 4, p.pitch);
-        const unsigned row_bytes = (unsigned)(c_hi - c_lo) * 4u;
-        const int t_lo = max(xs, 0) >> 7, t_hi = (min(xs + WI, p.pitch) - 1) >> 7;   // tasks under the strip
-        auto issue = [&](int gg) {
-            unsigned long long *bar = full + gg % NST;
-            float *sbase = stage + (size_t)(gg % NST) * RB * 9 * WS;
-            bool need[RB];
-            int nrows = 0;
-#pragma unroll
-            for (int r = 0; r < RB; r++) {
-                const int j = a0 + gg * RB + r;
-                need[r] = false;
-                if (j <= y1)
-                    for (int t = t_lo; t <= t_hi; t++) need[r] |= (p.tflags[(size_t)j * p.tpr + t] & TF_NEED) != 0;
-                nrows += need[r] ? 1 : 0;
-            }
-            mbar_arrive_expect_tx(bar, (unsigned)nrows * 9u * row_bytes);
-            const int ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
-#pragma unroll
-            for (int r = 0; r < RB; r++) {
-                if (!need[r]) continue;
-                const int j = a0 + gg * RB + r;
-#pragma unroll
-                for (int i = 0; i < 9; i++) {
-                    const float *g = p.src + i * plane + (size_t)(j - ey[i]) * p.pitch + c_lo;
-                    ALB_CHECK_SRC(g, c_hi - c_lo);
-                    tma_load_1d(sbase + ((size_t)r * 9 + i) * WS + (c_lo - (xs - 4)), g, row_bytes, bar);
-                }
-            }
-        };
-        if (lane == 0)
-            for (int gg = 0; gg < NST - 1 && gg < nga; gg++) issue(gg);
-        for (int g = 0; g <= nga; g++) {
-            if (lane == 0 && g + NST - 1 < nga) issue(g + NST - 1);
-            __syncthreads();
-        }
-        return;
-    }
-
-    const bool role_b = warp >= NW;
-    const int w = role_b ? warp - NW : warp;
-    const int r = w / K, seg = w - r * K;
-    const int col = seg * 128 + lane * 4;          // column of this lane's quad inside the strip
-    const int gx = xs + col;                       // and on the lattice
-    const bool inx = gx >= 0 && gx < p.pitch;
-    const bool ownx = col >= 4 && col < min(p.wo, p.pitch - strip * p.wo) + 4;
-    unsigned hits = 0;
-    // task flags of this warp's task in super-step g (0 when it has none), fetched one super-step ahead
-    auto flags_of = [&](int g) -> unsigned {
-        if (!role_b) {
-            const int j = a0 + g * RB + r;
-            return (g < nga && j <= y1 && inx) ? p.tflags[(size_t)j * p.tpr + (gx >> 7)] : 0u;
-        }
-        const int j = y0 - 2 + (g - 1) * RB + r;
-        return (g >= 1 && j >= y0 && j < y1 && ownx) ? p.tflags[(size_t)j * p.tpr + (gx >> 7)] : 0u;
-    };
-    unsigned tf_next = flags_of(0);
-
-    for (int g = 0; g <= nga; g++) {
-        const unsigned tf = tf_next;
-        tf_next = g < nga ? flags_of(g + 1) : 0u;
-        if (!role_b) {
-            const int j = a0 + g * RB + r;
-            if (g < nga) mbar_wait(full + g % NST, (unsigned)(g / NST) & 1u);
-            if (__any_sync(FULL, tf & TF_NEED)) {
-                const float *sb = stage + ((size_t)(g % NST) * RB + r) * 9 * WS + col + 4;
-                float4 o[9];
-                const float4 v0 = *reinterpret_cast<const float4 *>(sb + 0 * WS);
-                const float4 v1 = *reinterpret_cast<const float4 *>(sb + 1 * WS);
-                const float4 v2 = *reinterpret_cast<const float4 *>(sb + 2 * WS);
-                const float4 v3 = *reinterpret_cast<const float4 *>(sb + 3 * WS);
-                const float4 v4 = *reinterpret_cast<const float4 *>(sb + 4 * WS);
-                const float4 v5 = *reinterpret_cast<const float4 *>(sb + 5 * WS);
-                const float4 v6 = *reinterpret_cast<const float4 *>(sb + 6 * WS);
-                const float4 v7 = *reinterpret_cast<const float4 *>(sb + 7 * WS);
-                const float4 v8 = *reinterpret_cast<const float4 *>(sb + 8 * WS);
-                float l1 = 0.f, l5 = 0.f, l8 = 0.f, r3 = 0.f, r6 = 0.f, r7 = 0.f;
-                if (lane == 0) {
-                    l1 = sb[1 * WS - 1];
-                    l5 = sb[5 * WS - 1];
-                    l8 = sb[8 * WS - 1];
-                }
-                if (lane == 31) {
-                    r3 = sb[3 * WS + 4];
-                    r6 = sb[6 * WS + 4];
-                    r7 = sb[7 * WS + 4];
-                }
-                o[0] = v0;
-                o[1] = from_left(v1, l1, lane);
-                o[2] = v2;
-                o[3] = from_right(v3, r3, lane);
-                o[4] = v4;
-                o[5] = from_left(v5, l5, lane);
-                o[6] = from_right(v6, r6, lane);
-                o[7] = from_right(v7, r7, lane);
-                o[8] = from_left(v8, l8, lane);
-                const unsigned hm = collide_quad(o, p.tau, p.inv_tau, p.inv_tau_lo);
-                // clamp hits of step 1: every deep cell is owned by exactly one tile
-                if ((tf & TF_DEEP) && ownx && j >= y0 && j < y1) hits += __popc(hm);
-                float *slot = ring + ((size_t)((j - a0) % RS) * 9) * WI + col;
-#pragma unroll
-                for (int i = 0; i < 9; i++) *reinterpret_cast<float4 *>(slot + i * WI) = o[i];
-            }
-        } else {
-            const int j = y0 - 2 + (g - 1) * RB + r;
-            const bool st = (tf & TF_DEEP) != 0;
-            if (__any_sync(FULL, st)) {
-                const int q = j - a0;
-                const float *s0 = ring + ((size_t)(q % RS) * 9) * WI + col;
-                const float *sm = ring + ((size_t)((q - 1) % RS) * 9) * WI + col;
-                const float *sp = ring + ((size_t)((q + 1) % RS) * 9) * WI + col;
-                float4 o[9];
-                const float4 v0 = *reinterpret_cast<const float4 *>(s0 + 0 * WI);
-                const float4 v1 = *reinterpret_cast<const float4 *>(s0 + 1 * WI);
-                const float4 v2 = *reinterpret_cast<const float4 *>(sm + 2 * WI);
-                const float4 v3 = *reinterpret_cast<const float4 *>(s0 + 3 * WI);
-                const float4 v4 = *reinterpret_cast<const float4 *>(sp + 4 * WI);
-                const float4 v5 = *reinterpret_cast<const float4 *>(sm + 5 * WI);
-                const float4 v6 = *reinterpret_cast<const float4 *>(sm + 6 * WI);
-                const float4 v7 = *reinterpret_cast<const float4 *>(sp + 7 * WI);
-                const float4 v8 = *reinterpret_cast<const float4 *>(sp + 8 * WI);
-                float l1 = 0.f, l5 = 0.f, l8 = 0.f, r3 = 0.f, r6 = 0.f, r7 = 0.f;
-                if (lane == 0 && col > 0) {
-                    l1 = s0[1 * WI - 1];
-                    l5 = sm[5 * WI - 1];
-                    l8 = sp[8 * WI - 1];
-                }
-                if (lane == 31 && col + 4 < WI) {
-                    r3 = s0[3 * WI + 4];
-                    r6 = sm[6 * WI + 4];
-                    r7 = sp[7 * WI + 4];
-                }
-                o[0] = v0;
-                o[1] = from_left(v1, l1, lane);
-                o[2] = v2;
-                o[3] = from_right(v3, r3, lane);
-                o[4] = v4;
-                o[5] = from_left(v5, l5, lane);
-                o[6] = from_right(v6, r6, lane);
-                o[7] = from_right(v7, r7, lane);
-                o[8] = from_left(v8, l8, lane);
-                const unsigned hm = collide_quad(o, p.tau, p.inv_tau, p.inv_tau_lo);
-                if (st) {
-                    hits += __popc(hm);
-                    float *d = p.dst + (size_t)j * p.pitch + gx;
-#pragma unroll
-                    for (int i = 0; i < 9; i++) ST4(d + i * plane, o[i]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (hits && p.clamp_hits) atomicAdd(p.clamp_hits, (unsigned long long)hits);
-}
-
-#endif  // ALB_S2_TMA
-
 // ---- small lattices: one persistent cooperative launch for a whole batch of steps -------------
 // A 320x160 lattice (the reference's default) moves 3.7 MB per step: it lives in L2 and a step
 // is bound by launch latency and by the length of one thread's dependent instruction chain, not
@@ -1392,66 +401,7 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
     }
 }
 
-// ---- self-test of div_pair() against true division (tests/test_gpu_div.py) -----------------------
-// Counter-based generator; operand regimes: lattice-like values, wide exponent ranges, numerators
-// placed within a few ulps of a rounding boundary of the quotient, zeros, and out-of-range values
-// (which must be rejected, never silently wrong).
-__device__ __forceinline__ unsigned long long splitmix(unsigned long long &x) {
-    unsigned long long z = (x += 0x9E3779B97F4A7C15ull);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-__global__ void div_selftest_kernel(unsigned long long seed, int iters, unsigned long long *out3) {
-    unsigned long long st = seed + 0x632BE59BD9B4E019ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
-    unsigned long long checked = 0, accepted = 0, wrong = 0;
-    for (int it = 0; it < iters; it++) {
-        const unsigned long long a = splitmix(st), b = splitmix(st);
-        const int regime = (int)(a >> 61);
-        float r, jx, jy;
-        const unsigned mant_r = (unsigned)b & 0x7fffffu, mant_x = (unsigned)(b >> 23) & 0x7fffffu, mant_y = (unsigned)(a >> 8) & 0x7fffffu;
-        const unsigned sx = ((unsigned)(a >> 40) & 1u) << 31, sy = ((unsigned)(a >> 41) & 1u) << 31;
-        if (regime <= 2) {            // lattice-like: rho in [0.25, 4), |j| in [2^-32, 1)
-            r = __uint_as_float(((125u + (unsigned)(b >> 50) % 4u) << 23) | mant_r);
-            jx = __uint_as_float(sx | ((95u + (unsigned)(a >> 32) % 32u) << 23) | mant_x);
-            jy = __uint_as_float(sy | ((95u + (unsigned)(a >> 48) % 32u) << 23) | mant_y);
-        } else if (regime <= 4) {     // the whole accepted range and beyond it on both sides
-            r = __uint_as_float(((80u + (unsigned)(b >> 50) % 96u) << 23) | mant_r);
-            jx = __uint_as_float(sx | ((60u + (unsigned)(a >> 32) % 116u) << 23) | mant_x);
-            jy = __uint_as_float(sy | ((60u + (unsigned)(a >> 48) % 116u) << 23) | mant_y);
-        } else if (regime <= 6) {     // numerator = q*r moved by -2..2 ulps: quotients next to rounding boundaries
-            r = __uint_as_float(((126u + (unsigned)(b >> 50) % 2u) << 23) | mant_r);
-            const float q1 = __uint_as_float(sx | ((100u + (unsigned)(a >> 32) % 28u) << 23) | mant_x);
-            const float q2 = __uint_as_float(sy | ((100u + (unsigned)(a >> 48) % 28u) << 23) | (mant_y | 1u));
-            jx = __uint_as_float(__float_as_uint(__fmul_rn(q1, r)) + (unsigned)(a >> 20) % 5u - 2u);
-            jy = __uint_as_float(__float_as_uint(__fmul_rz(q2, r)) + (unsigned)(a >> 24) % 5u - 2u);
-        } else {                      // special values
-            const float sp[8] = {0.0f, -0.0f, 1.0f, INFINITY, NAN, 1e-45f, 3e38f, -1.0f};
-            r = (b >> 60) & 1 ? sp[(b >> 40) & 7] : __uint_as_float((127u << 23) | mant_r);
-            jx = sp[(a >> 32) & 7];
-            jy = (a >> 36) & 1 ? sp[(a >> 44) & 7] : __uint_as_float(sy | (120u << 23) | mant_y);
-        }
-        float vx, vy;
-        const bool nums_ok = div_pair(jx, jy, r, vx, vy);
-        const bool ok = quad_accept(r, vx * vx + vy * vy, nums_ok);
-        checked++;
-        if (ok) {
-            accepted++;
-            const float tx = __fdiv_rn(jx, r), ty = __fdiv_rn(jy, r);
-            if (__float_as_uint(tx) != __float_as_uint(vx) || __float_as_uint(ty) != __float_as_uint(vy)) wrong++;
-        }
-    }
-    atomicAdd(out3 + 0, checked);
-    atomicAdd(out3 + 1, accepted);
-    atomicAdd(out3 + 2, wrong);
-}
-
 }  // namespace
-
-cudaError_t launch_div_selftest(unsigned long long seed, int nblocks, int iters, unsigned long long *d_out3, cudaStream_t s) {
-    div_selftest_kernel<<<nblocks, 256, 0, s>>>(seed, iters, d_out3);
-    return cudaGetLastError();
-}
 
 // The fast kernel and the general kernel of one step read the same source state and write
 // disjoint cells, so the caller may run them concurrently on two streams.
@@ -1482,97 +432,6 @@ cudaError_t launch_step_fast_list(const StepParams &p, cudaStream_t s) {
     const int nblocks = p.ngen > 0 ? (p.ngen + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK : 1;
     if (p.diag) step_kernel<MODE_STEP, KIND_FAST_LIST, true><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
     else step_kernel<MODE_STEP, KIND_FAST_LIST><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_copy_tasks(const StepParams &p, cudaStream_t s) {
-    if (p.ngen <= 0) return cudaSuccess;
-    copy_tasks_kernel<<<(p.ngen + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK, BLOCK_THREADS, 0, s>>>(p);
-    return cudaGetLastError();
-}
-
-int step2_strip_width() { return 128 * ALB_S2_K; }
-
-void step2_plan(Step2Params &p, int nsm) {
-    constexpr int WI = 128 * ALB_S2_K;
-    const int wo_max = WI - 8;
-    p.nstrips = (p.pitch + wo_max - 1) / wo_max;
-    int wo = (p.pitch + p.nstrips - 1) / p.nstrips;
-    wo = (wo + 7) / 8 * 8;                 // full 32-byte sectors per strip where possible
-    if (wo > wo_max) wo = wo_max;
-    while ((long long)(p.nstrips - 1) * wo >= p.pitch) p.nstrips--;   // rounding up may have emptied the last strip
-    p.wo = wo;
-    const int rows = p.nyl - 2;            // rows 2 .. nyl-1 can be deep
-    static int hs_env = -1;
-    if (hs_env < 0) {
-        const char *e = getenv("AEROLAB_LBM_S2_HS");
-        hs_env = e ? atoi(e) : 0;
-    }
-    if (rows <= 0) {
-        p.hs = 1;
-        p.ntiles = 0;
-        return;
-    }
-    if (hs_env > 0) {
-        p.hs = hs_env;
-    } else {
-        // Every tile costs about (rows + 6) row-group times (two recomputed rows, pipeline fill and
-        // drain) and one CTA runs per SM, so the step takes ceil(tiles / SMs) * (hs + 6): pick the
-        // segment height in [ALB_S2_HS_MIN, ALB_S2_HS_MAX] that minimises it.  Taller segments are not
-        // better per se: the list-driven passes on the aux stream only get SMs when a tile retires
-        // (measured on 32768x16384: 128..256 rows 125 GLUPS, 443 rows 123, 1024 rows 115).
-        long long best_cost = -1;
-        int best = rows < ALB_S2_HS_MAX ? rows : ALB_S2_HS_MAX;
-        for (int nsegs = (rows + ALB_S2_HS_MAX - 1) / ALB_S2_HS_MAX; nsegs <= rows; nsegs++) {
-            const int hs = (rows + nsegs - 1) / nsegs;
-            if (hs < ALB_S2_HS_MIN && best_cost >= 0) break;
-            const long long tiles = (long long)p.nstrips * ((rows + hs - 1) / hs);
-            const long long cost = ((tiles + nsm - 1) / nsm) * (hs + 6);
-            if (best_cost < 0 || cost < best_cost) {
-                best_cost = cost;
-                best = hs;
-            }
-        }
-        p.hs = best;
-    }
-    const int nsegs = (rows + p.hs - 1) / p.hs;
-    p.ntiles = p.nstrips * nsegs;
-}
-
-cudaError_t launch_step2(const Step2Params &p, cudaStream_t s) {
-    if (p.ntiles <= 0) return cudaSuccess;
-    constexpr int RB = ALB_S2_RB, K = ALB_S2_K;
-#if ALB_S2_TMA
-    {
-        constexpr int NST = ALB_S2_NST;
-        constexpr size_t smem_t = sizeof(float) * ((size_t)NST * RB * 9 * (128 * K + 8) + (size_t)(2 * RB + 2) * 9 * 128 * K) +
-                                  8 * NST;
-        static bool configured_t[64] = {};
-        int dev_t = 0;
-        cudaGetDevice(&dev_t);
-        if (dev_t < 0 || dev_t >= 64 || !configured_t[dev_t]) {
-            cudaError_t e = cudaFuncSetAttribute(step2t_kernel<RB, K, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem_t);
-            if (e != cudaSuccess) return e;
-            if (dev_t >= 0 && dev_t < 64) configured_t[dev_t] = true;
-        }
-        step2t_kernel<RB, K, NST><<<p.ntiles, (2 * RB * K + 1) * 32, smem_t, s>>>(p);
-        return cudaGetLastError();
-    }
-#endif
-    constexpr size_t smem = sizeof(float) * ((size_t)(2 * RB + 2) * 9 * 128 * K + (ALB_S2_ASYNC ? (size_t)RB * K * (9 * (4 + 128 + 4) + 2) : 0));
-    static bool configured[64] = {};       // the attribute is per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(step2_kernel<RB, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(step2_kernel<RB, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
-    if (p.diag) step2_kernel<RB, K, true><<<p.ntiles, 2 * RB * K * 32, smem, s>>>(p);
-    else step2_kernel<RB, K, false><<<p.ntiles, 2 * RB * K * 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 
