@@ -111,7 +111,7 @@ struct StepParams {
     size_t peer_hi_row;      // float offset of its lower ghost row (row 0)
 };
 
-// Task flags of the two-steps-per-pass path (see step2_kernel in alb_step.cu), one byte per warp
+// Task flags of the two-steps-per-pass path (see step2_kernel in alb_step2.cu), one byte per warp
 // task [nrows][tpr]:
 //   TF_DEEP  every cell of the task and every cell within one cell of it is a plain interior fluid
 //            cell (type fluid, no solid pull source) and the row is not a slab edge row: the fused
@@ -167,21 +167,23 @@ cudaError_t launch_particles_step(ParticleState *ps, unsigned *ctrs, int n, unsi
                                   const uint8_t *mask, const float *ux, const float *uy, int pitch, int nx, int ny,
                                   double U0, cudaStream_t s);
 
-// alb_step.cu
+// alb_step.cu -- one step per pass
 cudaError_t launch_step_fast(const StepParams &p, cudaStream_t s);
 cudaError_t launch_step_general(const StepParams &p, cudaStream_t s);
 cudaError_t launch_step_unified(const StepParams &p, cudaStream_t s);
 cudaError_t launch_macro(const StepParams &p, cudaStream_t s);
 cudaError_t launch_step_fast_list(const StepParams &p, cudaStream_t s);   // p.gen_list/p.ngen = the list
+int small_lattice_capacity(int device);
+cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps, cudaStream_t s);
+void host_feq0(float u0, float *out9);
+
+// alb_step2.cu -- two steps per pass
 cudaError_t launch_copy_tasks(const StepParams &p, cudaStream_t s);       // dst = src on the listed tasks
 // geometry of the fused two-step kernel for a pitch x nyl slab: fills wo/hs/nstrips/ntiles
 void step2_plan(Step2Params &p, int nsm);
 int step2_strip_width();   // 128 * K of the compiled kernel shape
 cudaError_t launch_step2(const Step2Params &p, cudaStream_t s);
 cudaError_t launch_div_selftest(unsigned long long seed, int nblocks, int iters, unsigned long long *d_out3, cudaStream_t s);
-int small_lattice_capacity(int device);
-cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps, cudaStream_t s);
-void host_feq0(float u0, float *out9);
 
 // alb_geometry.cu
 void host_rotate_panelise(const double *xy, int npts, double alpha_deg, double *xp, double *yp);

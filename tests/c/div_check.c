@@ -1,5 +1,5 @@
 /* Exhaustive check of the step kernel's div_by_tau() sequence against IEEE division.
- * Mirrors airfoil-cfd-tool_b200/csrc/alb_step.cu:div_by_tau with C99 fmaf (exact FMA).
+ * Mirrors airfoil-cfd-tool_b200/csrc/alb_lbm.cuh:div_by_tau with C99 fmaf (exact FMA).
  * Build: gcc -O2 -fopenmp -ffp-contract=off [-mfma]  (see tests/test_div_by_tau.py) */
 #include <math.h>
 #include <stdint.h>

@@ -1,5 +1,5 @@
 """CPU: the 5-instruction division by the uniform tau used in the step kernel
-(alb_step.cu: div_by_tau) equals IEEE-754 division for every operand the kernel can see.
+(alb_lbm.cuh: div_by_tau) equals IEEE-754 division for every operand the kernel can see.
 
 Exhaustive over all fp32 values with magnitude in [2^-40, 2^8) for the reference's tau = 0.58 and
 other practical relaxation times, strided for a set of random ones.  (Operands in the kernel are
