@@ -40,7 +40,7 @@ def main():
         out.append(d)
     with open(os.path.join(OUT, f"{tag}_step_c3_ncu_full_summary.json"), "w") as fh:
         json.dump({"source": f"gpurun_out/prof_{tag}_step_c3.ncu-rep (ncu --set full --clock-control none --import-source on "
-                             "-k regex:step2_kernel|step_kernel|copy_tasks -s 12 -c 12; python bench.py --steps 20 --warmup 3 "
+                             "-k regex:step2_kernel|step_kernel|copy_tasks -s 12 -c 12 (r1f) / -c 6 (r1g); python bench.py --steps 20 --warmup 3 "
                              "--no-cpu-baseline --no-e2e)",
                    "workload": "configs[3] 32768x16384 NACA 2412 alpha=5, double steps", "launches": out}, fh, indent=1)
 
