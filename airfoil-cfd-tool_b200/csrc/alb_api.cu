@@ -23,7 +23,7 @@ constexpr int DIAG_BLOCKS = 148 * 4;          // fixed reduction grid -> determi
 constexpr int UNIFIED_MAX_TASKS = 148 * 2 * 8;   // one wave of the unified kernel (2 CTAs/SM x 8 tasks)
 constexpr long long WAIT_TIMEOUT_NS = 20LL * 1000 * 1000 * 1000;
 // Lattices at least this wide and this large advance two steps per pass (see step_batch).  Measured:
-// 32768x16384 125 vs 94 GLUPS; 4096x2048 (7 strips, not enough tiles per SM) 74 vs 79 -> stays on single steps.
+// 32768x16384 130 vs 94 GLUPS; 4096x2048 (7 strips, one wave of tiles) 83 vs 85, 2048x1024 33 vs 74 -> single steps.
 constexpr int DOUBLE_MIN_NX = 8192;
 constexpr long long DOUBLE_MIN_CELLS = 32LL << 20;
 
