@@ -24,13 +24,9 @@ namespace {
 #ifndef ALB_S2_HS_MIN
 #define ALB_S2_HS_MIN 64
 #endif
-// 1: step2t_kernel (TMA-fed staging ring, NST stages), 0: step2_kernel (loads through registers)
-#ifndef ALB_S2_TMA
-#define ALB_S2_TMA 0
-#endif
-#ifndef ALB_S2_NST
-#define ALB_S2_NST 3
-#endif
+// (A variant that staged whole row groups through a shared-memory ring filled by a producer warp with
+// TMA bulk copies, 2-3 stages deep, was measured at 96-112 GLUPS and removed: the staging ring costs
+// the shared memory of 4-8 compute warps.  See DESIGN.md section 4.2 and the git history.)
 // step2_kernel: 1 = the A warps prefetch their next task with TMA bulk copies into private shared-memory
 // staging instead of loading it into registers just before the barrier.  Measured on 32768x16384:
 // long_scoreboard stalls drop from 15 % to 3 % of the samples, but the step is SLOWER (116 vs 125 GLUPS;
@@ -186,7 +182,7 @@ copy_tasks_kernel(const __grid_constant__ StepParams p) {
     for (int i = 0; i < 9; i++) ST4(p.dst + i * plane + c, v[i]);
 }
 
-#if ALB_S2_TMA || ALB_S2_ASYNC
+#if ALB_S2_ASYNC
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -497,201 +493,6 @@ step2_kernel(const __grid_constant__ Step2Params p) {
     if (hits && p.clamp_hits) atomicAdd(p.clamp_hits, (unsigned long long)hits);
 }
 
-#if ALB_S2_TMA
-// ---- the same two-step scheme, fed by TMA ----------------------------------------------------------
-// step2_kernel's A warps still sit on HBM latency (ncu: long_scoreboard + barrier stalls, issue slots
-// 62 % busy).  Here a producer warp streams the source rows of row group g+NST-1 into a shared-memory
-// staging ring with 1-D bulk copies (cp.async.bulk, completion on an mbarrier) while the A warps run
-// step 1 of group g out of staging and the B warps run step 2 of group g-1 out of the intermediate
-// ring: every compute warp works from shared memory, nothing waits on HBM, and the 18 copies per group
-// cost one thread a few dozen instructions instead of nine LDG.128 per lane.
-//   staging  [NST][RB][9][WI+8]   source populations as the pull needs them (population i of the row
-//                                 j - ey_i), 4 cells of padding left and right for the x-neighbours
-//   ring     [2RB+2][9][WI]       intermediate state (one step ahead)
-template <int RB, int K, int NST>
-__global__ void __launch_bounds__((2 * RB * K + 1) * 32, 1)
-step2t_kernel(const __grid_constant__ Step2Params p) {
-    constexpr int WI = 128 * K, WS = WI + 8, NW = RB * K, RS = 2 * RB + 2;
-    extern __shared__ float4 smem4[];
-    float *stage = reinterpret_cast<float *>(smem4);                 // [NST][RB][9][WS]
-    float *ring = stage + (size_t)NST * RB * 9 * WS;                  // [RS][9][WI]
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(ring + (size_t)RS * 9 * WI);   // [NST]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int strip = blockIdx.x % p.nstrips, sgm = blockIdx.x / p.nstrips;
-    const int y0 = 2 + sgm * p.hs;                 // owned output rows [y0, y1)
-    const int y1 = min(y0 + p.hs, p.nyl);
-    const int a0 = y0 - 1;                         // first intermediate row
-    const int nga = (y1 - y0 + 2 + RB - 1) / RB;   // row groups of step 1
-    const int xs = strip * p.wo - 4;               // lattice x of intermediate column 0
-    const size_t plane = p.plane;
-    [[maybe_unused]] const float *const src = p.src;
-    [[maybe_unused]] float *const dst_base = p.dst;
-
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < NST; k++) mbar_init(full + k, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (warp == 2 * NW) {
-        // ---- producer: one lane issues the bulk copies of group gg, NST-1 super-steps ahead ----
-        // staged columns [xs-4, xs+WI+4) clipped to the lattice row
-        const int c_lo = max(xs - 4, 0), c_hi = min(xs + WI + 4, p.pitch);
-        const unsigned row_bytes = (unsigned)(c_hi - c_lo) * 4u;
-        const int t_lo = max(xs, 0) >> 7, t_hi = (min(xs + WI, p.pitch) - 1) >> 7;   // tasks under the strip
-        auto issue = [&](int gg) {
-            unsigned long long *bar = full + gg % NST;
-            float *sbase = stage + (size_t)(gg % NST) * RB * 9 * WS;
-            bool need[RB];
-            int nrows = 0;
-#pragma unroll
-            for (int r = 0; r < RB; r++) {
-                const int j = a0 + gg * RB + r;
-                need[r] = false;
-                if (j <= y1)
-                    for (int t = t_lo; t <= t_hi; t++) need[r] |= (p.tflags[(size_t)j * p.tpr + t] & TF_NEED) != 0;
-                nrows += need[r] ? 1 : 0;
-            }
-            mbar_arrive_expect_tx(bar, (unsigned)nrows * 9u * row_bytes);
-            const int ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
-#pragma unroll
-            for (int r = 0; r < RB; r++) {
-                if (!need[r]) continue;
-                const int j = a0 + gg * RB + r;
-#pragma unroll
-                for (int i = 0; i < 9; i++) {
-                    const float *g = p.src + i * plane + (size_t)(j - ey[i]) * p.pitch + c_lo;
-                    ALB_CHECK_SRC(g, c_hi - c_lo);
-                    tma_load_1d(sbase + ((size_t)r * 9 + i) * WS + (c_lo - (xs - 4)), g, row_bytes, bar);
-                }
-            }
-        };
-        if (lane == 0)
-            for (int gg = 0; gg < NST - 1 && gg < nga; gg++) issue(gg);
-        for (int g = 0; g <= nga; g++) {
-            if (lane == 0 && g + NST - 1 < nga) issue(g + NST - 1);
-            __syncthreads();
-        }
-        return;
-    }
-
-    const bool role_b = warp >= NW;
-    const int w = role_b ? warp - NW : warp;
-    const int r = w / K, seg = w - r * K;
-    const int col = seg * 128 + lane * 4;          // column of this lane's quad inside the strip
-    const int gx = xs + col;                       // and on the lattice
-    const bool inx = gx >= 0 && gx < p.pitch;
-    const bool ownx = col >= 4 && col < min(p.wo, p.pitch - strip * p.wo) + 4;
-    unsigned hits = 0;
-    // task flags of this warp's task in super-step g (0 when it has none), fetched one super-step ahead
-    auto flags_of = [&](int g) -> unsigned {
-        if (!role_b) {
-            const int j = a0 + g * RB + r;
-            return (g < nga && j <= y1 && inx) ? p.tflags[(size_t)j * p.tpr + (gx >> 7)] : 0u;
-        }
-        const int j = y0 - 2 + (g - 1) * RB + r;
-        return (g >= 1 && j >= y0 && j < y1 && ownx) ? p.tflags[(size_t)j * p.tpr + (gx >> 7)] : 0u;
-    };
-    unsigned tf_next = flags_of(0);
-
-    for (int g = 0; g <= nga; g++) {
-        const unsigned tf = tf_next;
-        tf_next = g < nga ? flags_of(g + 1) : 0u;
-        if (!role_b) {
-            const int j = a0 + g * RB + r;
-            if (g < nga) mbar_wait(full + g % NST, (unsigned)(g / NST) & 1u);
-            if (__any_sync(FULL, tf & TF_NEED)) {
-                const float *sb = stage + ((size_t)(g % NST) * RB + r) * 9 * WS + col + 4;
-                float4 o[9];
-                const float4 v0 = *reinterpret_cast<const float4 *>(sb + 0 * WS);
-                const float4 v1 = *reinterpret_cast<const float4 *>(sb + 1 * WS);
-                const float4 v2 = *reinterpret_cast<const float4 *>(sb + 2 * WS);
-                const float4 v3 = *reinterpret_cast<const float4 *>(sb + 3 * WS);
-                const float4 v4 = *reinterpret_cast<const float4 *>(sb + 4 * WS);
-                const float4 v5 = *reinterpret_cast<const float4 *>(sb + 5 * WS);
-                const float4 v6 = *reinterpret_cast<const float4 *>(sb + 6 * WS);
-                const float4 v7 = *reinterpret_cast<const float4 *>(sb + 7 * WS);
-                const float4 v8 = *reinterpret_cast<const float4 *>(sb + 8 * WS);
-                float l1 = 0.f, l5 = 0.f, l8 = 0.f, r3 = 0.f, r6 = 0.f, r7 = 0.f;
-                if (lane == 0) {
-                    l1 = sb[1 * WS - 1];
-                    l5 = sb[5 * WS - 1];
-                    l8 = sb[8 * WS - 1];
-                }
-                if (lane == 31) {
-                    r3 = sb[3 * WS + 4];
-                    r6 = sb[6 * WS + 4];
-                    r7 = sb[7 * WS + 4];
-                }
-                o[0] = v0;
-                o[1] = from_left(v1, l1, lane);
-                o[2] = v2;
-                o[3] = from_right(v3, r3, lane);
-                o[4] = v4;
-                o[5] = from_left(v5, l5, lane);
-                o[6] = from_right(v6, r6, lane);
-                o[7] = from_right(v7, r7, lane);
-                o[8] = from_left(v8, l8, lane);
-                const unsigned hm = collide_quad(o, p.tau, p.inv_tau, p.inv_tau_lo);
-                // clamp hits of step 1: every deep cell is owned by exactly one tile
-                if ((tf & TF_DEEP) && ownx && j >= y0 && j < y1) hits += __popc(hm);
-                float *slot = ring + ((size_t)((j - a0) % RS) * 9) * WI + col;
-#pragma unroll
-                for (int i = 0; i < 9; i++) *reinterpret_cast<float4 *>(slot + i * WI) = o[i];
-            }
-        } else {
-            const int j = y0 - 2 + (g - 1) * RB + r;
-            const bool st = (tf & TF_DEEP) != 0;
-            if (__any_sync(FULL, st)) {
-                const int q = j - a0;
-                const float *s0 = ring + ((size_t)(q % RS) * 9) * WI + col;
-                const float *sm = ring + ((size_t)((q - 1) % RS) * 9) * WI + col;
-                const float *sp = ring + ((size_t)((q + 1) % RS) * 9) * WI + col;
-                float4 o[9];
-                const float4 v0 = *reinterpret_cast<const float4 *>(s0 + 0 * WI);
-                const float4 v1 = *reinterpret_cast<const float4 *>(s0 + 1 * WI);
-                const float4 v2 = *reinterpret_cast<const float4 *>(sm + 2 * WI);
-                const float4 v3 = *reinterpret_cast<const float4 *>(s0 + 3 * WI);
-                const float4 v4 = *reinterpret_cast<const float4 *>(sp + 4 * WI);
-                const float4 v5 = *reinterpret_cast<const float4 *>(sm + 5 * WI);
-                const float4 v6 = *reinterpret_cast<const float4 *>(sm + 6 * WI);
-                const float4 v7 = *reinterpret_cast<const float4 *>(sp + 7 * WI);
-                const float4 v8 = *reinterpret_cast<const float4 *>(sp + 8 * WI);
-                float l1 = 0.f, l5 = 0.f, l8 = 0.f, r3 = 0.f, r6 = 0.f, r7 = 0.f;
-                if (lane == 0 && col > 0) {
-                    l1 = s0[1 * WI - 1];
-                    l5 = sm[5 * WI - 1];
-                    l8 = sp[8 * WI - 1];
-                }
-                if (lane == 31 && col + 4 < WI) {
-                    r3 = s0[3 * WI + 4];
-                    r6 = sm[6 * WI + 4];
-                    r7 = sp[7 * WI + 4];
-                }
-                o[0] = v0;
-                o[1] = from_left(v1, l1, lane);
-                o[2] = v2;
-                o[3] = from_right(v3, r3, lane);
-                o[4] = v4;
-                o[5] = from_left(v5, l5, lane);
-                o[6] = from_right(v6, r6, lane);
-                o[7] = from_right(v7, r7, lane);
-                o[8] = from_left(v8, l8, lane);
-                const unsigned hm = collide_quad(o, p.tau, p.inv_tau, p.inv_tau_lo);
-                if (st) {
-                    hits += __popc(hm);
-                    float *d = p.dst + (size_t)j * p.pitch + gx;
-#pragma unroll
-                    for (int i = 0; i < 9; i++) ST4(d + i * plane, o[i]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (hits && p.clamp_hits) atomicAdd(p.clamp_hits, (unsigned long long)hits);
-}
-
-#endif  // ALB_S2_TMA
 
 // ---- self-test of div_pair() against true division (tests/test_gpu_div.py) -----------------------
 // Counter-based generator; operand regimes: lattice-like values, wide exponent ranges, numerators
@@ -811,24 +612,6 @@ void step2_plan(Step2Params &p, int nsm) {
 cudaError_t launch_step2(const Step2Params &p, cudaStream_t s) {
     if (p.ntiles <= 0) return cudaSuccess;
     constexpr int RB = ALB_S2_RB, K = ALB_S2_K;
-#if ALB_S2_TMA
-    {
-        constexpr int NST = ALB_S2_NST;
-        constexpr size_t smem_t = sizeof(float) * ((size_t)NST * RB * 9 * (128 * K + 8) + (size_t)(2 * RB + 2) * 9 * 128 * K) +
-                                  8 * NST;
-        static bool configured_t[64] = {};
-        int dev_t = 0;
-        cudaGetDevice(&dev_t);
-        if (dev_t < 0 || dev_t >= 64 || !configured_t[dev_t]) {
-            cudaError_t e = cudaFuncSetAttribute(step2t_kernel<RB, K, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem_t);
-            if (e != cudaSuccess) return e;
-            if (dev_t >= 0 && dev_t < 64) configured_t[dev_t] = true;
-        }
-        step2t_kernel<RB, K, NST><<<p.ntiles, (2 * RB * K + 1) * 32, smem_t, s>>>(p);
-        return cudaGetLastError();
-    }
-#endif
     constexpr size_t smem = sizeof(float) * ((size_t)(2 * RB + 2) * 9 * 128 * K + (ALB_S2_ASYNC ? (size_t)RB * K * (9 * (4 + 128 + 4) + 2) : 0));
     static bool configured[64] = {};       // the attribute is per device
     int dev = 0;
