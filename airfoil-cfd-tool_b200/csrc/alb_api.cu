@@ -531,9 +531,9 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         // 2.23 ms (measured on one GPU with AEROLAB_LBM_FAKE_HALO=1; 434 -> see DESIGN.md section 7 at 4
         // GPUs).  At normal priority they run before the fused kernel's CTAs when they are ready first,
         // else in its tail.  AEROLAB_LBM_AUX_PRIO=1 restores the high priority for measurements.
-        (void)prio_lo;
+        const char *aux_prio = getenv("AEROLAB_LBM_AUX_PRIO");
         CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking,
-                                        getenv("AEROLAB_LBM_AUX_PRIO") && atoi(getenv("AEROLAB_LBM_AUX_PRIO")) == 1 ? prio_hi : prio_lo));
+                                        aux_prio && atoi(aux_prio) == 1 ? prio_hi : prio_lo));
         CK(cudaEventCreate(&h->ev0));
         CK(cudaEventCreate(&h->ev1));
         CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
