@@ -528,8 +528,8 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         // The aux stream runs the general-task kernel of single steps and the list-driven passes of
         // double steps.  NORMAL priority: with a high-priority aux stream the passes cut into the fused
         // step2_kernel at its wave boundaries and every double step of a slab costs 2.47 instead of
-        // 2.23 ms (measured on one GPU with AEROLAB_LBM_FAKE_HALO=1; 434 -> see DESIGN.md section 7 at 4
-        // GPUs).  At normal priority they run before the fused kernel's CTAs when they are ready first,
+        // 2.23 ms (measured on one GPU with AEROLAB_LBM_FAKE_HALO=1; 434 -> 482 GLUPS at 4 GPUs, 867 -> 929 at
+        // 8).  At normal priority they run before the fused kernel's CTAs when they are ready first,
         // else in its tail.  AEROLAB_LBM_AUX_PRIO=1 restores the high priority for measurements.
         const char *aux_prio = getenv("AEROLAB_LBM_AUX_PRIO");
         CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking,
