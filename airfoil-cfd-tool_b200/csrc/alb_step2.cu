@@ -266,9 +266,14 @@ step2_kernel(const __grid_constant__ Step2Params p) {
         // barrier that ends the current one (their 36 registers are dead by then), so HBM latency
         // overlaps the barrier wait and the B warps' work instead of heading every task; the task
         // flags are fetched two groups ahead for the same reason.
-        auto flags_of = [&](int g) -> unsigned {
-            const int j = a0 + g * RB + r;
-            return (g < nga && j <= y1 && inx) ? tfl[(size_t)j * p.tpr] : 0u;
+        // flags of this warp's tasks in row-group order (0 once past the last intermediate row):
+        // a running row / pointer pair instead of index arithmetic per group
+        int jf = a0 + r, of = jf * p.tpr;       // rows * tasks per row < 2^30 (checked in alb_create)
+        auto next_flags = [&]() -> unsigned {
+            const unsigned v = (jf <= y1 && inx) ? tfl[of] : 0u;
+            jf += RB;
+            of += RB * p.tpr;
+            return v;
         };
 #if ALB_S2_ASYNC
         // Each A warp owns a private staging buffer of one task, 9 rows of 4 + 128 + 4 floats (the
@@ -305,11 +310,11 @@ step2_kernel(const __grid_constant__ Step2Params p) {
                 }
             }
         };
-        unsigned tf = flags_of(0), tf1 = flags_of(1), phase = 0;
+        unsigned tf = next_flags(), tf1 = next_flags(), phase = 0;
         bool have = __any_sync(FULL, tf & TF_NEED);
         if (have) issue_loads(0);
         for (int g = 0; g <= nga; g++) {
-            const unsigned tf2 = flags_of(g + 2);
+            const unsigned tf2 = next_flags();
             const bool have_next = __any_sync(FULL, tf1 & TF_NEED);
             float4 o[9];
             if (have) {
@@ -393,11 +398,11 @@ step2_kernel(const __grid_constant__ Step2Params p) {
                 r7 = LD1P(src + 7 * plane + cp + 4);
             }
         };
-        unsigned tf = flags_of(0), tf1 = flags_of(1);
+        unsigned tf = next_flags(), tf1 = next_flags();
         bool have = __any_sync(FULL, tf & TF_NEED);
         if (have) issue_loads(0);
         for (int g = 0; g <= nga; g++) {
-            const unsigned tf2 = flags_of(g + 2);
+            const unsigned tf2 = next_flags();
             if (have) {
                 const int j = a0 + g * RB + r;
                 float4 o[9];
@@ -426,14 +431,19 @@ step2_kernel(const __grid_constant__ Step2Params p) {
 #endif  // ALB_S2_ASYNC
     } else {
         // ---- B warps: step 2, ring -> HBM, one row group behind ----
-        auto flags_of = [&](int g) -> unsigned {
-            const int j = y0 - 2 + (g - 1) * RB + r;
-            return (g >= 1 && g <= nga && j >= y0 && j < y1 && ownx) ? tfl[(size_t)j * p.tpr] : 0u;
+        // flags of this warp's output rows, group 1 first (0 for rows outside [y0, y1) and for lanes
+        // outside the strip's own columns)
+        int jf = y0 - 2 + r, of = jf * p.tpr;
+        auto next_flags = [&]() -> unsigned {
+            const unsigned v = ((unsigned)(jf - y0) < (unsigned)(y1 - y0) && ownx) ? tfl[of] : 0u;
+            jf += RB;
+            of += RB * p.tpr;
+            return v;
         };
-        unsigned tf = 0u, tf1 = flags_of(1);
+        unsigned tf = 0u, tf1 = next_flags();
         [[maybe_unused]] DiagLocal dl;
         for (int g = 0; g <= nga; g++) {
-            const unsigned tf2 = flags_of(g + 2);
+            const unsigned tf2 = next_flags();
             const bool st = (tf & TF_DEEP) != 0;
             if (__any_sync(FULL, st)) {
                 const int j = y0 - 2 + (g - 1) * RB + r;
