@@ -9,11 +9,11 @@ stall indicator.  CUDA only: no Triton, no backend dispatch, no CPU fallback.
 from ._ffi import AerolabLbmError, LIB_PATH, device_count
 from .geometry import SHAPES, clark_y, naca4, naca_digits, round_coords
 from .tunnel import (DEFAULT_ALPHA, DEFAULT_NX, DEFAULT_NY, DEFAULT_TAU, DEFAULT_U0, LocalMultiTunnel,
-                     WindTunnel, build_lbm_component)
+                     WindTunnel, build_lbm_component, state_hash_numpy)
 
 __all__ = [
     "AerolabLbmError", "LIB_PATH", "device_count", "SHAPES", "clark_y", "naca4", "naca_digits",
-    "round_coords", "WindTunnel", "LocalMultiTunnel", "build_lbm_component", "DEFAULT_ALPHA", "DEFAULT_NX", "DEFAULT_NY",
+    "round_coords", "WindTunnel", "LocalMultiTunnel", "build_lbm_component", "state_hash_numpy", "DEFAULT_ALPHA", "DEFAULT_NX", "DEFAULT_NY",
     "DEFAULT_TAU", "DEFAULT_U0",
 ]
 __version__ = "0.1.0"

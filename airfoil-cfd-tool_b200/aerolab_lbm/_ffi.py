@@ -34,7 +34,7 @@ EXPORTS = [
     "alb_set_params", "alb_get_params", "alb_reset",
     "alb_rasterize", "alb_rasterize_panels", "alb_set_mask", "alb_get_mask", "alb_get_panels",
     "alb_step", "alb_sync", "alb_step_count", "alb_last_step_ms",
-    "alb_get_populations", "alb_set_populations", "alb_get_macro", "alb_set_macro", "alb_total_mass",
+    "alb_get_populations", "alb_get_population_rows", "alb_state_hash", "alb_set_populations", "alb_get_macro", "alb_set_macro", "alb_total_mass",
     "alb_update_stats", "alb_stats_partial", "alb_set_stats", "alb_get_stats",
     "alb_get_field", "alb_get_rgba",
     "alb_compute_forces", "alb_forces_partial", "alb_reset_force_emas",
@@ -98,6 +98,8 @@ def lib():
     L.alb_last_step_ms.argtypes = [H, C.POINTER(C.c_float)]
     L.alb_get_populations.argtypes = [H, vp]
     L.alb_set_populations.argtypes = [H, vp]
+    L.alb_get_population_rows.argtypes = [H, C.c_int, C.c_int, vp]
+    L.alb_state_hash.argtypes = [H, vp]
     L.alb_get_macro.argtypes = [H, vp, vp, vp]
     L.alb_set_macro.argtypes = [H, vp, vp, vp]
     L.alb_total_mass.argtypes = [H, dp]

@@ -347,6 +347,14 @@ class DistributedTunnel:
             out.update(Fx_me=fxm, Fy_me=fym, CL_me=fym / q, CD_me=fxm / q)
         return out
 
+    def state_hash(self) -> np.ndarray:
+        """Nine uint64 checksum words of the whole lattice's populations: the slabs' words added
+        modulo 2^64 (identical for every decomposition of the same state)."""
+        mine = self.t.state_hash()
+        # int64 two's-complement addition wraps exactly like uint64 addition
+        tot = self.comm.allreduce(mine.view(np.int64), "sum")
+        return np.ascontiguousarray(tot, dtype=np.int64).view(np.uint64)
+
     def frame(self) -> dict:
         """The reference frame (HTML:902-930) across slabs: 4 steps, autoscale, forces every 3rd."""
         self.step(4)

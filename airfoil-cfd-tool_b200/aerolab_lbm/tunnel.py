@@ -34,6 +34,24 @@ FORCES_EVERY_FRAMES = 3               # HTML:914
 MIN_POINTS, MAX_POINTS = 10, 500
 
 
+def state_hash_numpy(f: np.ndarray, nx_global: int, gy0: int = 0) -> np.ndarray:
+    """NumPy twin of ``alb_state_hash`` for populations of shape (9, rows, nx) whose first row is
+    global row ``gy0`` (tests compare the device checksum with this one)."""
+    f = np.ascontiguousarray(f, dtype=np.float32)
+    _, rows, nx = f.shape
+    g = ((np.arange(rows, dtype=np.uint64)[:, None] + np.uint64(gy0)) * np.uint64(nx_global)
+         + np.arange(nx, dtype=np.uint64)[None, :])
+    out = np.zeros(9, np.uint64)
+    with np.errstate(over="ignore"):
+        for i in range(9):
+            z = g * np.uint64(0x9E3779B97F4A7C15) + f[i].view(np.uint32).astype(np.uint64) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            out[i] = z.sum(dtype=np.uint64)
+    return out
+
+
 class WindTunnel:
     """One D2Q9 lattice on one GPU.
 
@@ -197,6 +215,20 @@ class WindTunnel:
     def populations(self) -> np.ndarray:
         out = np.empty((9,) + self.shape, np.float32)
         self._ck(self._lib.alb_get_populations(self._h, ptr(out)))
+        return out
+
+    def population_rows(self, row0: int, nrows: int) -> np.ndarray:
+        """Rows row0 .. row0+nrows-1 of this slab's populations (0 = first owned row; -1 and
+        ny_local are the ghost rows), shape (9, nrows, nx)."""
+        out = np.empty((9, int(nrows), self.nx), np.float32)
+        self._ck(self._lib.alb_get_population_rows(self._h, int(row0), int(nrows), ptr(out)))
+        return out
+
+    def state_hash(self) -> np.ndarray:
+        """Nine uint64 words, one per population plane (``alb_state_hash``); the words of all
+        slabs of a lattice add up modulo 2^64 to those of the whole lattice."""
+        out = np.zeros(9, np.uint64)
+        self._ck(self._lib.alb_state_hash(self._h, ptr(out)))
         return out
 
     def set_populations(self, f: np.ndarray):
@@ -380,6 +412,12 @@ class WindTunnel:
         a = C.c_int(0)
         self._ck(self._lib.alb_get_double_steps(self._h, None, C.byref(a)))
         return bool(a.value)
+
+    def step2_plan(self, nsm: int = 148) -> dict:
+        """Tiling of the fused two-step kernel for this slab (``alb_debug_step2_plan``)."""
+        out = (C.c_int * 5)()
+        check(self._lib.alb_debug_step2_plan(self.nx, self.ny_local, int(nsm), out))
+        return dict(nseg=out[0], wo=out[1], hs=out[2], nunits=out[3], wi=out[4])
 
     def set_double_steps(self, mode: int):
         """-1 automatic, 0 never, 1 always: two steps per pass over HBM (bit-identical results)."""

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "aerolab_lbm", "_lib")
 OUT = os.path.join(OUT_DIR, "libaerolab_lbm.so")
-SOURCES = ["alb_api.cu", "alb_step.cu", "alb_step2.cu", "alb_geometry.cu", "alb_diag.cu", "alb_particles.cu"]
+SOURCES = ["alb_api.cu", "alb_step.cu", "alb_step2.cu", "alb_march.cu", "alb_geometry.cu", "alb_diag.cu", "alb_particles.cu"]
 DEPS = SOURCES + ["alb_common.cuh", "alb_lbm.cuh", os.path.join("..", "..", "include", "aerolab_lbm.h")]
 
 NVCC_FLAGS = [
@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2",
-    "-shared", "-cudart", "static",
+    "-shared", "-cudart", "static", "--threads", "0",
 ]
 
 

@@ -79,6 +79,8 @@ struct alb_handle {
     int *lists[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // see launch_build_lists
     int *list_counts = nullptr;
     int nlist[5] = {0, 0, 0, 0, 0};
+    int *s2_queue = nullptr;      // work queue of march2_kernel: {next unit, finished warps}, zero between launches
+    int s2_kernel = 0;            // 0: march2_kernel (one independent warp per unit), 1: step2_kernel (strip CTAs)
     bool solid_synced = false;    // both ping-pong buffers hold the same values on the all-solid tasks (lists[4])
     int double_mode = -1;         // -1 automatic, 0 never, 1 whenever possible (AEROLAB_LBM_DOUBLE / alb_set_option)
     int graph_parity = 0;         // h->parity the graph was captured at
@@ -422,6 +424,7 @@ void free_handle(alb_handle *h) {
     cudaFree(h->deep_tmp);
     for (auto &l : h->lists) cudaFree(l);
     cudaFree(h->list_counts);
+    cudaFree(h->s2_queue);
     cudaFree(h->me);
     cudaFree(h->parts);
     cudaFree(h->d_frame);
@@ -558,6 +561,8 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaMalloc(&h->deep_tmp, (size_t)h->nrows * h->tpr));
         for (auto &l : h->lists) CK(cudaMalloc(&l, sizeof(int) * (size_t)h->nrows * h->tpr));
         CK(cudaMalloc(&h->list_counts, 5 * sizeof(int)));
+        CK(cudaMalloc(&h->s2_queue, 2 * sizeof(int)));
+        CK(cudaMemsetAsync(h->s2_queue, 0, 2 * sizeof(int), h->stream));
         CK(cudaMalloc(&h->me, sizeof(MeState)));
         CK(cudaMalloc(&h->clamp_hits, sizeof(unsigned long long)));
         CK(cudaMalloc(&h->d_xp, sizeof(double) * 1024));
@@ -588,6 +593,7 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device));
         h->use_graph = getenv("AEROLAB_LBM_NO_GRAPH") == nullptr;   // A/B switch for measurements
         if (const char *e = getenv("AEROLAB_LBM_DOUBLE")) h->double_mode = atoi(e) != 0 ? 1 : 0;
+        if (const char *e = getenv("AEROLAB_LBM_S2_KERNEL")) h->s2_kernel = strcmp(e, "ring") == 0 ? 1 : 0;   // A/B switch
         if (const char *e = getenv("AEROLAB_LBM_TRACE")) {
             h->trace_step = atoll(e);
             for (auto &ev : h->tev) CK(cudaEventCreate(&ev));
@@ -845,11 +851,17 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
     q.inv_tau = h->inv_tau;
     q.inv_tau_lo = h->inv_tau_lo;
     q.clamp_hits = h->clamp_hits;
+    q.queue = h->s2_queue;
     if (diag) arm_diag2(h, q);
-    step2_plan(q, h->nsm);
     // no flags here: next to a neighbouring slab two edge rows are shallow, the fused kernel never
     // reads a ghost row, and the GPUs only meet in the short list-driven passes
-    CK(launch_step2(q, h->stream));
+    if (h->s2_kernel == 1) {
+        step2_plan(q, h->nsm);
+        CK(launch_step2(q, h->stream));
+    } else {
+        march_plan(q, h->nsm);
+        CK(launch_march2(q, h->nsm, h->stream));
+    }
     h->launches += q.ntiles > 0 ? 1 : 0;
     if (trace) CK(cudaEventRecord(h->tev[5], h->stream));                  // fused kernel finished
     CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
@@ -1126,6 +1138,29 @@ int alb_get_populations(alb_handle *h, float *f) {
         int r = copy_out_rows(h, f + i * dense, h->f[h->cur] + i * h->plane + h->pitch, sizeof(float));
         if (r) return r;
     }
+    CK(cudaStreamSynchronize(h->stream));
+    return check_wait_error(h);
+}
+
+int alb_get_population_rows(alb_handle *h, int row0, int nrows, float *f) {
+    NEED(h);
+    ARG(f && nrows >= 1 && row0 >= -1 && row0 + nrows <= h->nyl + 1,
+        "alb_get_population_rows: need -1 <= row0, nrows >= 1, row0 + nrows <= ny_local + 1");
+    const size_t dense = (size_t)h->nx * nrows;
+    for (int i = 0; i < 9; i++)
+        CK(cudaMemcpy2DAsync(f + i * dense, (size_t)h->nx * sizeof(float),
+                             h->f[h->cur] + i * h->plane + (size_t)(row0 + 1) * h->pitch, (size_t)h->pitch * sizeof(float),
+                             (size_t)h->nx * sizeof(float), nrows, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return check_wait_error(h);
+}
+
+int alb_state_hash(alb_handle *h, unsigned long long *out9) {
+    NEED(h);
+    ARG(out9, "alb_state_hash: output is NULL");
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(h->d_part);   // 9 words of the reduction scratch
+    CK(launch_state_hash(h->f[h->cur], h->plane, h->pitch, h->nx, h->nyl, h->y0, d, h->stream));
+    CK(cudaMemcpyAsync(out9, d, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return check_wait_error(h);
 }
@@ -1691,12 +1726,12 @@ int alb_debug_step2_plan(int nx, int ny_local, int nsm, int *out5) {
     memset(&q, 0, sizeof q);
     q.pitch = (nx + TASK_CELLS - 1) / TASK_CELLS * TASK_CELLS;
     q.nyl = ny_local;
-    step2_plan(q, nsm);
-    out5[0] = q.nstrips;
+    march_plan(q, nsm);
+    out5[0] = q.nseg;
     out5[1] = q.wo;
     out5[2] = q.hs;
-    out5[3] = q.ntiles;
-    out5[4] = step2_strip_width();
+    out5[3] = q.nunits;
+    out5[4] = march_out_width() + 8;
     return ALB_OK;
 }
 

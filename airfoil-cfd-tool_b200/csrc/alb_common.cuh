@@ -131,6 +131,10 @@ struct Step2Params {
     int wo;                  // output columns per strip (multiple of 4, <= 128*K - 8)
     int hs;                  // output rows per segment
     int nstrips, ntiles;
+    // march2_kernel (alb_march.cu): column segments per row, units = nseg * row segments, and the work
+    // queue {next unit, warps that have finished}, both zero between launches
+    int nseg, nunits;
+    int *queue;
     float tau, inv_tau, inv_tau_lo;
     unsigned long long *clamp_hits;
     // fused statistics of the state being written (nullable), same meaning as in StepParams
@@ -183,6 +187,10 @@ cudaError_t launch_copy_tasks(const StepParams &p, cudaStream_t s);       // dst
 void step2_plan(Step2Params &p, int nsm);
 int step2_strip_width();   // 128 * K of the compiled kernel shape
 cudaError_t launch_step2(const Step2Params &p, cudaStream_t s);
+// alb_march.cu -- two steps per pass, one independent warp per unit (the default two-step kernel)
+void march_plan(Step2Params &p, int nsm);
+int march_out_width();     // output columns per warp
+cudaError_t launch_march2(const Step2Params &p, int nsm, cudaStream_t s);
 cudaError_t launch_div_selftest(unsigned long long seed, int nblocks, int iters, unsigned long long *d_out3, cudaStream_t s);
 
 // alb_geometry.cu
@@ -216,6 +224,8 @@ cudaError_t launch_render(const uint8_t *mask, const float *rho, const float *ux
                           float cpMax, float vortScale, float *t_out, uint8_t *rgba, cudaStream_t s);
 cudaError_t launch_mass(const float *f, size_t plane, int pitch, int nx, int nyl, double *d_part,
                         int nblocks, cudaStream_t s);
+cudaError_t launch_state_hash(const float *f, size_t plane, int pitch, int nx, int nyl, int gy0,
+                              unsigned long long *d_out9, cudaStream_t s);
 cudaError_t launch_fill_init(float *f0, float *f1, size_t plane, const float *feq9, float *rho,
                              float *ux, float *uy, float u0, cudaStream_t s);
 

@@ -159,6 +159,36 @@ mass_kernel(const float *__restrict__ f, size_t plane, int pitch, int nx, int ny
     }
 }
 
+// Checksum of the population bit patterns, one 64-bit word per plane: the sum over the slab's
+// owned cells of mix64(global cell index, bits) modulo 2^64.  Every term depends on WHERE the
+// value sits on the global lattice, and integer sums are order independent, so the per-slab
+// words of any decomposition add up to the word of the whole lattice (bench.py `check`,
+// tests/test_gpu_large.py; numpy twin: aerolab_lbm.tunnel.state_hash_numpy).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long g, unsigned v) {
+    unsigned long long z = g * 0x9E3779B97F4A7C15ull + (unsigned long long)v * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(DIAG_THREADS)
+hash_kernel(const float *__restrict__ f, size_t plane, int pitch, int nx, int nyl, int gy0, unsigned long long *out9) {
+    unsigned long long h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t ncell = (size_t)nx * nyl;
+    for (size_t t = (size_t)blockIdx.x * DIAG_THREADS + threadIdx.x; t < ncell; t += (size_t)gridDim.x * DIAG_THREADS) {
+        const int y = (int)(t / nx), x = (int)(t - (size_t)y * nx);
+        const size_t c = (size_t)(y + 1) * pitch + x;
+        const unsigned long long g = (unsigned long long)(gy0 + y) * nx + x;
+#pragma unroll
+        for (int i = 0; i < 9; i++) h[i] += mix64(g, __float_as_uint(f[i * plane + c]));
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) h[i] += __shfl_xor_sync(FULL, h[i], d);
+        if ((threadIdx.x & 31) == 0 && h[i]) atomicAdd(out9 + i, h[i]);
+    }
+}
+
 __device__ __forceinline__ float mixf(float a, float b, float u) { return a * (1.0f - u) + b * u; }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ uint8_t unorm8(float v) {
@@ -366,6 +396,14 @@ cudaError_t launch_render(const uint8_t *mask, const float *rho, const float *ux
 cudaError_t launch_mass(const float *f, size_t plane, int pitch, int nx, int nyl, double *d_part,
                         int nblocks, cudaStream_t s) {
     mass_kernel<<<nblocks, DIAG_THREADS, 0, s>>>(f, plane, pitch, nx, nyl, d_part);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_state_hash(const float *f, size_t plane, int pitch, int nx, int nyl, int gy0,
+                              unsigned long long *d_out9, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(d_out9, 0, 9 * sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    hash_kernel<<<148 * 8, DIAG_THREADS, 0, s>>>(f, plane, pitch, nx, nyl, gy0, d_out9);
     return cudaGetLastError();
 }
 

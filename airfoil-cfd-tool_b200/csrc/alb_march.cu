@@ -1,0 +1,300 @@
+// Two LBM steps per pass over HBM, second generation: march2_kernel.
+//
+// step2_kernel (alb_step2.cu) splits a CTA into step-1 and step-2 warps that meet at a
+// __syncthreads per row group; ncu showed a quarter of its issue slots lost at that barrier and
+// the kernel exists in one shape only (632-column strips), which rules out lattices narrower
+// than ~8000 columns.  Here every WARP is an independent unit of work and there is no barrier at
+// all:
+//
+//   * a warp owns a column segment of 128 cells (4 per lane) and marches up a range of rows;
+//   * per row it runs step 1 on the 128 cells (inputs staged in its private shared-memory
+//     double buffer by nine 512-byte TMA bulk copies, issued two rows ahead, completion on the
+//     warp's own mbarrier), keeps the part of the intermediate state that later rows need in
+//     REGISTERS (36 per lane: f0,f1,f3 of the row below the new one, f2,f5,f6 of the two rows
+//     below) and immediately runs step 2 of the row below, whose remaining inputs (f4,f7,f8 of
+//     the row just computed) are in registers already; the result goes to HBM with 128-bit stores;
+//   * step 2 of a cell needs step 1 of its x-neighbours, so only lanes 1..30 produce output
+//     (120 columns per warp, segments overlap by 8 columns; 6.7 % redundant arithmetic instead of
+//     a shared intermediate ring and its barriers).  The intermediate state never touches shared
+//     memory;
+//   * units (row segment x column segment) are handed out through an atomic queue to the
+//     persistent warps of one CTA per SM, so there is no wave tail and any lattice with at least
+//     three 128-cell tasks per row can use it (2048- and 4096-wide lattices included).
+//
+// Which cells it may write (deep tasks) and which intermediate values it needs (TF_NEED) comes
+// from the same task flags as before; everything else is advanced by the list-driven two-pass
+// path on the aux stream (alb_api.cu, issue_double).  Same collide_quad() arithmetic as
+// everywhere else -> bit-identical to two single steps (HTML:283-360 twice).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "alb_lbm.cuh"
+
+// Shape knobs: warps per CTA (one CTA per SM; 16 x 128 registers = the whole register file), the
+// tallest row segment the planner may choose, and the fixed cost of starting a unit (pipeline fill)
+// in row-steps.
+#ifndef ALB_MARCH_WARPS
+#define ALB_MARCH_WARPS 16
+#endif
+#ifndef ALB_MARCH_HS_MAX
+#define ALB_MARCH_HS_MAX 256
+#endif
+#ifndef ALB_MARCH_UNIT_OVERHEAD
+#define ALB_MARCH_UNIT_OVERHEAD 3
+#endif
+
+namespace alb {
+
+namespace {
+
+constexpr int M_WARPS = ALB_MARCH_WARPS;      // warps per CTA, one CTA per SM
+constexpr int M_OUT = 120;                    // output columns per warp (lanes 1..30)
+constexpr int M_STAGE = 9 * 128;              // floats of one staged step-1 row (9 planes x 128 columns)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// x-shifts inside the warp; the outermost cell of lane 0 / lane 31 receives a value that is never used
+__device__ __forceinline__ float4 shl(const float4 &v) {   // populations arriving from x-1
+    return make_float4(__shfl_up_sync(FULL, v.w, 1), v.x, v.y, v.z);
+}
+__device__ __forceinline__ float4 shr(const float4 &v) {   // populations arriving from x+1
+    return make_float4(v.y, v.z, v.w, __shfl_down_sync(FULL, v.x, 1));
+}
+
+template <bool DIAG>
+__global__ void __launch_bounds__(M_WARPS * 32, 1)
+march2_kernel(const __grid_constant__ Step2Params p) {
+    extern __shared__ float4 smem4[];
+    float *const stage_all = reinterpret_cast<float *>(smem4);                       // [M_WARPS][2][9][128]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *const stg = stage_all + (size_t)warp * 2 * M_STAGE;
+    const unsigned stg_u32 = smem_u32(stg);
+    const unsigned bar_u32 = smem_u32(stage_all + (size_t)M_WARPS * 2 * M_STAGE) + warp * 16;   // two mbarriers
+    if (lane == 0) {
+        mbar_init(bar_u32, 1);
+        mbar_init(bar_u32 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned phase = 0;                         // bit k: parity to wait for on mbarrier k
+    const size_t plane = p.plane;
+    const int pitch = p.pitch, tpr = p.tpr;
+    [[maybe_unused]] const float *const src = p.src;
+    [[maybe_unused]] float *const dst_base = p.dst;
+    // lanes 0..8 each copy one population plane: plane `lane`, row offset -e_y of that population
+    const int ey_l = (lane == 2 || lane == 5 || lane == 6) ? 1 : ((lane == 4 || lane == 7 || lane == 8) ? -1 : 0);
+    const float *const tma_base = p.src + (size_t)(lane < 9 ? lane : 0) * plane - (ptrdiff_t)ey_l * pitch;
+    const bool own = lane >= 1 && lane <= 30;
+    const int total_warps = gridDim.x * M_WARPS;
+    unsigned hits = 0;
+    [[maybe_unused]] DiagLocal dl;
+
+    int unit = blockIdx.x * M_WARPS + warp;     // first unit: static; afterwards from the queue
+    for (;;) {
+        if (unit >= p.nunits) break;
+        // fetch the id of the unit after this one now: the atomic's latency hides behind the work
+        int next_unit = 0;
+        if (lane == 0) next_unit = total_warps + atomicAdd(p.queue, 1);
+        const int rowseg = unit / p.nseg, s = unit - rowseg * p.nseg;
+        const int y0 = 2 + rowseg * p.hs;                // owned output rows [y0, y1)
+        const int y1 = min(y0 + p.hs, p.nyl);
+        const int c0 = 124 + M_OUT * s;                  // first staged column; outputs are [c0 + 4, c0 + 124)
+        const int gx = c0 + lane * 4;
+        const uint8_t *const tfl = p.tflags + (gx >> 7);
+        const float *const tsrc = tma_base + c0;
+        // task flags of rows a, a+1, a+2 (pipelined; rows beyond y1 are of no interest to this unit)
+        auto row_flags = [&](int a) -> unsigned { return a <= y1 ? (unsigned)tfl[(size_t)a * tpr] : 0u; };
+        auto issue = [&](int a, int k) {                  // stage k <- inputs of step 1 of row a
+            if (lane == 0) mbar_arrive_expect_tx(bar_u32 + 8 * k, 9u * 512u);
+            __syncwarp();
+            if (lane < 9) {
+                const float *g = tsrc + (size_t)a * pitch;
+                ALB_CHECK_SRC(g, 128);
+                tma_load_1d(stg_u32 + (unsigned)(k * M_STAGE + lane * 128) * 4u, g, 512u, bar_u32 + 8 * k);
+            }
+        };
+        int a = y0 - 1;
+        unsigned tf0 = row_flags(a), tf1 = row_flags(a + 1), tf2 = row_flags(a + 2);
+        unsigned tfb = 0;                                // flags of the step-2 row a - 1
+        bool have = __any_sync(FULL, tf0 & TF_NEED);
+        bool have1 = __any_sync(FULL, tf1 & TF_NEED);
+        if (have) issue(a, 0);
+        if (have1) issue(a + 1, 1);
+        float4 wn0, wn1, wn3;                            // f0, f1, f3 of intermediate row a-1, already x-shifted
+        float4 up2, up5, up6;                            // f2, f5, f6 of intermediate row a-2
+        float4 uq2, uq5, uq6;                            // f2, f5, f6 of intermediate row a-1
+        wn0 = wn1 = wn3 = up2 = up5 = up6 = uq2 = uq5 = uq6 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float *d = p.dst + (size_t)(a - 1) * pitch + gx;  // destination of step-2 row a-1
+        int k = 0;
+#pragma unroll 1
+        for (; a <= y1; a++, k ^= 1, d += pitch) {
+            const unsigned tf3 = row_flags(a + 3);
+            const bool have2 = __any_sync(FULL, tf2 & TF_NEED);
+            float4 o[9];
+            if (have) {
+                // ---- step 1 of row a: staged inputs -> intermediate state (registers) ----
+                mbar_wait(bar_u32 + 8 * k, (phase >> k) & 1u);
+                phase ^= 1u << k;
+                const float *sp = stg + k * M_STAGE + lane * 4;
+                const float4 v0 = *reinterpret_cast<const float4 *>(sp + 0 * 128);
+                const float4 v1 = *reinterpret_cast<const float4 *>(sp + 1 * 128);
+                const float4 v2 = *reinterpret_cast<const float4 *>(sp + 2 * 128);
+                const float4 v3 = *reinterpret_cast<const float4 *>(sp + 3 * 128);
+                const float4 v4 = *reinterpret_cast<const float4 *>(sp + 4 * 128);
+                const float4 v5 = *reinterpret_cast<const float4 *>(sp + 5 * 128);
+                const float4 v6 = *reinterpret_cast<const float4 *>(sp + 6 * 128);
+                const float4 v7 = *reinterpret_cast<const float4 *>(sp + 7 * 128);
+                const float4 v8 = *reinterpret_cast<const float4 *>(sp + 8 * 128);
+                o[0] = v0;
+                o[1] = shl(v1);
+                o[2] = v2;
+                o[3] = shr(v3);
+                o[4] = v4;
+                o[5] = shl(v5);
+                o[6] = shr(v6);
+                o[7] = shr(v7);
+                o[8] = shl(v8);
+            }
+            if (have) {
+                const unsigned hm = collide_quad(o, p.tau, p.inv_tau, p.inv_tau_lo);
+                // clamp hits of step 1: every deep cell is owned by exactly one unit
+                if ((tf0 & TF_DEEP) && own && a >= y0 && a < y1) hits += __popc(hm);
+                // what later rows pull from this one, x-shifts applied now
+                o[1] = shl(o[1]);
+                o[3] = shr(o[3]);
+                o[5] = shl(o[5]);
+                o[6] = shr(o[6]);
+                o[7] = shr(o[7]);
+                o[8] = shl(o[8]);
+            }
+            // every staged value of row a has been consumed by the arithmetic above: refill the buffer
+            if (have2) issue(a + 2, k);
+            // ---- step 2 of row a-1: f0,f1,f3 of its own row, f2,f5,f6 of row a-2, f4,f7,f8 of row a ----
+            const bool st = (tfb & TF_DEEP) && own;
+            if (__any_sync(FULL, st)) {
+                float4 q[9];
+                q[0] = wn0; q[1] = wn1; q[3] = wn3;
+                q[2] = up2; q[5] = up5; q[6] = up6;
+                q[4] = o[4]; q[7] = o[7]; q[8] = o[8];
+                float mac[4][3];
+                const unsigned hm = collide_quad<ALB_QUAD_GB>(q, p.tau, p.inv_tau, p.inv_tau_lo, DIAG ? mac : nullptr);
+                if (st) {
+                    hits += __popc(hm);
+#pragma unroll
+                    for (int i = 0; i < 9; i++) ST4(d + i * plane, q[i]);
+                    if (DIAG) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) diag_cell(p, dl, mac[c][0], mac[c][1], mac[c][2]);
+                    }
+                }
+            }
+            // rotate the carried rows
+            wn0 = o[0]; wn1 = o[1]; wn3 = o[3];
+            up2 = uq2; up5 = uq5; up6 = uq6;
+            uq2 = o[2]; uq5 = o[5]; uq6 = o[6];
+            tfb = (a >= y0 && a < y1) ? tf0 : 0u;
+            tf0 = tf1; tf1 = tf2; tf2 = tf3;
+            have = have1; have1 = have2;
+        }
+        unit = __shfl_sync(FULL, next_unit, 0);
+    }
+    if (DIAG) diag_flush<false>(p, dl, lane);
+    if (hits && p.clamp_hits) atomicAdd(p.clamp_hits, (unsigned long long)hits);
+    // the last warp to leave re-arms the queue for the next launch (stream order does the rest)
+    if (lane == 0) {
+        __threadfence();
+        const int left = atomicAdd(p.queue + 1, 1);
+        if (left == total_warps - 1) {
+            p.queue[0] = 0;
+            p.queue[1] = 0;
+        }
+    }
+}
+
+constexpr size_t MARCH_SMEM = sizeof(float) * (size_t)M_WARPS * 2 * M_STAGE + (size_t)M_WARPS * 16;
+
+}  // namespace
+
+// Geometry of the marching kernel for a pitch x nyl slab on nsm SMs: column segments of 120 output
+// columns over the columns that can be deep, [128, pitch - 128), and row segments of hs rows over
+// rows 2 .. nyl-1.  A unit costs about 2 hs + 2 row-steps (hs + 2 rows of step 1, hs rows of step
+// 2) plus a fixed start-up; the persistent warps take units from a queue, so the pass lasts about
+// ceil(units / warps) units -- pick the segment height that minimises it.
+void march_plan(Step2Params &p, int nsm) {
+    p.nseg = p.pitch >= 3 * TASK_CELLS ? (p.pitch - 2 * TASK_CELLS + M_OUT - 1) / M_OUT : 0;
+    const int rows = p.nyl - 2;
+    p.nstrips = p.nseg;
+    p.wo = M_OUT;
+    if (rows <= 0 || p.nseg == 0) {
+        p.hs = 1;
+        p.nunits = p.ntiles = 0;
+        return;
+    }
+    static int hs_env = -1;
+    if (hs_env < 0) {
+        const char *e = getenv("AEROLAB_LBM_S2_HS");
+        hs_env = e ? atoi(e) : 0;
+    }
+    const long long warps = (long long)nsm * M_WARPS;
+    int best = rows;
+    if (hs_env > 0) {
+        best = hs_env < rows ? hs_env : rows;
+    } else {
+        long long best_cost = -1;
+        const int hs_max = rows < ALB_MARCH_HS_MAX ? rows : ALB_MARCH_HS_MAX;
+        for (int hs = hs_max; hs >= 1; hs--) {
+            const long long units = (long long)p.nseg * ((rows + hs - 1) / hs);
+            const long long cost = ((units + warps - 1) / warps) * (2 * hs + 2 + ALB_MARCH_UNIT_OVERHEAD);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                best = hs;
+            }
+        }
+    }
+    p.hs = best;
+    p.nunits = p.ntiles = p.nseg * ((rows + best - 1) / best);
+}
+
+int march_out_width() { return M_OUT; }
+
+cudaError_t launch_march2(const Step2Params &p, int nsm, cudaStream_t s) {
+    if (p.nunits <= 0) return cudaSuccess;
+    static bool configured[64] = {};       // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(march2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(march2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    // persistent: one CTA per SM, but never more warps than units
+    int grid = (p.nunits + M_WARPS - 1) / M_WARPS;
+    if (grid > nsm) grid = nsm;
+    if (p.diag) march2_kernel<true><<<grid, M_WARPS * 32, MARCH_SMEM, s>>>(p);
+    else march2_kernel<false><<<grid, M_WARPS * 32, MARCH_SMEM, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace alb

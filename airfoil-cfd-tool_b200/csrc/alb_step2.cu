@@ -60,109 +60,6 @@ namespace {
 // Same moments_clamped()/collide() as everywhere else -> bit-identical to two single steps.
 // Everything that is not "deep" (border cells, the body and its surroundings, slab edge rows) is
 // advanced by two passes of the list-driven single-step kernels through a third buffer.
-// jx/r and jy/r with a shared reciprocal: the instruction sequence of nvcc's own div.rn.f32 fast
-// path (MUFU.RCP, one Newton step, quotient, exact residual, one correction).  It yields the
-// correctly rounded quotient as long as no intermediate leaves the normal range.  The caller only
-// uses the result when quad_accept() holds: rho within the clamp interval [0.5, 2] (so the
-// reciprocal is harmless), |u|^2 <= uMax^2 (which bounds the numerators from above; the negated
-// comparison also catches NaN), and each numerator either +0 or at least 2^-60 in magnitude (the
-// return value; -0 and anything tiny go to true division, which knows about signed zeros and
-// underflow).  tests/test_gpu_div.py compares accepted results with IEEE division.
-__device__ __forceinline__ bool div_pair(float jx, float jy, float r, float &vx, float &vy) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(r));
-    const float e = __fmaf_rn(-r, y, 1.0f);
-    y = __fmaf_rn(y, e, y);
-    const float qx = __fmaf_rn(jx, y, 0.0f), qy = __fmaf_rn(jy, y, 0.0f);
-    const float rx = __fmaf_rn(-r, qx, jx), ry = __fmaf_rn(-r, qy, jy);
-    vx = __fmaf_rn(y, rx, qx);
-    vy = __fmaf_rn(y, ry, qy);
-    const bool nx_ok = fabsf(jx) >= 0x1p-60f || __float_as_uint(jx) == 0u;
-    const bool ny_ok = fabsf(jy) >= 0x1p-60f || __float_as_uint(jy) == 0u;
-    return nx_ok && ny_ok;
-}
-// true: the fast path's rho/ux/uy ARE the shader's values (no clamp fires, division exact)
-__device__ __forceinline__ bool quad_accept(float r, float spd2, bool nums_ok) {
-    const float rc = fminf(fmaxf(r, 0.5f), 2.0f);
-    return nums_ok && rc == r && spd2 <= 0.35f * 0.35f;
-}
-
-// Four cells at once, written so that the common case is ONE basic block: the generic IEEE
-// division (range check + branch to a slow path) and the |u| clamp (branch) would otherwise cut
-// the code of every cell into pieces that the scheduler cannot interleave, and a warp then crawls
-// along one dependent chain at a time (ncu: ~7 cycles between issues of a warp).
-//   * ux = jx/rho and uy = jy/rho use the very sequence nvcc emits for the fast path of
-//     div.rn.f32 (MUFU.RCP, one Newton step, quotient, exact residual, one correction -- see the
-//     SASS of moments_clamped), sharing the reciprocal of rho.  It is valid when no intermediate
-//     leaves the normal range; here: 2^-40 <= rho <= 2^40 and the numerator is +0 or has
-//     2^-60 <= |j| <= 2^40 (checked on the bit patterns).  tests/test_gpu_div.py compares it with
-//     true division for ~10^10 operand pairs.
-//   * anything else -- operands outside that range, a rho or |u| clamp that fires -- sets a bit
-//     in `bad`; those cells are redone by moments_clamped(), the literal transcription of the
-//     shader, in a cold branch.  Clamp hits can only occur there.
-// ALB_QUAD_G cells are worked on together (4: all in one basic block, most ILP, most registers;
-// 2: two pairs; 1: one cell at a time).
-#ifndef ALB_QUAD_G
-#define ALB_QUAD_G 4
-#endif
-#ifndef ALB_QUAD_GB          // the same for the step-2 warps of step2_kernel
-#define ALB_QUAD_GB ALB_QUAD_G
-#endif
-// mac: optional, receives rho/ux/uy of the four cells (what the shader writes to its macro texture)
-template <int G = ALB_QUAD_G>
-__device__ __forceinline__ unsigned collide_quad(float4 (&o)[9], float tau, float rcp, float rcp_lo,
-                                                 float (*mac)[3] = nullptr) {
-    unsigned hitmask = 0;
-#pragma unroll
-    for (int k0 = 0; k0 < 4; k0 += G) {
-        float rho[G], ux[G], uy[G];
-        unsigned bad = 0;
-#pragma unroll
-        for (int kk = 0; kk < G; kk++) {
-            const int k = k0 + kk;
-            const float f0 = comp(o[0], k), f1 = comp(o[1], k), f2 = comp(o[2], k), f3 = comp(o[3], k), f4 = comp(o[4], k);
-            const float f5 = comp(o[5], k), f6 = comp(o[6], k), f7 = comp(o[7], k), f8 = comp(o[8], k);
-            float r = f0;
-            r = r + f1; r = r + f2; r = r + f3; r = r + f4; r = r + f5; r = r + f6; r = r + f7; r = r + f8;
-            const float jx = f1 + f5 + f8 - f3 - f6 - f7;
-            const float jy = f2 + f5 + f6 - f4 - f7 - f8;
-            float vx, vy;
-            const bool nums_ok = div_pair(jx, jy, r, vx, vy);
-            const float spd2 = vx * vx + vy * vy;
-            if (!quad_accept(r, spd2, nums_ok)) bad |= 1u << kk;
-            rho[kk] = r;          // in [0.5, 2] unless the cell is flagged
-            ux[kk] = vx;
-            uy[kk] = vy;
-        }
-        if (bad) {
-#pragma unroll
-            for (int kk = 0; kk < G; kk++) {
-                if (bad & (1u << kk)) {
-                    float f[9];
-#pragma unroll
-                    for (int i = 0; i < 9; i++) f[i] = comp(o[i], k0 + kk);
-                    const Moments m = moments_clamped(f);
-                    rho[kk] = m.rho; ux[kk] = m.ux; uy[kk] = m.uy;
-                    if (m.hit) hitmask |= 1u << (k0 + kk);
-                }
-            }
-        }
-#pragma unroll
-        for (int kk = 0; kk < G; kk++) {
-            float f[9];
-#pragma unroll
-            for (int i = 0; i < 9; i++) f[i] = comp(o[i], k0 + kk);
-            Moments m;
-            m.rho = rho[kk]; m.ux = ux[kk]; m.uy = uy[kk]; m.hit = false;
-            if (mac) { mac[k0 + kk][0] = m.rho; mac[k0 + kk][1] = m.ux; mac[k0 + kk][2] = m.uy; }
-            collide(f, m, tau, rcp, rcp_lo);
-#pragma unroll
-            for (int i = 0; i < 9; i++) setc(o[i], k0 + kk, f[i]);
-        }
-    }
-    return hitmask;
-}
-
 // dst = src on the listed tasks (all-solid tasks over a double step, see build_lists_kernel)
 __global__ void __launch_bounds__(BLOCK_THREADS)
 copy_tasks_kernel(const __grid_constant__ StepParams p) {

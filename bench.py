@@ -141,7 +141,7 @@ def cpu_sample(nx, ny, shape, alpha, band_rows, steps, warmup, max_seconds=None)
     # rasterise only the band (+ghost rows): reuse the oracle's scan conversion row by row
     full_rows = range(y0 - 1, y0 + band + 1)
     mask = np.zeros((nrows, nx), np.uint8)
-    sub = _raster_rows(ogeo, xp, yp, nx, ny, full_rows)
+    sub = ogeo.raster_rows(xp, yp, nx, ny, full_rows)
     mask[:, :] = sub
     F, rho, ux, uy = olbm.init(nx, nrows, U0)
     G = F.copy()
@@ -163,29 +163,6 @@ def cpu_sample(nx, ny, shape, alpha, band_rows, steps, warmup, max_seconds=None)
     return dict(glups=cells * done / dt / 1e9, seconds=dt, steps=done, cells=cells, cores=cores,
                 sample=f"rows {y0}..{y0 + band - 1} of the {nx}x{ny} lattice ({cells} cells/step), "
                        f"{done} steps, {cores} OpenMP threads")
-
-
-def _raster_rows(ogeo, xp, yp, nx, ny, rows):
-    import math
-    import numpy as np
-    out = np.zeros((len(rows), nx), np.uint8)
-    n = len(xp)
-    for k, iy in enumerate(rows):
-        if iy < 0 or iy >= ny:
-            continue
-        wy = ogeo.DY0 + (iy + 0.5) / ny * (ogeo.DY1 - ogeo.DY0)
-        xs = []
-        for i in range(n - 1):
-            y1, y2 = yp[i], yp[i + 1]
-            if (y1 > wy) != (y2 > wy):
-                xs.append(xp[i] + (xp[i + 1] - xp[i]) * (wy - y1) / (y2 - y1))
-        xs.sort()
-        for q in range(0, len(xs) - 1, 2):
-            a = max(0, math.ceil((xs[q] - ogeo.DX0) / (ogeo.DX1 - ogeo.DX0) * nx))
-            b = min(nx - 1, math.floor((xs[q + 1] - ogeo.DX0) / (ogeo.DX1 - ogeo.DX0) * nx))
-            if b >= a:
-                out[k, a:b + 1] = 255
-    return out
 
 
 def run_reference(args, rank, world):

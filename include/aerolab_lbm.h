@@ -115,6 +115,16 @@ int alb_last_step_ms(alb_handle *h, float *ms);
 /* ---- state: replaces readPixels of the ping-pong set, HTML:547-552 -------- */
 
 int alb_get_populations(alb_handle *h, float *f /* 9*ny_local*nx */);
+/* Rows row0 .. row0+nrows-1 of the slab's current populations (0 = first owned row;
+ * -1 and ny_local are the ghost rows), dense [9][nrows][nx].  For inspecting bands of
+ * lattices too large to copy whole (configs[3] is 19 GB per state).  Synchronises. */
+int alb_get_population_rows(alb_handle *h, int row0, int nrows, float *f);
+/* Checksum of the current populations: out9[i] = sum over the slab's owned cells of
+ * mix64(global cell index, bit pattern of f_i) mod 2^64.  Position dependent and order
+ * independent, so the words of all slabs of a lattice add up (mod 2^64) to the words of
+ * the same state held by one GPU -- the cheap proof that N GPUs computed what one GPU
+ * computes (HTML:283-360 has no decomposition to mirror).  Synchronises. */
+int alb_state_hash(alb_handle *h, unsigned long long *out9);
 int alb_set_populations(alb_handle *h, const float *f);
 /* texC.gba of the current set (HTML:359, 547-552): rho, ux, uy as the last
  * step wrote them (clamped values in the interior, (1,0,0) in solids, (1,U0,0)
@@ -258,8 +268,10 @@ int alb_set_double_steps(alb_handle *h, int mode);
 /* mode as set; active = 1 when step batches of this handle use double steps. */
 int alb_get_double_steps(const alb_handle *h, int *mode, int *active);
 /* Host-only (no device needed): the tiling the fused two-step kernel would use for
- * an nx-wide slab of ny_local rows on a GPU with nsm SMs.  out5 = {strips, output
- * columns per strip, rows per segment, tiles, strip width of the kernel}. */
+ * an nx-wide slab of ny_local rows on a GPU with nsm SMs.  out5 = {column segments
+ * (over columns [128, pitch-128): the first and last 128-cell task of a row hold the
+ * inlet / outlet and are never deep), output columns per segment, rows per segment,
+ * units (= column segments x row segments; one warp each), columns a unit reads}. */
 int alb_debug_step2_plan(int nx, int ny_local, int nsm, int *out5);
 /* Number of CUDA kernels the step batches of this handle have launched so far
  * (alb_step / alb_run_frames; kernels inside replayed CUDA graphs included). */

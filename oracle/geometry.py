@@ -124,16 +124,20 @@ def panelise(coords):
     return xp, yp
 
 
-def raster_mask(xp, yp, nx, ny):
-    """HTML:160-182. Scanline even-odd fill; returns uint8[ny, nx] of 0/255.
+def raster_rows(xp, yp, nx, ny, rows):
+    """HTML:160-182 for the lattice rows listed in ``rows`` (global indices; rows outside
+    [0, ny) come out empty): uint8[len(rows), nx] of 0/255.  Scanline even-odd fill.
 
     Row 0 is the bottom of the world window (y up).  y is sampled at cell
     centres, x at integer node positions; the polygon is NOT closed and an
     unpaired last crossing is dropped -- all as in the reference.
     """
-    mask = np.zeros((ny, nx), dtype=np.uint8)
+    rows = list(rows)
+    mask = np.zeros((len(rows), nx), dtype=np.uint8)
     n = len(xp)
-    for iy in range(ny):
+    for r, iy in enumerate(rows):
+        if iy < 0 or iy >= ny:
+            continue
         wy = DY0 + (iy + 0.5) / ny * (DY1 - DY0)
         xs = []
         for i in range(n - 1):
@@ -151,9 +155,14 @@ def raster_mask(xp, yp, nx, ny):
             ix0 = max(0, ix0)
             ix1 = min(nx - 1, ix1)
             if ix1 >= ix0:
-                mask[iy, ix0:ix1 + 1] = 255
+                mask[r, ix0:ix1 + 1] = 255
             k += 2
     return mask
+
+
+def raster_mask(xp, yp, nx, ny):
+    """HTML:160-182 for the whole lattice: uint8[ny, nx] of 0/255."""
+    return raster_rows(xp, yp, nx, ny, range(ny))
 
 
 def build_geometry(base_coords, a_deg, nx, ny):
