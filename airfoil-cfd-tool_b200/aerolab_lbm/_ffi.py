@@ -43,7 +43,7 @@ EXPORTS = [
     "alb_run_frames", "alb_frames_enqueue", "alb_frames_collect",
     "alb_particles_init", "alb_particles_resize", "alb_particles_step", "alb_particles_get",
     "alb_create_multi", "alb_step_multi", "alb_connect_local", "alb_ipc_export", "alb_ipc_connect", "alb_halo_prime", "alb_halo_ptrs",
-    "alb_set_external_halo", "alb_set_double_steps", "alb_selftest_division", "alb_launch_count", "alb_get_double_steps", "alb_debug_step2_plan",
+    "alb_set_external_halo", "alb_set_double_steps", "alb_selftest_division", "alb_launch_count", "alb_get_double_steps", "alb_debug_step2_plan", "alb_get_div_mode", "alb_set_div_mode",
 ]
 
 
@@ -136,6 +136,8 @@ def lib():
     L.alb_launch_count.argtypes = [H, C.POINTER(C.c_longlong)]
     L.alb_get_double_steps.argtypes = [H, ip, ip]
     L.alb_debug_step2_plan.argtypes = [C.c_int, C.c_int, C.c_int, ip]
+    L.alb_get_div_mode.argtypes = [H, ip]
+    L.alb_set_div_mode.argtypes = [H, C.c_int]
     L.alb_selftest_division.argtypes = [H, C.c_ulonglong, C.c_longlong, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

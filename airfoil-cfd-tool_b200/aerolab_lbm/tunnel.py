@@ -413,6 +413,17 @@ class WindTunnel:
         self._ck(self._lib.alb_get_double_steps(self._h, None, C.byref(a)))
         return bool(a.value)
 
+    def div_mode(self) -> int:
+        """0: the verified three-instruction division by tau is in use; 1: IEEE division."""
+        m = C.c_int(0)
+        self._ck(self._lib.alb_get_div_mode(self._h, C.byref(m)))
+        return m.value
+
+    def set_div_mode(self, mode: int):
+        """1 forces IEEE division by tau, -1 returns to automatic (bit-identical results either way)."""
+        self._ck(self._lib.alb_set_div_mode(self._h, int(mode)))
+        return self
+
     def step2_plan(self, nsm: int = 148) -> dict:
         """Tiling of the fused two-step kernel for this slab (``alb_debug_step2_plan``)."""
         out = (C.c_int * 5)()

@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <new>
 
 #include "alb_common.cuh"
@@ -80,7 +82,6 @@ struct alb_handle {
     int *list_counts = nullptr;
     int nlist[5] = {0, 0, 0, 0, 0};
     int *s2_queue = nullptr;      // work queue of march2_kernel: {next unit, finished warps}, zero between launches
-    int s2_kernel = 0;            // 0: march2_kernel (one independent warp per unit), 1: step2_kernel (strip CTAs)
     bool solid_synced = false;    // both ping-pong buffers hold the same values on the all-solid tasks (lists[4])
     int double_mode = -1;         // -1 automatic, 0 never, 1 whenever possible (AEROLAB_LBM_DOUBLE / alb_set_option)
     int graph_parity = 0;         // h->parity the graph was captured at
@@ -96,7 +97,9 @@ struct alb_handle {
     int small_capacity = 0;       // cells the persistent small-lattice kernel can hold on this GPU
     int nsm = 148;                // SMs of the device
     double u0 = 0.06, tau = 0.58;
-    float u0f = 0, tauf = 0, inv_tau = 0, inv_tau_lo = 0;
+    float u0f = 0, tauf = 0, inv_tau = 0;
+    int div_mode = 1;             // DM_IEEE until the three-instruction x / tau has been verified for tauf
+    bool div_forced = false;      // alb_set_div_mode(h, 1): stay on IEEE division whatever tau is
     float feq0[9];
     cudaStream_t stream = nullptr;
     cudaStream_t aux = nullptr;   // runs the general-task kernel concurrently with the fast kernel
@@ -104,6 +107,10 @@ struct alb_handle {
     bool timed = false;
     long long steps = 0;          // user-visible step count
     long long sync_steps = 0;     // monotonic, drives the halo flags and the ME ring
+    // Slab protocol: the signal that ends a batch is held back until the next batch starts.  Until
+    // then the neighbours cannot begin the step that overwrites the ghost rows of my PREVIOUS state,
+    // which the lazy macroscopic pass (run_macro_pass / ensure_prev) still reads.  -1: nothing held.
+    long long pending_signal = -1;
     MeState *me = nullptr;
     cudaGraphExec_t graph = nullptr;   // GRAPH_STEPS steps starting at cur == 0 (see alb_step)
     unsigned long long *clamp_hits = nullptr;
@@ -191,11 +198,47 @@ void drop_graph(alb_handle *h) {
     }
 }
 
+// How the kernels may divide by this tau (div_by_tau in alb_lbm.cuh).  The three-instruction
+// sequence is used only for a tau for which the device has just compared it with IEEE division
+// over every operand the kernels can see (805 M values, well under a millisecond); the verdicts are
+// remembered per process.  AEROLAB_LBM_DIV=ieee forces true division (A/B measurements).
+int div_mode_for(alb_handle *h, float tau) {
+    static std::mutex mu;
+    static std::map<uint32_t, int> verdicts;
+    static const bool force_ieee = getenv("AEROLAB_LBM_DIV") && strcmp(getenv("AEROLAB_LBM_DIV"), "ieee") == 0;
+    if (force_ieee) return 1;
+    uint32_t key;
+    memcpy(&key, &tau, 4);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = verdicts.find(key);
+        if (it != verdicts.end()) return it->second;
+    }
+    int mode = 1;                                  // DM_IEEE unless proven otherwise
+    const float rcp = 1.0f / tau;
+    if (isfinite(rcp) && tau >= 0x1p-20f && tau <= 0x1p20f) {
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(h->d_part), bad = 1;
+        if (cudaStreamSynchronize(h->stream) == cudaSuccess &&          // d_part is reduction scratch
+            launch_divtau_check(tau, rcp, d, h->stream) == cudaSuccess &&
+            cudaMemcpyAsync(&bad, d, sizeof bad, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess &&
+            cudaStreamSynchronize(h->stream) == cudaSuccess && bad == 0)
+            mode = 0;                              // DM_FAST3
+        else
+            cudaGetLastError();
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    verdicts[key] = mode;
+    return mode;
+}
+
 void refresh_params(alb_handle *h) {
     h->u0f = (float)h->u0;
-    h->tauf = (float)h->tau;
-    h->inv_tau = 1.0f / h->tauf;
-    h->inv_tau_lo = (float)(1.0 / (double)h->tauf - (double)h->inv_tau);
+    const float tauf = (float)h->tau;
+    if (tauf != h->tauf || h->inv_tau == 0) {
+        h->tauf = tauf;
+        h->inv_tau = 1.0f / tauf;
+        h->div_mode = h->div_forced ? 1 : div_mode_for(h, tauf);
+    }
     host_feq0(h->u0f, h->feq0);
 }
 
@@ -216,7 +259,7 @@ StepParams make_params(alb_handle *h, int src_idx, int dst_idx = -1, int parity 
     p.nx = h->nx;
     p.tau = h->tauf;
     p.inv_tau = h->inv_tau;
-    p.inv_tau_lo = h->inv_tau_lo;
+    p.div_mode = h->div_mode;
     p.u0 = h->u0f;
     memcpy(p.feq0, h->feq0, sizeof p.feq0);
     p.rho = h->rho;
@@ -593,7 +636,6 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device));
         h->use_graph = getenv("AEROLAB_LBM_NO_GRAPH") == nullptr;   // A/B switch for measurements
         if (const char *e = getenv("AEROLAB_LBM_DOUBLE")) h->double_mode = atoi(e) != 0 ? 1 : 0;
-        if (const char *e = getenv("AEROLAB_LBM_S2_KERNEL")) h->s2_kernel = strcmp(e, "ring") == 0 ? 1 : 0;   // A/B switch
         if (const char *e = getenv("AEROLAB_LBM_TRACE")) {
             h->trace_step = atoll(e);
             for (auto &ev : h->tev) CK(cudaEventCreate(&ev));
@@ -755,8 +797,17 @@ void halo_signal(alb_handle *h, long long steps_done, cudaStream_t st) {
                                    (int)steps_done);
 }
 
+// The previous batch's closing signal: from here on the neighbours may overwrite the ghost rows of
+// what was this slab's previous state.
+void flush_pending_signal(alb_handle *h) {
+    if (h->pending_signal < 0) return;
+    halo_signal(h, h->pending_signal, h->stream);
+    h->launches++;
+    h->pending_signal = -1;
+}
+
 // Enqueue one step that reads buffer src_idx.  Used directly and under stream capture.
-int issue_step(alb_handle *h, int src_idx, int parity, bool halo, long long sync_step, bool diag) {
+int issue_step(alb_handle *h, int src_idx, int parity, bool halo, long long sync_step, bool diag, bool last_of_batch) {
     StepParams p = make_params(h, src_idx, 1 - src_idx, parity);
     h->solid_synced = false;    // solid cells swap their populations: the two buffers differ there now
     if (diag) {
@@ -786,7 +837,10 @@ int issue_step(alb_handle *h, int src_idx, int parity, bool halo, long long sync
         CK(launch_step_fast(p, h->stream));
         if (p.ngen > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     }
-    if (halo) halo_signal(h, sync_step + 1, h->stream);
+    if (halo) {
+        if (last_of_batch) h->pending_signal = sync_step + 1;
+        else halo_signal(h, sync_step + 1, h->stream);
+    }
     return ALB_OK;
 }
 
@@ -798,7 +852,7 @@ int issue_step(alb_handle *h, int src_idx, int parity, bool halo, long long sync
 //                by these passes exactly as by single steps, so step2_kernel needs no flags at all:
 //                next to a neighbouring slab TWO edge rows are shallow and it never reads a ghost row.
 int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sync_step, bool copy_solid,
-                 bool diag = false) {
+                 bool diag = false, bool last_of_batch = false) {
     const int dst_idx = 1 - src_idx;
     if (diag) {
         // a batch that ends with a double step: its second step reduces the statistics / face sums
@@ -834,7 +888,10 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
             CK(launch_copy_tasks(c, h->aux));
             h->launches++;
         }
-        if (halo) halo_signal(h, sync_step + pass + 1, h->aux);
+        if (halo) {
+            if (pass == 1 && last_of_batch) h->pending_signal = sync_step + 2;
+            else halo_signal(h, sync_step + pass + 1, h->aux);
+        }
         if (trace) CK(cudaEventRecord(h->tev[2 + 2 * pass], h->aux));      // pass finished and signalled
     }
     CK(cudaEventRecord(h->ev_join, h->aux));
@@ -849,19 +906,14 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
     q.nyl = h->nyl;
     q.tau = h->tauf;
     q.inv_tau = h->inv_tau;
-    q.inv_tau_lo = h->inv_tau_lo;
+    q.div_mode = h->div_mode;
     q.clamp_hits = h->clamp_hits;
     q.queue = h->s2_queue;
     if (diag) arm_diag2(h, q);
     // no flags here: next to a neighbouring slab two edge rows are shallow, the fused kernel never
     // reads a ghost row, and the GPUs only meet in the short list-driven passes
-    if (h->s2_kernel == 1) {
-        step2_plan(q, h->nsm);
-        CK(launch_step2(q, h->stream));
-    } else {
-        march_plan(q, h->nsm);
-        CK(launch_march2(q, h->nsm, h->stream));
-    }
+    march_plan(q, h->nsm);
+    CK(launch_march2(q, h->nsm, h->stream));
     h->launches += q.ntiles > 0 ? 1 : 0;
     if (trace) CK(cudaEventRecord(h->tev[5], h->stream));                  // fused kernel finished
     CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
@@ -918,7 +970,7 @@ int capture_graph(alb_handle *h, bool doubles) {
             r = issue_double(h, cur, parity, false, 0, s == 0);   // replayed after anything: the first one always copies
             s += 2;
         } else {
-            r = issue_step(h, cur, parity, false, 0, false);
+            r = issue_step(h, cur, parity, false, 0, false, false);
             parity ^= 1;
             s += 1;
         }
@@ -953,6 +1005,7 @@ static int step_batch(alb_handle *h, int nsteps) {
     static const bool fake_halo = getenv("AEROLAB_LBM_FAKE_HALO") != nullptr;
     const bool halo = !h->external_halo && (h->lo.base || h->hi.base || fake_halo);
     int left = nsteps;
+    flush_pending_signal(h);
     const bool doubles = double_steps_enabled(h);
     const bool persistent = !doubles && h->whole() && !halo && !h->external_halo && nsteps >= 2 &&
                             (long long)h->nx * h->nyl <= h->small_capacity;
@@ -993,7 +1046,7 @@ static int step_batch(alb_handle *h, int nsteps) {
         if (doubles && left >= 2 && left != 3) {
             // a batch may END with a double step (which then carries the diagnostics); the state in
             // between is not materialised, ensure_prev() recomputes it if the fields are asked for
-            int r = issue_double(h, h->cur, h->parity, halo, h->sync_steps + done, !h->solid_synced, left == 2);
+            int r = issue_double(h, h->cur, h->parity, halo, h->sync_steps + done, !h->solid_synced, left == 2, left == 2);
             if (r) return r;
             h->solid_synced = true;
             h->prev_idx = -1;
@@ -1002,7 +1055,7 @@ static int step_batch(alb_handle *h, int nsteps) {
             done += 2;
             continue;
         }
-        int r = issue_step(h, h->cur, h->parity, halo, h->sync_steps + done, left == 1);
+        int r = issue_step(h, h->cur, h->parity, halo, h->sync_steps + done, left == 1, left == 1);
         if (r) return r;
         h->prev_idx = h->cur;
         h->cur = 1 - h->cur;
@@ -1610,6 +1663,13 @@ int alb_step_multi(alb_handle **slabs, int nslabs, int nsteps) {
             if (slabs[a] && slabs[b] && slabs[a]->device == slabs[b]->device) chunk = 1;
     for (int done = 0; done < nsteps; done += chunk) {
         const int n = nsteps - done < chunk ? nsteps - done : chunk;
+        // all closing signals of the previous round first, so that no wait kernel below depends on
+        // work that is enqueued after it
+        for (int k = 0; k < nslabs; k++) {
+            if (!slabs[k]) return ALB_ERR_INVALID;
+            if (cudaSetDevice(slabs[k]->device) != cudaSuccess) return slabs[k]->fail(ALB_ERR_CUDA, "cudaSetDevice");
+            flush_pending_signal(slabs[k]);
+        }
         for (int k = 0; k < nslabs; k++) {
             int rc = alb_step(slabs[k], n);
             if (rc != ALB_OK) return rc;
@@ -1683,6 +1743,7 @@ int alb_halo_prime(alb_handle *h) {
     signal_kernel<<<1, 1, 0, h->stream>>>(h->lo.flags ? h->lo.flags + 1 : nullptr,
                                           h->hi.flags ? h->hi.flags + 0 : nullptr, (int)h->sync_steps);
     CK(cudaGetLastError());
+    h->pending_signal = -1;     // the neighbours now know this slab's step count
     return ALB_OK;
 }
 
@@ -1745,6 +1806,23 @@ int alb_get_double_steps(const alb_handle *h, int *mode, int *active) {
     if (!h) return ALB_ERR_INVALID;
     if (mode) *mode = h->double_mode;
     if (active) *active = double_steps_enabled(h) ? 1 : 0;
+    return ALB_OK;
+}
+
+int alb_get_div_mode(const alb_handle *h, int *mode) {
+    if (!h || !mode) return ALB_ERR_INVALID;
+    *mode = h->div_mode;
+    return ALB_OK;
+}
+
+int alb_set_div_mode(alb_handle *h, int mode) {
+    NEED(h);
+    NO_PENDING_FRAMES(h);
+    ARG(mode == -1 || mode == 1, "alb_set_div_mode: mode must be -1 (verified shortcut when possible) or 1 (IEEE division)");
+    const int m = mode == 1 ? 1 : div_mode_for(h, h->tauf);
+    if (m != h->div_mode) drop_graph(h);
+    h->div_mode = m;
+    h->div_forced = mode == 1;
     return ALB_OK;
 }
 

@@ -87,7 +87,7 @@ struct StepParams {
     int nyl;                 // rows owned by this slab
     int nx;
     float tau, inv_tau;      // inv_tau = RN(1/tau)
-    float inv_tau_lo;        // RN(1/tau - inv_tau): the part of the reciprocal that fp32 cannot hold
+    int div_mode;            // how x / tau is evaluated: DM_FAST3 (verified for this tau) or DM_IEEE, see div_by_tau()
     float u0;
     float feq0[9];           // feq_i(1, U0, 0) in fp32, source order (HTML:315-317)
     // macro output (macro mode only)
@@ -135,7 +135,8 @@ struct Step2Params {
     // queue {next unit, warps that have finished}, both zero between launches
     int nseg, nunits;
     int *queue;
-    float tau, inv_tau, inv_tau_lo;
+    float tau, inv_tau;
+    int div_mode;            // as in StepParams
     unsigned long long *clamp_hits;
     // fused statistics of the state being written (nullable), same meaning as in StepParams
     DiagAcc *diag;
@@ -181,17 +182,15 @@ int small_lattice_capacity(int device);
 cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps, cudaStream_t s);
 void host_feq0(float u0, float *out9);
 
-// alb_step2.cu -- two steps per pass
+// alb_step2.cu -- helpers of the two-steps-per-pass path
 cudaError_t launch_copy_tasks(const StepParams &p, cudaStream_t s);       // dst = src on the listed tasks
-// geometry of the fused two-step kernel for a pitch x nyl slab: fills wo/hs/nstrips/ntiles
-void step2_plan(Step2Params &p, int nsm);
-int step2_strip_width();   // 128 * K of the compiled kernel shape
-cudaError_t launch_step2(const Step2Params &p, cudaStream_t s);
 // alb_march.cu -- two steps per pass, one independent warp per unit (the default two-step kernel)
 void march_plan(Step2Params &p, int nsm);
 int march_out_width();     // output columns per warp
 cudaError_t launch_march2(const Step2Params &p, int nsm, cudaStream_t s);
 cudaError_t launch_div_selftest(unsigned long long seed, int nblocks, int iters, unsigned long long *d_out3, cudaStream_t s);
+// mismatches of the three-instruction x / tau against IEEE division over all fp32 x with 2^-40 <= |x| < 2^8
+cudaError_t launch_divtau_check(float tau, float rcp, unsigned long long *d_out1, cudaStream_t s);
 
 // alb_geometry.cu
 void host_rotate_panelise(const double *xy, int npts, double alpha_deg, double *xp, double *yp);

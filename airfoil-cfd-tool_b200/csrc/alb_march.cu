@@ -1,25 +1,31 @@
 // Two LBM steps per pass over HBM, second generation: march2_kernel.
 //
-// step2_kernel (alb_step2.cu) splits a CTA into step-1 and step-2 warps that meet at a
-// __syncthreads per row group; ncu showed a quarter of its issue slots lost at that barrier and
-// the kernel exists in one shape only (632-column strips), which rules out lattices narrower
-// than ~8000 columns.  Here every WARP is an independent unit of work and there is no barrier at
-// all:
+// step2_kernel (round 1) split a CTA into step-1 and step-2 warps that met at a __syncthreads per
+// row group; ncu showed a quarter of its issue slots lost at that barrier, and its one shape
+// (632-column strips) ruled out lattices narrower than ~8000 columns.  Here every WARP is an
+// independent unit of work and there is no barrier of any kind:
 //
 //   * a warp owns a column segment of 128 cells (4 per lane) and marches up a range of rows;
-//   * per row it runs step 1 on the 128 cells (inputs staged in its private shared-memory
-//     double buffer by nine 512-byte TMA bulk copies, issued two rows ahead, completion on the
-//     warp's own mbarrier), keeps the part of the intermediate state that later rows need in
-//     REGISTERS (36 per lane: f0,f1,f3 of the row below the new one, f2,f5,f6 of the two rows
-//     below) and immediately runs step 2 of the row below, whose remaining inputs (f4,f7,f8 of
-//     the row just computed) are in registers already; the result goes to HBM with 128-bit stores;
-//   * step 2 of a cell needs step 1 of its x-neighbours, so only lanes 1..30 produce output
-//     (120 columns per warp, segments overlap by 8 columns; 6.7 % redundant arithmetic instead of
-//     a shared intermediate ring and its barriers).  The intermediate state never touches shared
-//     memory;
-//   * units (row segment x column segment) are handed out through an atomic queue to the
-//     persistent warps of one CTA per SM, so there is no wave tail and any lattice with at least
-//     three 128-cell tasks per row can use it (2048- and 4096-wide lattices included).
+//   * per row it runs step 1 on the 128 cells.  The nine input vectors were copied into the warp's
+//     private shared-memory double buffer two rows ahead with cp.async (every lane copies and later
+//     reads its own 16 bytes, so completion is a per-thread cp.async.wait_group: no mbarrier, no
+//     __syncwarp).  The part of the intermediate state that the NEXT row's step 2 needs (f0,f1,f3)
+//     stays in registers; f2,f5,f6, needed two rows later, go through a private shared-memory slot
+//     (again own bytes only);
+//   * it then runs step 2 of the row below, whose remaining inputs (f4,f7,f8 of the row just
+//     computed) are in registers already, and stores the result to HBM with 128-bit stores;
+//   * step 2 of a cell needs step 1 of its x-neighbours, so only lanes 1..30 produce output (120
+//     columns per warp, segments overlap by 8 columns: 6.7 % redundant arithmetic instead of a
+//     shared intermediate ring and its barriers);
+//   * units (row segment x column segment) are handed out through an atomic queue to the persistent
+//     warps of one CTA per SM, so there is no wave tail, and any lattice with at least three
+//     128-cell tasks per row can use it (2048- and 4096-wide lattices included).
+//
+// Measured and rejected (profiles/r2a_*): staging with TMA bulk copies (nine 512-byte
+// cp.async.bulk per row and warp on the warp's own mbarrier).  UBLKCP takes its operands from
+// uniform registers, so per-lane issue turns into a 9-trip waterfall loop; 28 % of the kernel's
+// stall samples sat in that loop and the try_wait spin, and it ran no faster than the round-1
+// kernel (134.6 vs 131.6 GLUPS at configs[3]).
 //
 // Which cells it may write (deep tasks) and which intermediate values it needs (TF_NEED) comes
 // from the same task flags as before; everything else is advanced by the list-driven two-pass
@@ -50,28 +56,16 @@ namespace {
 constexpr int M_WARPS = ALB_MARCH_WARPS;      // warps per CTA, one CTA per SM
 constexpr int M_OUT = 120;                    // output columns per warp (lanes 1..30)
 constexpr int M_STAGE = 9 * 128;              // floats of one staged step-1 row (9 planes x 128 columns)
+constexpr int M_CARRY = 3 * 128;              // floats of one carried row (f2, f5, f6 of an intermediate row)
+constexpr int M_WARP_SMEM = 2 * M_STAGE + 2 * M_CARRY;   // floats of shared memory per warp
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+__device__ __forceinline__ void cp_async16(unsigned dst, const float *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}"
-        ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // x-shifts inside the warp; the outermost cell of lane 0 / lane 31 receives a value that is never used
 __device__ __forceinline__ float4 shl(const float4 &v) {   // populations arriving from x-1
@@ -81,29 +75,19 @@ __device__ __forceinline__ float4 shr(const float4 &v) {   // populations arrivi
     return make_float4(v.y, v.z, v.w, __shfl_down_sync(FULL, v.x, 1));
 }
 
-template <bool DIAG>
+template <bool DIAG, int DM>
 __global__ void __launch_bounds__(M_WARPS * 32, 1)
 march2_kernel(const __grid_constant__ Step2Params p) {
     extern __shared__ float4 smem4[];
-    float *const stage_all = reinterpret_cast<float *>(smem4);                       // [M_WARPS][2][9][128]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *const stg = stage_all + (size_t)warp * 2 * M_STAGE;
+    // this lane's own 16 bytes of every row of the warp's private buffers
+    float *const stg = reinterpret_cast<float *>(smem4) + (size_t)warp * M_WARP_SMEM + lane * 4;   // [2][9][128]
+    float *const car = stg + 2 * M_STAGE;                                                           // [2][3][128]
     const unsigned stg_u32 = smem_u32(stg);
-    const unsigned bar_u32 = smem_u32(stage_all + (size_t)M_WARPS * 2 * M_STAGE) + warp * 16;   // two mbarriers
-    if (lane == 0) {
-        mbar_init(bar_u32, 1);
-        mbar_init(bar_u32 + 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    unsigned phase = 0;                         // bit k: parity to wait for on mbarrier k
     const size_t plane = p.plane;
     const int pitch = p.pitch, tpr = p.tpr;
     [[maybe_unused]] const float *const src = p.src;
     [[maybe_unused]] float *const dst_base = p.dst;
-    // lanes 0..8 each copy one population plane: plane `lane`, row offset -e_y of that population
-    const int ey_l = (lane == 2 || lane == 5 || lane == 6) ? 1 : ((lane == 4 || lane == 7 || lane == 8) ? -1 : 0);
-    const float *const tma_base = p.src + (size_t)(lane < 9 ? lane : 0) * plane - (ptrdiff_t)ey_l * pitch;
     const bool own = lane >= 1 && lane <= 30;
     const int total_warps = gridDim.x * M_WARPS;
     unsigned hits = 0;
@@ -118,19 +102,20 @@ march2_kernel(const __grid_constant__ Step2Params p) {
         const int rowseg = unit / p.nseg, s = unit - rowseg * p.nseg;
         const int y0 = 2 + rowseg * p.hs;                // owned output rows [y0, y1)
         const int y1 = min(y0 + p.hs, p.nyl);
-        const int c0 = 124 + M_OUT * s;                  // first staged column; outputs are [c0 + 4, c0 + 124)
-        const int gx = c0 + lane * 4;
+        const int gx = 124 + M_OUT * s + lane * 4;       // this lane's quad; the warp writes columns [c0 + 4, c0 + 124)
         const uint8_t *const tfl = p.tflags + (gx >> 7);
-        const float *const tsrc = tma_base + c0;
         // task flags of rows a, a+1, a+2 (pipelined; rows beyond y1 are of no interest to this unit)
         auto row_flags = [&](int a) -> unsigned { return a <= y1 ? (unsigned)tfl[(size_t)a * tpr] : 0u; };
-        auto issue = [&](int a, int k) {                  // stage k <- inputs of step 1 of row a
-            if (lane == 0) mbar_arrive_expect_tx(bar_u32 + 8 * k, 9u * 512u);
-            __syncwarp();
-            if (lane < 9) {
-                const float *g = tsrc + (size_t)a * pitch;
-                ALB_CHECK_SRC(g, 128);
-                tma_load_1d(stg_u32 + (unsigned)(k * M_STAGE + lane * 128) * 4u, g, 512u, bar_u32 + 8 * k);
+        // stage k <- the nine input vectors of step 1 of row a (population i comes from row a - e_y(i))
+        auto issue = [&](int a, int k) {
+            const float *g = p.src + (size_t)a * pitch + gx;
+            const unsigned d = stg_u32 + (unsigned)(k * M_STAGE) * 4u;
+            const int ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                const float *gi = g + i * plane - (ptrdiff_t)ey[i] * pitch;
+                ALB_CHECK_SRC(gi, 4);
+                cp_async16(d + i * 512u, gi);
             }
         };
         int a = y0 - 1;
@@ -139,11 +124,11 @@ march2_kernel(const __grid_constant__ Step2Params p) {
         bool have = __any_sync(FULL, tf0 & TF_NEED);
         bool have1 = __any_sync(FULL, tf1 & TF_NEED);
         if (have) issue(a, 0);
+        cp_async_commit();
         if (have1) issue(a + 1, 1);
+        cp_async_commit();
         float4 wn0, wn1, wn3;                            // f0, f1, f3 of intermediate row a-1, already x-shifted
-        float4 up2, up5, up6;                            // f2, f5, f6 of intermediate row a-2
-        float4 uq2, uq5, uq6;                            // f2, f5, f6 of intermediate row a-1
-        wn0 = wn1 = wn3 = up2 = up5 = up6 = uq2 = uq5 = uq6 = make_float4(0.f, 0.f, 0.f, 0.f);
+        wn0 = wn1 = wn3 = make_float4(0.f, 0.f, 0.f, 0.f);
         float *d = p.dst + (size_t)(a - 1) * pitch + gx;  // destination of step-2 row a-1
         int k = 0;
 #pragma unroll 1
@@ -151,11 +136,10 @@ march2_kernel(const __grid_constant__ Step2Params p) {
             const unsigned tf3 = row_flags(a + 3);
             const bool have2 = __any_sync(FULL, tf2 & TF_NEED);
             float4 o[9];
+            cp_async_wait<1>();                          // everything but the newest group (row a+1) has landed
             if (have) {
                 // ---- step 1 of row a: staged inputs -> intermediate state (registers) ----
-                mbar_wait(bar_u32 + 8 * k, (phase >> k) & 1u);
-                phase ^= 1u << k;
-                const float *sp = stg + k * M_STAGE + lane * 4;
+                const float *sp = stg + k * M_STAGE;
                 const float4 v0 = *reinterpret_cast<const float4 *>(sp + 0 * 128);
                 const float4 v1 = *reinterpret_cast<const float4 *>(sp + 1 * 128);
                 const float4 v2 = *reinterpret_cast<const float4 *>(sp + 2 * 128);
@@ -174,9 +158,7 @@ march2_kernel(const __grid_constant__ Step2Params p) {
                 o[6] = shr(v6);
                 o[7] = shr(v7);
                 o[8] = shl(v8);
-            }
-            if (have) {
-                const unsigned hm = collide_quad(o, p.tau, p.inv_tau, p.inv_tau_lo);
+                const unsigned hm = collide_quad<DM>(o, p.tau, p.inv_tau);
                 // clamp hits of step 1: every deep cell is owned by exactly one unit
                 if ((tf0 & TF_DEEP) && own && a >= y0 && a < y1) hits += __popc(hm);
                 // what later rows pull from this one, x-shifts applied now
@@ -189,15 +171,19 @@ march2_kernel(const __grid_constant__ Step2Params p) {
             }
             // every staged value of row a has been consumed by the arithmetic above: refill the buffer
             if (have2) issue(a + 2, k);
+            cp_async_commit();                           // one group per row, empty or not
             // ---- step 2 of row a-1: f0,f1,f3 of its own row, f2,f5,f6 of row a-2, f4,f7,f8 of row a ----
             const bool st = (tfb & TF_DEEP) && own;
+            float *const cs = car + k * M_CARRY;         // holds f2,f5,f6 of row a-2; receives those of row a
             if (__any_sync(FULL, st)) {
                 float4 q[9];
                 q[0] = wn0; q[1] = wn1; q[3] = wn3;
-                q[2] = up2; q[5] = up5; q[6] = up6;
+                q[2] = *reinterpret_cast<const float4 *>(cs + 0 * 128);
+                q[5] = *reinterpret_cast<const float4 *>(cs + 1 * 128);
+                q[6] = *reinterpret_cast<const float4 *>(cs + 2 * 128);
                 q[4] = o[4]; q[7] = o[7]; q[8] = o[8];
                 float mac[4][3];
-                const unsigned hm = collide_quad<ALB_QUAD_GB>(q, p.tau, p.inv_tau, p.inv_tau_lo, DIAG ? mac : nullptr);
+                const unsigned hm = collide_quad<DM, ALB_QUAD_GB>(q, p.tau, p.inv_tau, DIAG ? mac : nullptr);
                 if (st) {
                     hits += __popc(hm);
 #pragma unroll
@@ -208,14 +194,18 @@ march2_kernel(const __grid_constant__ Step2Params p) {
                     }
                 }
             }
-            // rotate the carried rows
-            wn0 = o[0]; wn1 = o[1]; wn3 = o[3];
-            up2 = uq2; up5 = uq5; up6 = uq6;
-            uq2 = o[2]; uq5 = o[5]; uq6 = o[6];
+            // carry: this row's f0,f1,f3 in registers, its f2,f5,f6 in the slot just read
+            if (have) {
+                wn0 = o[0]; wn1 = o[1]; wn3 = o[3];
+                *reinterpret_cast<float4 *>(cs + 0 * 128) = o[2];
+                *reinterpret_cast<float4 *>(cs + 1 * 128) = o[5];
+                *reinterpret_cast<float4 *>(cs + 2 * 128) = o[6];
+            }
             tfb = (a >= y0 && a < y1) ? tf0 : 0u;
             tf0 = tf1; tf1 = tf2; tf2 = tf3;
             have = have1; have1 = have2;
         }
+        cp_async_wait<0>();
         unit = __shfl_sync(FULL, next_unit, 0);
     }
     if (DIAG) diag_flush<false>(p, dl, lane);
@@ -231,7 +221,7 @@ march2_kernel(const __grid_constant__ Step2Params p) {
     }
 }
 
-constexpr size_t MARCH_SMEM = sizeof(float) * (size_t)M_WARPS * 2 * M_STAGE + (size_t)M_WARPS * 16;
+constexpr size_t MARCH_SMEM = sizeof(float) * (size_t)M_WARPS * M_WARP_SMEM;
 
 }  // namespace
 
@@ -277,24 +267,27 @@ void march_plan(Step2Params &p, int nsm) {
 
 int march_out_width() { return M_OUT; }
 
-cudaError_t launch_march2(const Step2Params &p, int nsm, cudaStream_t s) {
-    if (p.nunits <= 0) return cudaSuccess;
-    static bool configured[64] = {};       // the attribute is per device
+template <bool DIAG, int DM>
+cudaError_t launch_march2_t(const Step2Params &p, int grid, cudaStream_t s) {
+    static bool configured[64] = {};       // the attribute is per device (and per instantiation)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(march2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(march2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(march2_kernel<DIAG, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
+    march2_kernel<DIAG, DM><<<grid, M_WARPS * 32, MARCH_SMEM, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_march2(const Step2Params &p, int nsm, cudaStream_t s) {
+    if (p.nunits <= 0) return cudaSuccess;
     // persistent: one CTA per SM, but never more warps than units
     int grid = (p.nunits + M_WARPS - 1) / M_WARPS;
     if (grid > nsm) grid = nsm;
-    if (p.diag) march2_kernel<true><<<grid, M_WARPS * 32, MARCH_SMEM, s>>>(p);
-    else march2_kernel<false><<<grid, M_WARPS * 32, MARCH_SMEM, s>>>(p);
-    return cudaGetLastError();
+    if (p.div_mode == DM_FAST3) return p.diag ? launch_march2_t<true, DM_FAST3>(p, grid, s) : launch_march2_t<false, DM_FAST3>(p, grid, s);
+    return p.diag ? launch_march2_t<true, DM_IEEE>(p, grid, s) : launch_march2_t<false, DM_IEEE>(p, grid, s);
 }
 
 }  // namespace alb

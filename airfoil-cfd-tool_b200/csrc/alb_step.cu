@@ -41,7 +41,23 @@ constexpr int KIND_FAST = 0, KIND_GENERAL = 1, KIND_UNIFIED = 2, KIND_FAST_LIST 
 
 // DIAG (step mode): also accumulate the autoscale statistics and pressure-face sums of the state
 // being WRITTEN (its rho/ux/uy are computed here anyway) -- used for the last step of a batch.
-template <int MODE, int KIND, bool DIAG = false>
+// halo push: a slab's edge rows go straight into the neighbours' ghost rows of the DESTINATION
+// buffer (peer memory over NVLink, or the same GPU for in-process slabs); only the populations that
+// cross the face: f2,f5,f6 upwards, f4,f7,f8 downwards
+__device__ __forceinline__ void push_halo(const StepParams &p, int j, int x0, const float4 (&o)[9]) {
+    if (j == p.nyl && p.peer_hi_dst) {
+        st4(p.peer_hi_dst + 2 * p.peer_hi_plane + p.peer_hi_row + x0, o[2]);
+        st4(p.peer_hi_dst + 5 * p.peer_hi_plane + p.peer_hi_row + x0, o[5]);
+        st4(p.peer_hi_dst + 6 * p.peer_hi_plane + p.peer_hi_row + x0, o[6]);
+    }
+    if (j == 1 && p.peer_lo_dst) {
+        st4(p.peer_lo_dst + 4 * p.peer_lo_plane + p.peer_lo_row + x0, o[4]);
+        st4(p.peer_lo_dst + 7 * p.peer_lo_plane + p.peer_lo_row + x0, o[7]);
+        st4(p.peer_lo_dst + 8 * p.peer_lo_plane + p.peer_lo_row + x0, o[8]);
+    }
+}
+
+template <int MODE, int KIND, bool DIAG = false, int DM = DM_FAST3>
 __global__ void __launch_bounds__(BLOCK_THREADS, (KIND == KIND_FAST || KIND == KIND_FAST_LIST) ? (DIAG ? ALB_DIAG_MINBLOCKS : ALB_FAST_MINBLOCKS) : 2)
 step_kernel(const __grid_constant__ StepParams p) {
     const int lane = threadIdx.x & 31;
@@ -78,8 +94,10 @@ step_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
             for (int i = 0; i < 9; i++) {
                 const float v = p.feq0[i];
-                ST4(p.dst + i * plane + c, make_float4(v, v, v, v));
+                o[i] = make_float4(v, v, v, v);
+                ST4(p.dst + i * plane + c, o[i]);
             }
+            push_halo(p, j, x0, o);   // a bottom / top slab of a single row: its border row is an edge row too
             if (DIAG) {   // 128 identical border cells (1, U0, 0), none of them next to a solid
                 DiagLocal d;
                 if (lane == 0) diag_cell(p, d, 1.0f, p.u0, 0.0f);
@@ -107,6 +125,7 @@ step_kernel(const __grid_constant__ StepParams p) {
             for (int i = 0; i < 9; i++) o[i] = LD4(src + opp[i] * plane + c);
 #pragma unroll
             for (int i = 0; i < 9; i++) ST4(p.dst + i * plane + c, o[i]);
+            push_halo(p, j, x0, o);   // nobody pulls from a solid cell, but keep the ghost rows a faithful copy
         } else if (p.write_macro) {
             st4(p.rho + c, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
             st4(p.ux + c, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
@@ -204,7 +223,7 @@ step_kernel(const __grid_constant__ StepParams p) {
 
         const Moments m = moments_clamped(f);
         float rho = m.rho, ux = m.ux, uy = m.uy;
-        if (MODE == MODE_STEP) collide(f, m, p.tau, p.inv_tau, p.inv_tau_lo);
+        if (MODE == MODE_STEP) collide<DM>(f, m, p.tau, p.inv_tau);
         bool hit = m.hit;
 
         if (GENERAL) {
@@ -265,18 +284,7 @@ step_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
         for (int i = 0; i < 9; i++) ST4(p.dst + i * plane + c, o[i]);
 
-        // halo push: my edge rows go straight into the neighbours' ghost rows
-        // (peer memory over NVLink, or the same GPU for in-process slabs)
-        if (j == p.nyl && p.peer_hi_dst) {
-            st4(p.peer_hi_dst + 2 * p.peer_hi_plane + p.peer_hi_row + x0, o[2]);
-            st4(p.peer_hi_dst + 5 * p.peer_hi_plane + p.peer_hi_row + x0, o[5]);
-            st4(p.peer_hi_dst + 6 * p.peer_hi_plane + p.peer_hi_row + x0, o[6]);
-        }
-        if (j == 1 && p.peer_lo_dst) {
-            st4(p.peer_lo_dst + 4 * p.peer_lo_plane + p.peer_lo_row + x0, o[4]);
-            st4(p.peer_lo_dst + 7 * p.peer_lo_plane + p.peer_lo_row + x0, o[7]);
-            st4(p.peer_lo_dst + 8 * p.peer_lo_plane + p.peer_lo_row + x0, o[8]);
-        }
+        push_halo(p, j, x0, o);
 
         if (DIAG) {
             if (KIND == KIND_FAST || KIND == KIND_FAST_LIST) diag_flush<false>(p, dl, lane);
@@ -317,6 +325,7 @@ step_kernel(const __grid_constant__ StepParams p) {
 // batch of steps inside one launch with a grid-wide barrier between steps.  The arithmetic is the
 // same moments_clamped()/collide() as the streaming kernels -> bit-identical results.
 // The last step of the batch also reduces the statistics / face sums of the final state (p.diag).
+template <int DM>
 __global__ void __launch_bounds__(BLOCK_THREADS)
 small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, int cur, int nsteps) {
     cg::grid_group grid = cg::this_grid();
@@ -363,7 +372,7 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
                     }
                 }
                 const Moments m = moments_clamped(f);
-                collide(f, m, p.tau, p.inv_tau, p.inv_tau_lo);
+                collide<DM>(f, m, p.tau, p.inv_tau);
                 hit = m.hit;
                 rho = m.rho; ux = m.ux; uy = m.uy;
             } else if (type == CT_SOLID) {
@@ -405,34 +414,34 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
 
 // The fast kernel and the general kernel of one step read the same source state and write
 // disjoint cells, so the caller may run them concurrently on two streams.
-cudaError_t launch_step_fast(const StepParams &p, cudaStream_t s) {
-    const int nblocks = (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
-    if (p.diag) step_kernel<MODE_STEP, KIND_FAST, true><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
-    else step_kernel<MODE_STEP, KIND_FAST><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+template <int KIND>
+cudaError_t launch_step_kind(const StepParams &p, int nblocks, cudaStream_t s) {
+    if (p.div_mode == DM_FAST3) {
+        if (p.diag) step_kernel<MODE_STEP, KIND, true, DM_FAST3><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+        else step_kernel<MODE_STEP, KIND, false, DM_FAST3><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    } else {
+        if (p.diag) step_kernel<MODE_STEP, KIND, true, DM_IEEE><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+        else step_kernel<MODE_STEP, KIND, false, DM_IEEE><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
+    }
     return cudaGetLastError();
+}
+
+cudaError_t launch_step_fast(const StepParams &p, cudaStream_t s) {
+    return launch_step_kind<KIND_FAST>(p, (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK, s);
 }
 
 cudaError_t launch_step_general(const StepParams &p, cudaStream_t s) {
     if (p.ngen == 0) return cudaSuccess;
-    const int gblocks = (p.ngen + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
-    if (p.diag) step_kernel<MODE_STEP, KIND_GENERAL, true><<<gblocks, BLOCK_THREADS, 0, s>>>(p);
-    else step_kernel<MODE_STEP, KIND_GENERAL><<<gblocks, BLOCK_THREADS, 0, s>>>(p);
-    return cudaGetLastError();
+    return launch_step_kind<KIND_GENERAL>(p, (p.ngen + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK, s);
 }
 
 cudaError_t launch_step_unified(const StepParams &p, cudaStream_t s) {
-    const int nblocks = (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK;
-    if (p.diag) step_kernel<MODE_STEP, KIND_UNIFIED, true><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
-    else step_kernel<MODE_STEP, KIND_UNIFIED><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
-    return cudaGetLastError();
+    return launch_step_kind<KIND_UNIFIED>(p, (p.ntasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK, s);
 }
 
 cudaError_t launch_step_fast_list(const StepParams &p, cudaStream_t s) {
     // at least one CTA even for an empty list: its first thread does the momentum-exchange bookkeeping
-    const int nblocks = p.ngen > 0 ? (p.ngen + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK : 1;
-    if (p.diag) step_kernel<MODE_STEP, KIND_FAST_LIST, true><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
-    else step_kernel<MODE_STEP, KIND_FAST_LIST><<<nblocks, BLOCK_THREADS, 0, s>>>(p);
-    return cudaGetLastError();
+    return launch_step_kind<KIND_FAST_LIST>(p, p.ngen > 0 ? (p.ngen + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK : 1, s);
 }
 
 // Largest number of cells the persistent small-lattice kernel can own on this device (all CTAs
@@ -441,9 +450,11 @@ int small_lattice_capacity(int device) {
     int coop = 0, sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop) return 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, small_lattice_kernel, BLOCK_THREADS, 0) != cudaSuccess)
+    int per_sm2 = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, small_lattice_kernel<DM_FAST3>, BLOCK_THREADS, 0) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, small_lattice_kernel<DM_IEEE>, BLOCK_THREADS, 0) != cudaSuccess)
         return 0;
-    return sms * per_sm * BLOCK_THREADS;
+    return sms * (per_sm < per_sm2 ? per_sm : per_sm2) * BLOCK_THREADS;
 }
 
 cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps, cudaStream_t s) {
@@ -451,7 +462,8 @@ cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int 
     const int nblocks = (ncell + BLOCK_THREADS - 1) / BLOCK_THREADS;
     StepParams pp = p;
     void *args[] = {&pp, &f0, &f1, &cur, &nsteps};
-    return cudaLaunchCooperativeKernel((const void *)small_lattice_kernel, dim3(nblocks), dim3(BLOCK_THREADS), args, 0, s);
+    const void *fn = p.div_mode == DM_FAST3 ? (const void *)small_lattice_kernel<DM_FAST3> : (const void *)small_lattice_kernel<DM_IEEE>;
+    return cudaLaunchCooperativeKernel(fn, dim3(nblocks), dim3(BLOCK_THREADS), args, 0, s);
 }
 
 cudaError_t launch_macro(const StepParams &p, cudaStream_t s) {

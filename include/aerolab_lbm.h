@@ -265,6 +265,14 @@ int alb_set_external_halo(alb_handle *h, int on);
  * lattice must use the same mode.  The environment variable AEROLAB_LBM_DOUBLE
  * (0/1) sets the initial mode of new handles. */
 int alb_set_double_steps(alb_handle *h, int mode);
+/* How the kernels evaluate the shader's division by tau (HTML:355, `fin - (fin - feq) / tau`).
+ * 0: a three-instruction sequence (multiply by RN(1/tau), exact residual, one correction) that the
+ *    library has just compared on the device with IEEE division for every fp32 operand of magnitude
+ *    [2^-40, 2^8) -- it is used only for a tau that passes with zero mismatches;
+ * 1: IEEE division (any other tau; or forced).  The result is bit-identical either way.
+ * alb_set_div_mode(h, 1) forces IEEE division, alb_set_div_mode(h, -1) returns to automatic. */
+int alb_get_div_mode(const alb_handle *h, int *mode);
+int alb_set_div_mode(alb_handle *h, int mode);
 /* mode as set; active = 1 when step batches of this handle use double steps. */
 int alb_get_double_steps(const alb_handle *h, int *mode, int *active);
 /* Host-only (no device needed): the tiling the fused two-step kernel would use for

@@ -5,16 +5,14 @@
 #include <stdint.h>
 #include <string.h>
 
-/* rcp = RN(1/tau), rcp_lo = RN(1/tau - rcp) (host, float64): x*(rcp+rcp_lo) rounded once is a
- * faithful quotient estimate; one Markstein correction with the exact residual then gives the
- * correctly rounded x/tau. */
-static inline float div_by_tau(float x, float tau, float rcp, float rcp_lo)
+/* DM_FAST3 of alb_lbm.cuh: q0 = RN(x*rcp) with rcp = RN(1/tau); exact residual r = x - tau*q0 (FMA);
+ * q = RN(q0 + r*rcp) (FMA).  Whether it equals IEEE division for every x depends on tau -- the
+ * library checks each tau on the device before using it; this is the same check on the CPU. */
+static inline float div_by_tau(float x, float tau, float rcp)
 {
-    float t = x * rcp_lo;
-    float q = fmaf(x, rcp, t);
+    float q = x * rcp;
     float r = fmaf(-tau, q, x);
-    q = fmaf(r, rcp, q);
-    return q;
+    return fmaf(r, rcp, q);
 }
 
 /* Returns the number of x in [lo_bits, hi_bits) (stepping by `stride` in bit space, both signs)
@@ -22,7 +20,6 @@ static inline float div_by_tau(float x, float tau, float rcp, float rcp_lo)
 long div_check(float tau, uint32_t lo_bits, uint32_t hi_bits, uint32_t stride, uint32_t *first_bad)
 {
     const float rcp = 1.0f / tau;
-    const float rcp_lo = (float)(1.0 / (double)tau - (double)rcp);
     long bad = 0;
     uint32_t fb = 0;
 #pragma omp parallel for reduction(+ : bad) schedule(static)
@@ -32,7 +29,7 @@ long div_check(float tau, uint32_t lo_bits, uint32_t hi_bits, uint32_t stride, u
         memcpy(&x, &u, 4);
         for (int sgn = 0; sgn < 2; sgn++) {
             float xs = sgn ? -x : x;
-            q1 = div_by_tau(xs, tau, rcp, rcp_lo);
+            q1 = div_by_tau(xs, tau, rcp);
             q2 = xs / tau;
             uint32_t a, c;
             memcpy(&a, &q1, 4);

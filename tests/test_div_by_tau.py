@@ -1,9 +1,12 @@
-"""CPU: the 5-instruction division by the uniform tau used in the step kernel
-(alb_lbm.cuh: div_by_tau) equals IEEE-754 division for every operand the kernel can see.
+"""CPU: the three-instruction division by the uniform tau used in the step kernels
+(alb_lbm.cuh: div_by_tau<DM_FAST3>) equals IEEE-754 division for every operand the kernel can see.
 
-Exhaustive over all fp32 values with magnitude in [2^-40, 2^8) for the reference's tau = 0.58 and
-other practical relaxation times, strided for a set of random ones.  (Operands in the kernel are
-differences of populations: exactly 0 or at least ~2^-30 in magnitude, and below 4.)"""
+The library never assumes this: whenever tau changes it runs the same exhaustive comparison on the
+device (divtau_check_kernel) and falls back to true division for a tau that fails
+(tests/test_gpu_div.py).  Here: exhaustive over all fp32 values with magnitude in [2^-40, 2^8) for
+the reference's tau = 0.58 and other practical relaxation times, strided for a set of random ones.
+(Operands in the kernel are differences of populations: exactly 0 or at least ~2^-32 in magnitude,
+and below 4.)"""
 import ctypes as C
 import os
 import struct
