@@ -75,6 +75,18 @@ class Comm:
         self._dist.all_reduce(t, op=ops[op])
         return t.cpu().numpy()
 
+    def allgather_array(self, a: np.ndarray) -> np.ndarray:
+        """Stack one equally shaped float64 array per rank along a new first axis (bit patterns are
+        preserved: the payload may be integers stored in the double slots)."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if not self._dist:
+            return a[None].copy()
+        import torch
+        t = torch.from_numpy(a.view(np.int64).copy()).to(self.device or "cpu")
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self._dist.all_gather(out, t)
+        return np.stack([o.cpu().numpy().view(np.float64) for o in out], axis=0)
+
     def allgather_float(self, x: float) -> List[float]:
         """One float per rank, known to every rank afterwards."""
         v = np.zeros(self.world)
@@ -156,6 +168,63 @@ class _DevRow:
 
     def __init__(self, addr: int, n: int):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (addr, False), "version": 2}
+
+
+FRAME_COLUMNS = ("CL", "CD", "sep_frac", "CL_raw", "CD_raw", "surf", "rev", "maxS", "cpMin", "cpMax", "CL_me", "CD_me")
+
+
+def combine_frame_partials(parts: np.ndarray, sticky: dict) -> dict:
+    """The page's per-frame host logic (HTML:611-613 autoscale, 672-679 + 699 force EMAs) applied to
+    the raw partial reductions that the slabs of a decomposed lattice record per frame
+    (``alb_frames_collect`` on a slab handle; layout in include/aerolab_lbm.h).
+
+    ``parts``: (nslabs, nframes, 12).  ``sticky``: dict(maxS, cpMin, cpMax, cl_smooth, cd_smooth,
+    sep_frac, ema_valid), updated in place.  Returns per-frame arrays keyed like
+    ``WindTunnel.run_frames``.  Extrema combine by max / min and the face sums are exact integers,
+    and the float64 operations below are the ones ``frame_finalize_kernel`` performs on one GPU, so
+    the series is identical to that of the undivided lattice."""
+    parts = np.ascontiguousarray(parts, dtype=np.float64)
+    nslabs, nframes, _ = parts.shape
+    ints = np.ascontiguousarray(parts[:, :, 3:9]).view(np.int64)
+    me_scale = float(2 ** 40)
+    out = np.empty((nframes, 12))
+    for f in range(nframes):
+        smax = float(parts[:, f, 0].max())
+        rho_min = float(parts[:, f, 1].min())
+        rho_max = float(parts[:, f, 2].max())
+        fx, fy, surf_i, rev_i, mfx_i, mfy_i = (int(v) for v in ints[:, f, :].sum(axis=0))
+        u0, q, do_forces = float(parts[0, f, 9]), float(parts[0, f, 10]), parts[0, f, 11] != 0
+        cden = (1.5 * u0) * u0
+        if smax > 0:
+            sticky["maxS"] = smax
+        if rho_min <= rho_max:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                cmin = float(np.float64(rho_min - 1.0) / np.float64(cden))
+                cmax = float(np.float64(rho_max - 1.0) / np.float64(cden))
+            if math.isfinite(cmin):
+                sticky["cpMin"] = cmin
+            if math.isfinite(cmax):
+                sticky["cpMax"] = cmax
+        cl_raw = cd_raw = surf = rev = math.nan
+        if do_forces:
+            surf, rev = float(surf_i), float(rev_i)
+            if surf_i > 0:
+                cl_raw = (float(fy) / me_scale / 3.0) / q
+                cd_raw = (float(fx) / me_scale / 3.0) / q
+                if not sticky["ema_valid"]:
+                    sticky["cl_smooth"], sticky["cd_smooth"], sticky["ema_valid"] = cl_raw, cd_raw, True
+                else:
+                    sticky["cl_smooth"] = sticky["cl_smooth"] * 0.9 + cl_raw * 0.1
+                    sticky["cd_smooth"] = sticky["cd_smooth"] * 0.9 + cd_raw * 0.1
+                sticky["sep_frac"] = sticky["sep_frac"] * 0.85 + (rev / surf) * 0.15
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cl_me = float(np.float64(float(mfy_i) / me_scale) / np.float64(q))
+            cd_me = float(np.float64(float(mfx_i) / me_scale) / np.float64(q))
+        out[f] = (sticky["cl_smooth"] if sticky["ema_valid"] else math.nan,
+                  sticky["cd_smooth"] if sticky["ema_valid"] else math.nan,
+                  sticky["sep_frac"], cl_raw, cd_raw, surf, rev,
+                  sticky["maxS"], sticky["cpMin"], sticky["cpMax"], cl_me, cd_me)
+    return {k: out[:, i] for i, k in enumerate(FRAME_COLUMNS)}
 
 
 def resplit_rows(rows: Sequence[int], times: Sequence[float], ny: int, min_rows: int = 8) -> List[int]:
@@ -276,7 +345,14 @@ class DistributedTunnel:
         return self
 
     def reset(self, u0=None):
+        """``initSim`` on every slab.  A slab may be one step behind its neighbours, and that step
+        still pushes halo rows into this slab's buffers: every rank finishes its own work, all ranks
+        meet, and only then are the buffers (ghost rows included) refilled."""
+        self.t.sync()
+        self.comm.barrier()
         self.t.reset(u0)
+        self.t.sync()
+        self.comm.barrier()
         self.cl_smooth = self.cd_smooth = None
         self.sep_frac = 0.0
         return self
@@ -355,6 +431,34 @@ class DistributedTunnel:
         tot = self.comm.allreduce(mine.view(np.int64), "sum")
         return np.ascontiguousarray(tot, dtype=np.int64).view(np.uint64)
 
+    def _sticky(self) -> dict:
+        return dict(maxS=self.max_s, cpMin=self.cp_min, cpMax=self.cp_max,
+                    cl_smooth=self.cl_smooth if self.cl_smooth is not None else 0.0,
+                    cd_smooth=self.cd_smooth if self.cd_smooth is not None else 0.0,
+                    sep_frac=self.sep_frac, ema_valid=self.cl_smooth is not None)
+
+    def run_frames(self, nframes: int, controls=None, steps_per_frame: int = 4, forces_every: int = 3) -> dict:
+        """``frame()`` x nframes (HTML:902-930) on the decomposed lattice with no host synchronisation
+        and no collective inside the loop: every slab enqueues all its frames (``alb_frames_enqueue``),
+        the per-frame partial reductions land in host memory as the frames complete, and only then
+        are they gathered (ONE all-gather) and run through the page's host logic
+        (:func:`combine_frame_partials`).  Same columns as ``WindTunnel.run_frames``."""
+        if self.halo == "nccl":
+            raise NotImplementedError("run_frames needs the in-kernel halo (halo='p2p'); use frame() with halo='nccl'")
+        self.t.frames_enqueue(nframes, controls=controls, steps_per_frame=steps_per_frame, forces_every=forces_every)
+        mine = self.t.frames_collect_raw()
+        parts = self.comm.allgather_array(mine)
+        if self.comm.world == 1 and self.t.ny_local == self.ny:
+            return {k: mine[:, i] for i, k in enumerate(FRAME_COLUMNS)}       # whole lattice: finished records
+        st = self._sticky()
+        series = combine_frame_partials(parts, st)
+        self.max_s, self.cp_min, self.cp_max = st["maxS"], st["cpMin"], st["cpMax"]
+        if st["ema_valid"]:
+            self.cl_smooth, self.cd_smooth = st["cl_smooth"], st["cd_smooth"]
+        self.sep_frac = st["sep_frac"]
+        self.t.set_stats(self.max_s, self.cp_min, self.cp_max)
+        return series
+
     def frame(self) -> dict:
         """The reference frame (HTML:902-930) across slabs: 4 steps, autoscale, forces every 3rd."""
         self.step(4)
@@ -404,20 +508,60 @@ def bench_e2e(tun: DistributedTunnel, comm: Comm, steps: int, cells_global: int)
                 "statistics/force EMAs, a 96 B record copied to host memory; no host synchronisation inside the "
                 "loop; host wall clock around the call including the final synchronisation")
     else:
-        for _ in range(3):
-            tun.frame()
-        tun.sync()
-        comm.barrier()
-        t0 = time.perf_counter()
-        for _ in range(nframes):
-            tun.set_params(u0, tau)
-            tun.frame()
-        tun.sync()
-        dt = comm.max_float(time.perf_counter() - t0)
-        comm.barrier()
-        h2d, d2h = 16.0, 3 * 8.0 + (4 * 8.0 + 16.0) / 3.0
-        what = ("frame loop driven from Python on every rank: set_params + 4 steps + per-slab statistics read back "
-                "and all-reduced every frame, forces every 3rd frame; host wall clock, max over ranks")
+        controls = np.tile(np.array([u0, tau]), (nframes, 1))
+        if tun.halo == "nccl":
+            for _ in range(3):
+                tun.frame()
+            tun.sync()
+            comm.barrier()
+            t0 = time.perf_counter()
+            for _ in range(nframes):
+                tun.set_params(u0, tau)
+                tun.frame()
+            tun.sync()
+            dt = comm.max_float(time.perf_counter() - t0)
+            comm.barrier()
+            h2d, d2h = 16.0, 3 * 8.0 + (4 * 8.0 + 16.0) / 3.0
+            what = ("frame loop driven from Python on every rank: set_params + 4 steps + per-slab statistics read "
+                    "back and all-reduced every frame, forces every 3rd frame; host wall clock, max over ranks")
+        else:
+            tun.run_frames(3, controls=controls[:3])
+            tun.sync()
+            comm.barrier()
+            t0 = time.perf_counter()
+            series = tun.run_frames(nframes, controls=controls)
+            dt = comm.max_float(time.perf_counter() - t0)
+            comm.barrier()
+            assert series["CL"].shape == (nframes,)
+            h2d, d2h = 16.0, 12 * 8.0
+            what = ("DistributedTunnel.run_frames: every rank enqueues all frames on its slab (alb_frames_enqueue: per "
+                    "frame 16 B of control inputs, 4 steps with in-kernel NVLink halo, on-device partial reductions, a "
+                    "96 B record copied to host memory), no host synchronisation or collective inside the loop; then one "
+                    "all-gather of the records and the page's EMA logic on the host; host wall clock around the call "
+                    "including the final synchronisation and the all-gather, max over ranks")
     return {"value": cells_global * 4 * nframes / dt / 1e9, "unit": "GLUPS",
             "h2d_bytes_per_step": h2d / 4.0, "d2h_bytes_per_step": d2h / 4.0,
             "frames": nframes, "steps_per_frame": 4, "what": what}
+
+
+def bench_e2e_fields(tun: DistributedTunnel, cells_global: int, nframes: int = 3) -> dict:
+    """The frame loop WITH the frame's image, as the page draws it every frame (HTML:909
+    ``renderField``): per frame 4 steps, the autoscale statistics, the colour-mapped speed field
+    rendered on the device (``alb_get_rgba``) and copied to host memory.  One GPU.  At configs[3] the
+    image is 2.1 GB per frame, so this figure is a PCIe number; the headless loop is ``e2e``."""
+    t = tun.t
+    u0, tau = t.params()
+    t.frame(want_field=None)
+    t.rgba("speed")
+    t.sync()
+    t0 = time.perf_counter()
+    for _ in range(nframes):
+        t.set_params(u0, tau)
+        t.run_frames(1)
+        img = t.rgba("speed")
+    dt = time.perf_counter() - t0
+    assert img.shape == (t.ny_local, t.nx, 4)
+    return {"value": cells_global * 4 * nframes / dt / 1e9, "unit": "GLUPS", "frames": nframes, "steps_per_frame": 4,
+            "h2d_bytes_per_step": 16.0 / 4.0, "d2h_bytes_per_step": (12 * 8.0 + 4.0 * cells_global) / 4.0,
+            "what": "per frame: 4 steps + on-device statistics (alb_run_frames), then alb_get_rgba: macroscopic pass, "
+                    "render kernel with the page's palette, RGBA8 image copied to pageable host memory; host wall clock"}

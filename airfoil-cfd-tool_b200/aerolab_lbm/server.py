@@ -6,7 +6,8 @@
 Conventions mirror main.py:543-628: multipart upload of a ``.dat`` file plus Form fields,
 validation failures -> HTTPException(400), solver failures -> 500, blocking work in
 ``anyio.to_thread.run_sync`` under an ``asyncio.Semaphore``, JSON reply ``{"success": True, ...}``.
-The same limits are reused (main.py:39-45): file <= 1 MiB, <= 500 points, alpha in [-10, 20].
+The same limits are reused (main.py:39-45): file <= 1 MiB, 10..500 points, alpha in [-10, 20], and
+the route is rate limited per client like /upload_airfoil/ (main.py:543-545, "5/minute").
 The coordinates go through the application's own ``parse_dat_file`` and the 6-decimal rounding
 of pages/Airfoil_Analysis.py:34-36, exactly what the browser tunnel receives.
 """
@@ -14,14 +15,18 @@ from __future__ import annotations
 
 import asyncio
 import base64
+import collections
 import logging
+import math
 import os
 import shutil
 import tempfile
+import threading
+import time
 from typing import Optional
 
 from anyio import to_thread
-from fastapi import APIRouter, Form, HTTPException, UploadFile
+from fastapi import APIRouter, Form, HTTPException, Request, UploadFile
 
 from . import geometry as geom
 from ._ffi import AerolabLbmError, ALB_ERR_INVALID, device_count
@@ -39,6 +44,9 @@ MIN_U0, MAX_U0 = 0.030, 0.100       # slider range, HTML:41
 MIN_TAU, MAX_TAU = 0.505, 2.0
 MAX_CELLS = 64 * 1024 * 1024
 MAX_STEPS = 200_000
+MAX_CELL_UPDATES = 2 * 10 ** 12     # nx*ny*steps per request: ~20 s of one B200
+MAX_FIELD_PIXELS = 4 * 1024 * 1024  # returned RGBA image: 16 MiB before base64
+RATE_LIMIT, RATE_WINDOW_S = 5, 60.0   # main.py:544 `@limiter.limit("5/minute")`
 LBM_DEVICE = int(os.getenv("AEROLAB_LBM_DEVICE", "0"))
 
 _gpu_semaphore: Optional[asyncio.Semaphore] = None
@@ -49,6 +57,43 @@ def _semaphore() -> asyncio.Semaphore:
     if _gpu_semaphore is None:
         _gpu_semaphore = asyncio.Semaphore(int(os.getenv("AEROLAB_LBM_CONCURRENCY", "3")))   # main.py:47
     return _gpu_semaphore
+
+
+class _RateLimiter:
+    """Sliding-window limit per client address: what slowapi's ``Limiter(key_func=get_remote_address)``
+    does for main.py's routes, without the dependency."""
+
+    def __init__(self, limit: int, window_s: float):
+        self.limit, self.window = limit, window_s
+        self.hits = collections.defaultdict(collections.deque)
+        self.lock = threading.Lock()
+
+    def check(self, key: str, now: Optional[float] = None) -> bool:
+        now = time.monotonic() if now is None else now
+        with self.lock:
+            q = self.hits[key]
+            while q and now - q[0] >= self.window:
+                q.popleft()
+            if len(q) >= self.limit:
+                return False
+            q.append(now)
+            return True
+
+
+_limiter = _RateLimiter(RATE_LIMIT, RATE_WINDOW_S)
+
+
+def _json_safe(x):
+    """NaN / inf are not JSON: CL and CD are NaN until a frame has seen surface faces."""
+    if isinstance(x, float):
+        return x if math.isfinite(x) else None
+    if isinstance(x, dict):
+        return {k: _json_safe(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_json_safe(v) for v in x]
+    if hasattr(x, "item") and getattr(x, "shape", None) == ():
+        return _json_safe(x.item())
+    return x
 
 
 def run_tunnel_sync(coords, name, alpha, u0, tau, nx, ny, steps, field, want_field):
@@ -76,9 +121,13 @@ def run_tunnel_sync(coords, name, alpha, u0, tau, nx, ny, steps, field, want_fie
         }
         if want_field:
             rgba = t.rgba(field)
+            stride = max(1, math.ceil(math.sqrt(rgba.shape[0] * rgba.shape[1] / MAX_FIELD_PIXELS)))
+            if stride > 1:                       # large lattices: every stride-th pixel, at most MAX_FIELD_PIXELS
+                rgba = rgba[::stride, ::stride].copy()
+            out["field_stride"] = stride
             out["field"] = {"mode": field, "shape": list(rgba.shape), "encoding": "base64/rgba8, row 0 = bottom",
                             "data": base64.b64encode(rgba.tobytes()).decode("ascii")}
-        return out
+        return _json_safe(out)
 
 
 @router.get("/lbm/health")
@@ -89,6 +138,7 @@ async def lbm_health():
 
 @router.post("/lbm/run/")
 async def lbm_run(
+    request: Request,
     file: UploadFile,
     alpha: float = Form(6.0),
     u0: float = Form(0.06),
@@ -99,6 +149,9 @@ async def lbm_run(
     field: str = Form("speed"),
     return_field: bool = Form(False),
 ):
+    client = request.client.host if request.client else "unknown"
+    if not _limiter.check(client):
+        raise HTTPException(status_code=429, detail=f"Rate limit exceeded: {RATE_LIMIT} per minute")
     if not (MIN_ALPHA <= alpha <= MAX_ALPHA):
         raise HTTPException(status_code=400, detail=f"Alpha must be {MIN_ALPHA} to {MAX_ALPHA} degrees")
     if not (MIN_U0 <= u0 <= MAX_U0):
@@ -109,6 +162,8 @@ async def lbm_run(
         raise HTTPException(status_code=400, detail=f"Lattice must be at least 16x8 and at most {MAX_CELLS} cells")
     if not (1 <= steps <= MAX_STEPS):
         raise HTTPException(status_code=400, detail=f"steps must be 1 to {MAX_STEPS}")
+    if nx * ny * steps > MAX_CELL_UPDATES:
+        raise HTTPException(status_code=400, detail=f"nx*ny*steps must not exceed {MAX_CELL_UPDATES:.0e} cell updates")
     if field not in ("speed", "cp", "vort"):
         raise HTTPException(status_code=400, detail="field must be speed, cp or vort")
     if not (file.filename or "").endswith(".dat"):
@@ -122,9 +177,14 @@ async def lbm_run(
         raw_path = os.path.join(work_dir, "raw.dat")
         with open(raw_path, "wb") as fh:
             fh.write(content)
-        raw_coords, parser_fixes = resolve_parser(None)(raw_path)
+        try:
+            raw_coords, parser_fixes = resolve_parser(None)(raw_path)
+        except ValueError as e:          # the stand-alone reader; main.py's parser raises HTTPException(400) itself
+            raise HTTPException(status_code=400, detail=str(e))
         if len(raw_coords) > MAX_POINTS:
             raise HTTPException(status_code=400, detail=f"Too many points (max {MAX_POINTS})")
+        if len(raw_coords) < MIN_POINTS:
+            raise HTTPException(status_code=400, detail=f"Too few points (min {MIN_POINTS})")
         coords = geom.round_coords(raw_coords)
         name = os.path.splitext(os.path.basename(file.filename))[0]
         async with _semaphore():

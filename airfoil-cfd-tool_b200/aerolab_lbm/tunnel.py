@@ -487,6 +487,15 @@ class WindTunnel:
         self._pending_frames = int(nframes)
         return self
 
+    def frames_collect_raw(self) -> np.ndarray:
+        """Second half of ``run_frames`` as the raw (nframes, 12) record array.  On a slab of a
+        decomposed lattice the records are partial reductions (include/aerolab_lbm.h)."""
+        n = getattr(self, "_pending_frames", 0)
+        series = np.empty((n, _ffi.ALB_FRAME_ROW))
+        self._ck(self._lib.alb_frames_collect(self._h, ptr(series) if n else None))
+        self._pending_frames = 0
+        return series
+
     def frames_collect(self) -> dict:
         n = getattr(self, "_pending_frames", 0)
         series = np.empty((n, _ffi.ALB_FRAME_ROW))
@@ -585,6 +594,18 @@ class LocalMultiTunnel:
             t.set_params(u0, tau)
         return self
 
+    def reset(self, u0: Optional[float] = None):
+        """``initSim`` on every slab: all slabs quiesce first (a neighbour one step behind would still
+        push halo rows into buffers that are being refilled), then all are reset."""
+        for t in self.slabs:
+            t.sync()
+        for t in self.slabs:
+            t.reset(u0)
+        for t in self.slabs:
+            t.sync()
+        self._sticky = dict(maxS=0.6, cpMin=-1.0, cpMax=1.0, cl_smooth=0.0, cd_smooth=0.0, sep_frac=0.0, ema_valid=False)
+        return self
+
     def step(self, n: int = 1):
         check(self._lib.alb_step_multi(self._handles, len(self.slabs), int(n)))
         return self
@@ -617,7 +638,24 @@ class LocalMultiTunnel:
             out.update(CL_me=float(me[1]) / _ffi.ALB_ME_SCALE / q, CD_me=float(me[0]) / _ffi.ALB_ME_SCALE / q)
         return out
 
+    def run_frames(self, nframes: int, controls=None, steps_per_frame: int = STEPS_PER_FRAME,
+                   forces_every: int = FORCES_EVERY_FRAMES) -> dict:
+        """``WindTunnel.run_frames`` on the decomposed lattice: every slab runs its frame loop on its
+        own GPU without host synchronisation; the per-frame partial reductions are combined
+        afterwards (``aerolab_lbm.distributed.combine_frame_partials``)."""
+        from .distributed import combine_frame_partials
+        for t in self.slabs:
+            t.frames_enqueue(nframes, controls=controls, steps_per_frame=steps_per_frame, forces_every=forces_every)
+        parts = np.stack([t.frames_collect_raw() for t in self.slabs], axis=0)
+        if not hasattr(self, "_sticky"):
+            self._sticky = dict(maxS=0.6, cpMin=-1.0, cpMax=1.0, cl_smooth=0.0, cd_smooth=0.0, sep_frac=0.0,
+                                ema_valid=False)      # HTML:593, 641
+        return combine_frame_partials(parts, self._sticky)
+
     def close(self):
+        # quiesce every slab before any block is freed: neighbours store halo rows and flags into it
+        for t in self.slabs:
+            t.sync()
         for t in self.slabs:
             t.close()
         self.slabs = []

@@ -127,6 +127,7 @@ struct alb_handle {
     double *d_rows = nullptr, *h_rows = nullptr;      // per-frame records (device, pinned host)
     int rows_cap = 0;
     int frames_pending = 0;                           // frames enqueued by alb_frames_enqueue, not yet collected
+    bool frames_partial = false;                      // ... by a slab: the records are raw partial reductions
     long long frame_counter = 0;                      // statCounter, HTML:594, 913
     ParticleState *parts = nullptr;
     unsigned *part_ctr = nullptr;
@@ -572,14 +573,16 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         // The aux stream runs the general-task kernel of single steps and the list-driven passes of
-        // double steps.  NORMAL priority: with a high-priority aux stream the passes cut into the fused
-        // step2_kernel at its wave boundaries and every double step of a slab costs 2.47 instead of
-        // 2.23 ms (measured on one GPU with AEROLAB_LBM_FAKE_HALO=1; 434 -> 482 GLUPS at 4 GPUs, 867 -> 929 at
-        // 8).  At normal priority they run before the fused kernel's CTAs when they are ready first,
-        // else in its tail.  AEROLAB_LBM_AUX_PRIO=1 restores the high priority for measurements.
+        // double steps.  HIGH priority: march2_kernel fills every SM (one CTA owns the whole register
+        // file), so the short passes only get SMs when one of its CTAs retires (every warp takes a
+        // bounded number of units from the queue, see march_plan), and at that moment they must win
+        // against the next CTA of the fused kernel -- otherwise pass 2, and with it the neighbouring
+        // slabs, would wait for the end of the whole pass.  The units come from a queue, so an SM lent
+        // to a pass costs no wave.  (Round 1's strip kernel had whole waves of tiles; there a
+        // high-priority aux stream cost 10 %.)  AEROLAB_LBM_AUX_PRIO=0 selects normal priority.
         const char *aux_prio = getenv("AEROLAB_LBM_AUX_PRIO");
         CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking,
-                                        aux_prio && atoi(aux_prio) == 1 ? prio_hi : prio_lo));
+                                        aux_prio && atoi(aux_prio) == 0 ? prio_lo : prio_hi));
         CK(cudaEventCreate(&h->ev0));
         CK(cudaEventCreate(&h->ev1));
         CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -1089,8 +1092,9 @@ int alb_step(alb_handle *h, int nsteps) {
 int alb_frames_enqueue(alb_handle *h, int nframes, int steps_per_frame, int forces_every, const double *controls) {
     NEED(h);
     ARG(nframes >= 0 && steps_per_frame >= 1, "alb_run_frames: need nframes >= 0 and steps_per_frame >= 1");
-    if (!h->whole() || h->lo.base || h->hi.base)
-        return h->fail(ALB_ERR_STATE, "alb_run_frames needs a whole-lattice handle");
+    // a slab of a decomposed lattice records the raw partial reductions of every frame (see
+    // alb_frames_collect); the caller combines the slabs
+    const bool partial = !h->whole() || h->lo.base || h->hi.base || h->external_halo;
     if (h->frames_pending) return h->fail(ALB_ERR_STATE, "alb_frames_enqueue: collect the previous batch first");
     if (nframes == 0) return ALB_OK;
     if (controls)
@@ -1128,8 +1132,8 @@ int alb_frames_enqueue(alb_handle *h, int nframes, int steps_per_frame, int forc
         if (r) return r;
         h->frame_counter++;
         const int do_forces = forces_every > 0 && (h->frame_counter % forces_every == 0);
-        CK(launch_frame_finalize(h->d_diag, h->d_diag_pub, h->me, h->parity ^ 1, h->d_frame, do_forces, h->u0,
-                                 h->qdyn(), h->d_rows + (size_t)FRAME_ROW * f, h->stream));
+        CK(launch_frame_finalize(h->d_diag, h->d_diag_pub, h->me, h->parity ^ 1, partial ? nullptr : h->d_frame, do_forces,
+                                 h->u0, h->qdyn(), h->d_rows + (size_t)FRAME_ROW * f, h->stream));
         h->diag_prearmed = true;
     }
     CK(cudaEventRecord(h->ev1, h->stream));
@@ -1138,6 +1142,7 @@ int alb_frames_enqueue(alb_handle *h, int nframes, int steps_per_frame, int forc
     h->diag_slots_host = 1;
     CK(cudaMemcpyAsync(h->h_frame, h->d_frame, sizeof(FrameDev), cudaMemcpyDeviceToHost, h->stream));
     h->frames_pending = nframes;
+    h->frames_partial = partial;
     return ALB_OK;
 }
 
@@ -1147,10 +1152,12 @@ int alb_frames_collect(alb_handle *h, double *series) {
     if (nframes == 0) return ALB_OK;
     CK(cudaStreamSynchronize(h->stream));
     h->frames_pending = 0;
-    const FrameDev &o = *h->h_frame;
-    h->maxS = o.maxS; h->cpMin = o.cpMin; h->cpMax = o.cpMax;
-    h->cl_smooth = o.cl_smooth; h->cd_smooth = o.cd_smooth; h->sep_frac = o.sep_frac;
-    h->ema_valid = o.ema_valid != 0;
+    if (!h->frames_partial) {
+        const FrameDev &o = *h->h_frame;
+        h->maxS = o.maxS; h->cpMin = o.cpMin; h->cpMax = o.cpMax;
+        h->cl_smooth = o.cl_smooth; h->cd_smooth = o.cd_smooth; h->sep_frac = o.sep_frac;
+        h->ema_valid = o.ema_valid != 0;
+    }
     if (series) memcpy(series, h->h_rows, sizeof(double) * FRAME_ROW * nframes);
     return check_wait_error(h);
 }

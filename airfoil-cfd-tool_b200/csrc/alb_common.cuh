@@ -134,6 +134,7 @@ struct Step2Params {
     // march2_kernel (alb_march.cu): column segments per row, units = nseg * row segments, and the work
     // queue {next unit, warps that have finished}, both zero between launches
     int nseg, nunits;
+    int quota;               // units a warp may take before it retires
     int *queue;
     float tau, inv_tau;
     int div_mode;            // as in StepParams

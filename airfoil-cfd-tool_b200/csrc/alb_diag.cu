@@ -317,6 +317,23 @@ __global__ void frame_finalize_kernel(DiagAcc *d, DiagAcc *published, const MeSt
     }
     if (lane != 0) return;
     *published = m;
+    if (st == nullptr) {
+        // a slab of a decomposed lattice: publish the raw partial reductions of this frame; the host
+        // combines the slabs (max / min / exact integer sums) and applies the page's logic afterwards
+        row[0] = __longlong_as_double((long long)m.smax_bits);
+        row[1] = (double)m.rho_min;
+        row[2] = (double)m.rho_max;
+        row[3] = __longlong_as_double(m.fx);
+        row[4] = __longlong_as_double(m.fy);
+        row[5] = __longlong_as_double((long long)m.surf);
+        row[6] = __longlong_as_double((long long)m.rev);
+        row[7] = __longlong_as_double(me->acc[me_parity][0]);
+        row[8] = __longlong_as_double(me->acc[me_parity][1]);
+        row[9] = U0;
+        row[10] = q;
+        row[11] = (double)do_forces;
+        return;
+    }
     const double cden = __dmul_rn(__dmul_rn(1.5, U0), U0);
     const double smax = __longlong_as_double((long long)m.smax_bits);
     if (smax > 0) st->maxS = smax;

@@ -38,15 +38,34 @@
 
 // Shape knobs: warps per CTA (one CTA per SM; 16 x 128 registers = the whole register file), the
 // tallest row segment the planner may choose, and the fixed cost of starting a unit (pipeline fill)
-// in row-steps.
+// in row-steps.  Short segments win although they recompute two rows each: neighbouring column
+// segments re-read each other's edge columns, and the less two warps can drift apart the more of
+// those re-reads hit L2 (measured at configs[3]: 24 rows 144.1, 32 rows 144.8, 48 rows 142.6, 64 rows
+// 140.8, 96 rows 138.3, 171 rows 135.5 GLUPS).
 #ifndef ALB_MARCH_WARPS
 #define ALB_MARCH_WARPS 16
 #endif
 #ifndef ALB_MARCH_HS_MAX
-#define ALB_MARCH_HS_MAX 256
+#define ALB_MARCH_HS_MAX 32
 #endif
 #ifndef ALB_MARCH_UNIT_OVERHEAD
 #define ALB_MARCH_UNIT_OVERHEAD 3
+#endif
+// how many CTAs an SM works through per pass (1: persistent CTAs that hold their SM until the end)
+#ifndef ALB_MARCH_GENERATIONS
+#define ALB_MARCH_GENERATIONS 6
+#endif
+// L2 eviction hints on the staged loads.  Neighbouring column segments share 8 columns (plus the
+// rest of the 64-byte fetch granule), and the two warps reach a given row at different times: the
+// shared bytes have to survive in L2 until the second warp arrives or they are fetched from HBM
+// twice (ncu, profiles/r2b: 23.1 GB read per pass for 19.3 GB of state).
+//   0 no hints   1 first/last two lanes of a warp evict_last, the rest evict_first   2 only the evict_last part
+#ifndef ALB_MARCH_L2HINT
+#define ALB_MARCH_L2HINT 0
+#endif
+// registers per thread the kernel is compiled for (0: whatever the launch bounds allow)
+#ifndef ALB_MARCH_MAXNREG
+#define ALB_MARCH_MAXNREG 0
 #endif
 
 namespace alb {
@@ -60,8 +79,12 @@ constexpr int M_CARRY = 3 * 128;              // floats of one carried row (f2, 
 constexpr int M_WARP_SMEM = 2 * M_STAGE + 2 * M_CARRY;   // floats of shared memory per warp
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(unsigned dst, const float *src) {
+__device__ __forceinline__ void cp_async16(unsigned dst, const float *src, [[maybe_unused]] unsigned long long policy) {
+#if ALB_MARCH_L2HINT
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(policy) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -76,7 +99,11 @@ __device__ __forceinline__ float4 shr(const float4 &v) {   // populations arrivi
 }
 
 template <bool DIAG, int DM>
+#if ALB_MARCH_MAXNREG
+__global__ void __maxnreg__(ALB_MARCH_MAXNREG)
+#else
 __global__ void __launch_bounds__(M_WARPS * 32, 1)
+#endif
 march2_kernel(const __grid_constant__ Step2Params p) {
     extern __shared__ float4 smem4[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -89,16 +116,33 @@ march2_kernel(const __grid_constant__ Step2Params p) {
     [[maybe_unused]] const float *const src = p.src;
     [[maybe_unused]] float *const dst_base = p.dst;
     const bool own = lane >= 1 && lane <= 30;
+    unsigned long long policy = 0;
+#if ALB_MARCH_L2HINT
+    {
+        unsigned long long keep, stream;
+        asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+#if ALB_MARCH_L2HINT == 1
+        asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
+#else
+        asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(stream));
+#endif
+        policy = (lane < 2 || lane >= 30) ? keep : stream;
+    }
+#endif
     const int total_warps = gridDim.x * M_WARPS;
     unsigned hits = 0;
     [[maybe_unused]] DiagLocal dl;
 
-    int unit = blockIdx.x * M_WARPS + warp;     // first unit: static; afterwards from the queue
-    for (;;) {
+    // units come from the queue; a warp takes at most p.quota of them, so that CTAs retire while the
+    // pass is under way and the list-driven passes on the (high-priority) aux stream find SMs
+    int unit = 0;
+    if (lane == 0) unit = atomicAdd(p.queue, 1);
+    unit = __shfl_sync(FULL, unit, 0);
+    for (int taken = 1;; taken++) {
         if (unit >= p.nunits) break;
         // fetch the id of the unit after this one now: the atomic's latency hides behind the work
-        int next_unit = 0;
-        if (lane == 0) next_unit = total_warps + atomicAdd(p.queue, 1);
+        int next_unit = p.nunits;
+        if (lane == 0 && taken < p.quota) next_unit = atomicAdd(p.queue, 1);
         const int rowseg = unit / p.nseg, s = unit - rowseg * p.nseg;
         const int y0 = 2 + rowseg * p.hs;                // owned output rows [y0, y1)
         const int y1 = min(y0 + p.hs, p.nyl);
@@ -115,7 +159,7 @@ march2_kernel(const __grid_constant__ Step2Params p) {
             for (int i = 0; i < 9; i++) {
                 const float *gi = g + i * plane - (ptrdiff_t)ey[i] * pitch;
                 ALB_CHECK_SRC(gi, 4);
-                cp_async16(d + i * 512u, gi);
+                cp_async16(d + i * 512u, gi, policy);
             }
         };
         int a = y0 - 1;
@@ -263,6 +307,16 @@ void march_plan(Step2Params &p, int nsm) {
     }
     p.hs = best;
     p.nunits = p.ntiles = p.nseg * ((rows + best - 1) / best);
+    // CTA generations: about ALB_MARCH_GENERATIONS retirements per SM and pass
+    static int gen_env = -1;
+    if (gen_env < 0) {
+        const char *e = getenv("AEROLAB_LBM_S2_GENERATIONS");
+        gen_env = e ? atoi(e) : ALB_MARCH_GENERATIONS;
+        if (gen_env < 1) gen_env = 1;
+    }
+    const long long per_warp = (p.nunits + warps - 1) / warps;
+    p.quota = (int)((per_warp + gen_env - 1) / gen_env);
+    if (p.quota < 1) p.quota = 1;
 }
 
 int march_out_width() { return M_OUT; }
@@ -283,9 +337,11 @@ cudaError_t launch_march2_t(const Step2Params &p, int grid, cudaStream_t s) {
 
 cudaError_t launch_march2(const Step2Params &p, int nsm, cudaStream_t s) {
     if (p.nunits <= 0) return cudaSuccess;
-    // persistent: one CTA per SM, but never more warps than units
-    int grid = (p.nunits + M_WARPS - 1) / M_WARPS;
-    if (grid > nsm) grid = nsm;
+    // one CTA per SM at a time; every warp takes at most p.quota units from the queue, so the grid
+    // must offer at least nunits / quota warps (and never fewer CTAs than SMs that can be filled)
+    const long long need_warps = ((long long)p.nunits + p.quota - 1) / p.quota;
+    int grid = (int)((need_warps + M_WARPS - 1) / M_WARPS);
+    (void)nsm;
     if (p.div_mode == DM_FAST3) return p.diag ? launch_march2_t<true, DM_FAST3>(p, grid, s) : launch_march2_t<false, DM_FAST3>(p, grid, s);
     return p.diag ? launch_march2_t<true, DM_IEEE>(p, grid, s) : launch_march2_t<false, DM_IEEE>(p, grid, s);
 }

@@ -55,15 +55,19 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def committed_traffic(workload, doubles=False):
-    """DRAM bytes per launch of the dominant step kernel from the committed ncu capture, if any.
-    Single steps: one launch = one step.  Double steps: one launch of step2_kernel = two steps."""
+def committed_traffic(workload, kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from
+    the committed `ncu --set full` capture of this workload on ONE GPU, or None.  The entry names the
+    kernel it was measured on; a line for another kernel (or another N) gets no traffic figure."""
     path = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     try:
         with open(path) as fh:
-            return json.load(fh).get(workload + (":step2" if doubles else ""))
+            e = json.load(fh).get(workload)
+        if e and e.get("kernel") == kernel:
+            return e
     except Exception:
-        return None
+        pass
+    return None
 
 
 class ClockSampler:
@@ -129,8 +133,9 @@ def slab_rows(ny, world, rank):
     return y0, base + (1 if rank < rem else 0)
 
 
-def cpu_sample(nx, ny, shape, alpha, band_rows, steps, warmup, max_seconds=None):
-    """Time the oracle (OpenMP, all host threads) on a band of rows centred on the airfoil."""
+def cpu_sample(nx, ny, shape, alpha, band_rows, steps, warmup, max_seconds=None, threads=None):
+    """Time the oracle (OpenMP, all host threads unless `threads` says otherwise) on a band of rows
+    centred on the airfoil."""
     import numpy as np
     from oracle import geometry as ogeo
     from oracle import lbm as olbm
@@ -145,7 +150,7 @@ def cpu_sample(nx, ny, shape, alpha, band_rows, steps, warmup, max_seconds=None)
     mask[:, :] = sub
     F, rho, ux, uy = olbm.init(nx, nrows, U0)
     G = F.copy()
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     olbm.set_threads(cores)
     cells = nx * band
     for _ in range(warmup):
@@ -296,16 +301,24 @@ def main():
     launch_ms = ms_dev / args.steps * steps_per_launch
     alg_bytes = BYTES_PER_LUP * cells_local * steps_per_launch
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-    traffic = committed_traffic(args.workload, doubles)
+    kernel = "alb::march2_kernel" if doubles else "alb::step_kernel<MODE_STEP>"
+    # the ncu capture is of the one-GPU run of this workload: per-rank launches of an N-GPU run
+    # process 1/N of the cells and get no traffic figure
+    cap = committed_traffic(args.workload, kernel) if world == 1 and args.scaling == "strong" else None
+    traffic = cap["dram_bytes_per_launch"] if cap else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "copy_gbs_measured_in_this_run": copy_here,
-                "kernel": ("alb::step2_kernel (two steps per launch; + list-driven step_kernel passes for "
-                           "border/body/slab-edge tasks on a second stream)") if doubles else "alb::step_kernel<MODE_STEP>",
+                "traffic": traffic, "traffic_source": cap.get("source") if cap else None,
+                "peak_source": peak_src, "copy_gbs_measured_in_this_run": copy_here,
+                "kernel": kernel + (" (two steps per launch: reads the state once, writes it once; border/body/"
+                                    "slab-edge tasks go through list-driven step_kernel passes on a second stream)"
+                                    if doubles else ""),
                 "steps_per_launch": steps_per_launch,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "launch_ms": launch_ms,
-                "dram_frac": (traffic / (launch_ms * 1e-3) / 1e9 / peak) if (traffic and world == 1) else None}
+                # what bounds a kernel that performs TWO updates per cell and pass over HBM: 36 B per update
+                "bound_bytes_per_lup": BYTES_PER_LUP / steps_per_launch,
+                "frac_of_own_bound": achieved / steps_per_launch / peak,
+                "dram_frac": (traffic / (launch_ms * 1e-3) / 1e9 / peak) if traffic else None}
 
     # ---- end to end through the public API (`e2e`) ----------------------------
     e2e = None
@@ -313,13 +326,27 @@ def main():
         e2e = dist_mod.bench_e2e(tun, comm, args.steps, cells_global)
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------
+    # the oracle on all host threads on a band of this workload (the figure next to
+    # `value`), the same band on ONE thread, and configs[0] itself (320x160, 1,000 steps)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         band = 256 if nx * 256 <= 16 * 1024 * 1024 else max(16, (16 * 1024 * 1024) // nx)
-        r = cpu_sample(nx, ny, shape, alpha, min(band, ny), steps=1000, warmup=2, max_seconds=12.0)
-        cpu = {"value": r["glups"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        r = cpu_sample(nx, ny, shape, alpha, min(band, ny), steps=1000, warmup=2, max_seconds=10.0)
+        r1 = cpu_sample(nx, ny, shape, alpha, min(band, ny), steps=1000, warmup=1, max_seconds=6.0, threads=1)
+        c0nx, c0ny, c0shape, c0alpha = WORKLOADS["configs[1]"]
+        c0 = cpu_sample(c0nx, c0ny, c0shape, c0alpha, c0ny, steps=1000, warmup=2, max_seconds=20.0)
+        cpu = {"value": r["glups"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "one_thread": {"value": r1["glups"], "unit": UNIT, "cores": 1, "sample": r1["sample"]},
+               "configs[0]": {"value": c0["glups"], "unit": UNIT, "cores": c0["cores"], "seconds": c0["seconds"],
+                              "steps": c0["steps"], "sample": c0["sample"]}}
+
+    # ---- the same loop with the frame's image, as the page draws it (`e2e_fields`) ----------
+    e2e_fields = None
+    if not args.no_e2e and world == 1:
+        e2e_fields = dist_mod.bench_e2e_fields(tun, cells_global)
 
     forces = tun.forces()
+    state_hash = tun.state_hash()
     if rank == 0:
         line = {
             "metric": METRIC, "value": glups, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -332,14 +359,17 @@ def main():
                              % (36.0 * cells_local / 1e9),
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_fields": e2e_fields,
             # counted by the library (alb_launch_count): kernels launched on this rank in the timed
             # region, kernels inside replayed CUDA graphs included
             "gpu_launches": int(launches),
             "clocks": clocks,
             "check": {"CL_me": forces.get("CL_me"), "CD_me": forces.get("CD_me"),
                       "CL_pressure_raw": forces.get("CL_raw"), "CD_pressure_raw": forces.get("CD_raw"),
-                      "total_steps": tun.steps},
+                      "total_steps": tun.steps,
+                      # position-dependent checksum of the population bit patterns (alb_state_hash), slabs
+                      # added modulo 2^64: identical at every N for the same number of steps
+                      "state_hash": ["%016x" % int(v) for v in state_hash]},
         }
         print(json.dumps(line), flush=True)
     tun.close()

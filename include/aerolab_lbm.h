@@ -80,7 +80,12 @@ int alb_get_dims(const alb_handle *h, int *nx, int *ny_global, int *y0, int *ny_
 int alb_set_params(alb_handle *h, double u0, double tau);
 int alb_get_params(const alb_handle *h, double *u0, double *tau);
 /* initSim(u0), HTML:492-500: every cell (solids and borders too) := fp32 of
- * the float64 equilibrium at rho = 1, u = (u0, 0).  Also sets U0 = u0. */
+ * the float64 equilibrium at rho = 1, u = (u0, 0).  Also sets U0 = u0.
+ * On a slab with connected neighbours the ghost rows are refilled too, while a
+ * neighbour that is one step behind may still be pushing halo rows into them:
+ * call it only when ALL slabs of the lattice have been synchronised (alb_sync on
+ * each, then a barrier between their owners) and let no slab step before all have
+ * been reset (DistributedTunnel.reset and LocalMultiTunnel.reset do exactly that). */
 int alb_reset(alb_handle *h, double u0);
 
 /* ---- geometry: replaces rotate/panelise/rasterMask/applyGeometry,
@@ -196,7 +201,16 @@ int alb_stall_state(const alb_handle *h, int *state, int *sep_pct);
  * nframes x 12 doubles = {CL, CD (EMA; NaN before the first force frame),
  * sep_frac, CL_raw, CD_raw, surf, rev (NaN on frames without forces), maxS,
  * cpMin, cpMax, CL_me, CD_me (momentum exchange of the frame's last step)}.
- * Whole-lattice handles only.  Synchronises at the end. */
+ * Synchronises at the end.
+ * On a slab of a decomposed lattice (alb_create_slab / alb_create_multi) the loop runs
+ * the same way, but a slab cannot know the other slabs' extrema and face sums: its
+ * records are the frame's RAW PARTIAL reductions, {max s (double), min rho, max rho over
+ * the Cp window (+inf / -inf: none), then five 64-bit integers stored bit for bit in the
+ * double slots: pressure-face sums fx, fy (2^-40 fixed point, of rho, before the /3),
+ * surf, rev, momentum-exchange fx, fy (2^-40), then U0, q = 0.5 U0^2 CHORD_L, and 1.0 on
+ * force frames}.  The caller takes max / min / integer sums over the slabs and applies
+ * HTML:611-613, 672-699 (aerolab_lbm.distributed.DistributedTunnel.run_frames does);
+ * the sticky state of the slab handle itself is left alone. */
 #define ALB_FRAME_ROW 12
 int alb_run_frames(alb_handle *h, int nframes, int steps_per_frame, int forces_every,
                    const double *controls, double *series);

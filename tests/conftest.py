@@ -5,6 +5,11 @@ import sys
 import numpy as np
 import pytest
 
+# In-process slabs that share ONE device wait for each other inside kernels; streams that alias onto
+# the same hardware queue could then block each other (one process per GPU, the product layout, has
+# no such coupling).  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG_DIR = os.path.join(ROOT, "airfoil-cfd-tool_b200")
 for p in (ROOT, PKG_DIR):

@@ -21,6 +21,7 @@ def client(monkeypatch):
     from aerolab_lbm import dat, server
     # stand-alone deployment: plain reader instead of the host application's parser
     monkeypatch.setattr(server, "resolve_parser", lambda p: dat.read_plain_dat)
+    monkeypatch.setattr(server, "_limiter", server._RateLimiter(10 ** 6, 60.0))   # see test_rate_limit
     app = FastAPI()
     app.include_router(server.router)
     return TestClient(app)
@@ -42,6 +43,32 @@ def test_validation_400(client, data, frag):
 def test_rejects_non_dat_and_oversize(client):
     assert post(client, name="foil.txt").status_code == 400
     assert post(client, content=b"1 0\n" * 400000).status_code == 400
+
+
+def test_rate_limit_like_upload_airfoil(client, monkeypatch):
+    """main.py:543-545 limits /upload_airfoil/ to 5 requests per minute and client; so does this route."""
+    from aerolab_lbm import server
+    monkeypatch.setattr(server, "_limiter", server._RateLimiter(server.RATE_LIMIT, server.RATE_WINDOW_S))
+    codes = [post(client, {"alpha": "45"}).status_code for _ in range(server.RATE_LIMIT + 2)]
+    assert codes == [400] * server.RATE_LIMIT + [429, 429]
+    lim = server._RateLimiter(2, 10.0)
+    assert [lim.check("a", now=t) for t in (0.0, 1.0, 2.0, 10.5, 11.5, 12.0)] == [True, True, False, True, True, False]
+    assert lim.check("b", now=2.0)
+
+
+def test_too_few_points_and_work_cap(client):
+    r = post(client, content=b"1 0\n0.5 0.05\n0 0\n0.5 -0.05\n1 0\n")
+    assert r.status_code == 400 and ("Too few points" in r.json()["detail"] or "fewer than 10" in r.json()["detail"])
+    r = post(client, {"nx": "8192", "ny": "8192", "steps": "200000"})
+    assert r.status_code == 400 and "cell updates" in r.json()["detail"]
+
+
+def test_nan_becomes_null():
+    from aerolab_lbm import server
+    import json as _json
+    out = server._json_safe({"a": float("nan"), "b": [1.0, float("inf")], "c": {"d": np.float64("nan")}, "e": 2})
+    assert out == {"a": None, "b": [1.0, None], "c": {"d": None}, "e": 2}
+    _json.dumps(out, allow_nan=False)
 
 
 def test_health_route(client):
