@@ -36,7 +36,7 @@ EXPORTS = [
     "alb_step", "alb_sync", "alb_step_count", "alb_last_step_ms",
     "alb_get_populations", "alb_get_population_rows", "alb_state_hash", "alb_set_populations", "alb_get_macro", "alb_set_macro", "alb_total_mass",
     "alb_update_stats", "alb_stats_partial", "alb_set_stats", "alb_get_stats",
-    "alb_get_field", "alb_get_rgba",
+    "alb_get_field", "alb_get_rgba", "alb_get_macro_edges", "alb_set_macro_ghosts",
     "alb_compute_forces", "alb_forces_partial", "alb_reset_force_emas",
     "alb_get_me_history", "alb_get_me_forces", "alb_clamp_hits",
     "alb_reynolds", "alb_stall_state",
@@ -109,6 +109,8 @@ def lib():
     L.alb_get_stats.argtypes = [H, vp]
     L.alb_get_field.argtypes = [H, C.c_int, vp]
     L.alb_get_rgba.argtypes = [H, C.c_int, vp]
+    L.alb_get_macro_edges.argtypes = [H, vp, vp]
+    L.alb_set_macro_ghosts.argtypes = [H, vp, vp]
     L.alb_compute_forces.argtypes = [H, vp]
     L.alb_forces_partial.argtypes = [H, vp]
     L.alb_reset_force_emas.argtypes = [H]

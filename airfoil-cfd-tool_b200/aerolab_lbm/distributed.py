@@ -459,6 +459,41 @@ class DistributedTunnel:
         self.t.set_stats(self.max_s, self.cp_min, self.cp_max)
         return series
 
+    # -- field modes (HTML:395-422, 527-545) on the decomposed lattice ---------------------------
+    def _exchange_macro_edges(self):
+        """The vorticity taps of a slab's first / last row reach into the neighbouring slab: every
+        rank publishes ux, uy of its two edge rows (2 x 2 x nx floats) and installs its neighbours'."""
+        lo, hi = self.t.macro_edges()
+        edges = self.comm.allgather_array(np.stack([lo, hi]).astype(np.float64))     # (world, 2, 2, nx)
+        r, w = self.comm.rank, self.comm.world
+        below = edges[r - 1, 1].astype(np.float32) if r > 0 else None
+        above = edges[r + 1, 0].astype(np.float32) if r < w - 1 else None
+        self.t.set_macro_ghosts(below, above)
+
+    def field(self, mode="speed") -> np.ndarray:
+        """This rank's rows of the render shader's scalar (NaN in solids); uses the lattice-wide sticky
+        autoscale values of the last ``update_stats`` / ``run_frames``."""
+        from .tunnel import FIELD_MODES
+        if FIELD_MODES[mode] == 2 and self.comm.world > 1:
+            self._exchange_macro_edges()
+        return self.t.field(mode)
+
+    def rgba(self, mode="speed") -> np.ndarray:
+        """This rank's rows of the colour-mapped field (page palettes, HTML:371-393), (ny_local, nx, 4)."""
+        from .tunnel import FIELD_MODES
+        if FIELD_MODES[mode] == 2 and self.comm.world > 1:
+            self._exchange_macro_edges()
+        return self.t.rgba(mode)
+
+    def stall_state(self) -> str:
+        """Text of the separation card (HTML:869-884) from the lattice-wide separation fraction."""
+        x = self.sep_frac * 100
+        pct = math.floor(x) + (1 if x - math.floor(x) >= 0.5 else 0)      # Math.round, HTML:869
+        return "Attached" if pct < 5 else (f"{pct}% sep" if pct < 25 else f"STALL \u2248 {pct}% sep")
+
+    def reynolds(self) -> float:
+        return self.t.reynolds()
+
     def frame(self) -> dict:
         """The reference frame (HTML:902-930) across slabs: 4 steps, autoscale, forces every 3rd."""
         self.step(4)
@@ -476,6 +511,10 @@ class DistributedTunnel:
         if what == "populations":
             p = self.comm.gather_arrays(self.t.populations())
             return None if p is None else np.concatenate(p, axis=1)
+        if what.startswith("field:") or what.startswith("rgba:"):
+            kind, mode = what.split(":")
+            p = self.comm.gather_arrays(self.field(mode) if kind == "field" else self.rgba(mode))
+            return None if p is None else np.concatenate(p, axis=0)
         if what == "mask":
             p = self.comm.gather_arrays(self.t.mask())
             return None if p is None else np.concatenate(p, axis=0)

@@ -52,6 +52,25 @@ def state_hash_numpy(f: np.ndarray, nx_global: int, gy0: int = 0) -> np.ndarray:
     return out
 
 
+def write_png(path: str, rgba: np.ndarray) -> str:
+    """RGBA8 image of shape (rows, columns, 4), row 0 = bottom of the lattice, as a PNG file.
+    Pure-Python encoder (zlib), no imaging dependency."""
+    import struct
+    import zlib
+    img = np.ascontiguousarray(rgba[::-1])               # PNG rows run top to bottom
+    h, w = img.shape[:2]
+    raw = b"".join(b"\x00" + img[y].tobytes() for y in range(h))
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+
+    png = (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0))
+           + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+    with open(path, "wb") as fh:
+        fh.write(png)
+    return path
+
+
 class WindTunnel:
     """One D2Q9 lattice on one GPU.
 
@@ -302,6 +321,21 @@ class WindTunnel:
         self._ck(self._lib.alb_get_rgba(self._h, FIELD_MODES[mode], ptr(out)))
         return out
 
+    def macro_edges(self):
+        """(lo, hi): ux, uy of the first and last owned row, shape (2, nx) each -- what the
+        neighbouring slabs need for their vorticity taps (HTML:411-418)."""
+        lo = np.empty((2, self.nx), np.float32)
+        hi = np.empty((2, self.nx), np.float32)
+        self._ck(self._lib.alb_get_macro_edges(self._h, ptr(lo), ptr(hi)))
+        return lo, hi
+
+    def set_macro_ghosts(self, below=None, above=None):
+        """ux, uy of the rows just outside this slab (the neighbours' ``macro_edges``), (2, nx) each."""
+        b = None if below is None else np.ascontiguousarray(below, dtype=np.float32)
+        a = None if above is None else np.ascontiguousarray(above, dtype=np.float32)
+        self._ck(self._lib.alb_set_macro_ghosts(self._h, ptr(b), ptr(a)))
+        return self
+
     def forces(self) -> dict:
         """``computeForces`` (HTML:650-700) plus the momentum-exchange force of the last step."""
         o = np.zeros(10)
@@ -524,21 +558,7 @@ class WindTunnel:
         """Write the colour-mapped field (page palettes, HTML:371-393) as a PNG; row 0 of the
         lattice is the bottom of the image.  Default file name as in the page's export
         (HTML:990-992).  Pure-Python encoder (zlib), no imaging dependency."""
-        import struct
-        import zlib
-        rgba = self.rgba(mode)[::-1]                     # PNG rows run top to bottom
-        h, w = rgba.shape[:2]
-        raw = b"".join(b"\x00" + rgba[y].tobytes() for y in range(h))
-
-        def chunk(tag: bytes, data: bytes) -> bytes:
-            return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
-
-        png = (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0))
-               + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
-        path = path or self.png_name()
-        with open(path, "wb") as fh:
-            fh.write(png)
-        return path
+        return write_png(path or self.png_name(), self.rgba(mode))
 
     def png_name(self) -> str:
         """File name convention of the page's PNG export (HTML:990-992)."""
@@ -638,6 +658,43 @@ class LocalMultiTunnel:
             out.update(CL_me=float(me[1]) / _ffi.ALB_ME_SCALE / q, CD_me=float(me[0]) / _ffi.ALB_ME_SCALE / q)
         return out
 
+    def update_stats(self) -> dict:
+        """``updateFieldsFromMacro`` (HTML:596-614) over all slabs; the lattice-wide sticky values are
+        handed to every slab (they scale its field modes)."""
+        if not hasattr(self, "_sticky"):
+            self._sticky = dict(maxS=0.6, cpMin=-1.0, cpMax=1.0, cl_smooth=0.0, cd_smooth=0.0, sep_frac=0.0,
+                                ema_valid=False)
+        parts = np.array([t.stats_partial() for t in self.slabs])
+        mx, cmin, cmax = parts[:, 0].max(), parts[:, 1].min(), parts[:, 2].max()
+        if mx > 0:
+            self._sticky["maxS"] = float(mx)
+        if np.isfinite(cmin):
+            self._sticky["cpMin"] = float(cmin)
+        if np.isfinite(cmax):
+            self._sticky["cpMax"] = float(cmax)
+        self._push_stats()
+        return {k: self._sticky[k] for k in ("maxS", "cpMin", "cpMax")}
+
+    def _push_stats(self):
+        for t in self.slabs:
+            t.set_stats(self._sticky["maxS"], self._sticky["cpMin"], self._sticky["cpMax"])
+
+    def _exchange_macro_edges(self):
+        edges = [t.macro_edges() for t in self.slabs]
+        for k, t in enumerate(self.slabs):
+            t.set_macro_ghosts(edges[k - 1][1] if k > 0 else None, edges[k + 1][0] if k + 1 < len(self.slabs) else None)
+
+    def field(self, mode="speed") -> np.ndarray:
+        """Scalar of the render shader (HTML:395-420) for the whole lattice, slab by slab."""
+        if FIELD_MODES[mode] == 2:
+            self._exchange_macro_edges()
+        return np.concatenate([t.field(mode) for t in self.slabs], axis=0)
+
+    def rgba(self, mode="speed") -> np.ndarray:
+        if FIELD_MODES[mode] == 2:
+            self._exchange_macro_edges()
+        return np.concatenate([t.rgba(mode) for t in self.slabs], axis=0)
+
     def run_frames(self, nframes: int, controls=None, steps_per_frame: int = STEPS_PER_FRAME,
                    forces_every: int = FORCES_EVERY_FRAMES) -> dict:
         """``WindTunnel.run_frames`` on the decomposed lattice: every slab runs its frame loop on its
@@ -650,7 +707,9 @@ class LocalMultiTunnel:
         if not hasattr(self, "_sticky"):
             self._sticky = dict(maxS=0.6, cpMin=-1.0, cpMax=1.0, cl_smooth=0.0, cd_smooth=0.0, sep_frac=0.0,
                                 ema_valid=False)      # HTML:593, 641
-        return combine_frame_partials(parts, self._sticky)
+        series = combine_frame_partials(parts, self._sticky)
+        self._push_stats()
+        return series
 
     def close(self):
         # quiesce every slab before any block is freed: neighbours store halo rows and flags into it

@@ -24,10 +24,11 @@ constexpr int GRAPH_STEPS = 8;                // steps replayed per CUDA-graph l
 constexpr int DIAG_BLOCKS = 148 * 4;          // fixed reduction grid -> deterministic partials
 constexpr int UNIFIED_MAX_TASKS = 148 * 2 * 8;   // one wave of the unified kernel (2 CTAs/SM x 8 tasks)
 constexpr long long WAIT_TIMEOUT_NS = 20LL * 1000 * 1000 * 1000;
-// Lattices at least this wide and this large advance two steps per pass (see step_batch).  Measured:
-// 32768x16384 130 vs 94 GLUPS; 4096x2048 (7 strips, one wave of tiles) 83 vs 85, 2048x1024 33 vs 74 -> single steps.
-constexpr int DOUBLE_MIN_NX = 8192;
-constexpr long long DOUBLE_MIN_CELLS = 32LL << 20;
+// Lattices at least this wide and this large advance two steps per pass (see step_batch).  Measured
+// with march2_kernel: 32768x16384 141-145 vs 94 GLUPS; 4096x2048 112 vs 85; 2048x1024 71 vs 74 (one eighth
+// of its tasks sit in the first / last task column and go through the two list-driven passes) -> single steps.
+constexpr int DOUBLE_MIN_NX = 4096;
+constexpr long long DOUBLE_MIN_CELLS = 8LL << 20;
 
 thread_local std::string g_create_error;
 
@@ -60,6 +61,7 @@ struct alb_handle {
     int parity = 0;               // parity of the NEXT step (momentum-exchange slot); == cur until a double step ran
     float *rho = nullptr, *ux = nullptr, *uy = nullptr;
     bool macro_valid = true;
+    bool ghost_macro_valid = false;   // ux/uy ghost rows hold the neighbours' edge rows of the current state
     bool diag_valid = false;      // h_diag holds the fused statistics/forces of the current state
     DiagAcc *d_diag = nullptr;
     DiagAcc *d_diag_pub = nullptr;    // copy published by the frame-finalize kernel
@@ -415,6 +417,7 @@ int do_reset(alb_handle *h, double u0) {
     h->steps = 0;
     h->frame_counter = 0;
     h->macro_valid = true;
+    h->ghost_macro_valid = false;
     h->diag_valid = false;
     return ALB_OK;
 }
@@ -1070,6 +1073,7 @@ static int step_batch(alb_handle *h, int nsteps) {
     h->sync_steps += nsteps;
     CK(cudaGetLastError());
     h->macro_valid = false;
+    h->ghost_macro_valid = false;
     h->diag_valid = true;       // the last step reduced the new state's statistics and face sums
     return ALB_OK;
 }
@@ -1264,6 +1268,7 @@ int alb_set_macro(alb_handle *h, const float *rho, const float *ux, const float 
                                  sizeof(float) * h->nx, h->nyl, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->macro_valid = true;
+    h->ghost_macro_valid = false;
     h->diag_valid = false;
     return ALB_OK;
 }
@@ -1375,15 +1380,18 @@ int alb_get_stats(const alb_handle *h, double *stats3) {
 static int render_common(alb_handle *h, int mode, float *t_out, uint8_t *rgba) {
     NEED(h);
     ARG(mode >= 0 && mode <= 2, "field mode must be 0 (speed), 1 (Cp) or 2 (vorticity)");
-    if (!h->whole()) return h->fail(ALB_ERR_STATE, "field rendering needs a whole-lattice handle");
+    const int lo_ghost = h->y0 > 0 ? 1 : 0, hi_ghost = h->y0 + h->nyl < h->ny_global ? 1 : 0;
+    if (mode == ALB_FIELD_VORT && (lo_ghost || hi_ghost) && !h->ghost_macro_valid)
+        return h->fail(ALB_ERR_STATE, "vorticity on a slab needs the neighbours' edge rows: alb_get_macro_edges on "
+                                      "every slab, then alb_set_macro_ghosts, after the last step");
     int r = ensure_macro(h);
     if (r) return r;
     if ((r = ensure_tmp(h, 0))) return r;
     if ((r = ensure_tmp(h, 1))) return r;
     float *dt = h->d_tmp[0];
     uint8_t *drgba = reinterpret_cast<uint8_t *>(h->d_tmp[1]);
-    CK(launch_render(h->mask, h->rho, h->ux, h->uy, h->pitch, h->nx, h->nyl, mode, h->u0f, (float)h->maxS,
-                     (float)h->cpMin, (float)h->cpMax, 0.06f, dt, rgba ? drgba : nullptr, h->stream));
+    CK(launch_render(h->mask, h->rho, h->ux, h->uy, h->pitch, h->nx, h->nyl, lo_ghost, hi_ghost, mode, h->u0f,
+                     (float)h->maxS, (float)h->cpMin, (float)h->cpMax, 0.06f, dt, rgba ? drgba : nullptr, h->stream));
     const size_t n = (size_t)h->nx * h->nyl;
     if (t_out) CK(cudaMemcpyAsync(t_out, dt, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
     if (rgba) CK(cudaMemcpyAsync(rgba, drgba, 4 * n, cudaMemcpyDeviceToHost, h->stream));
@@ -1399,6 +1407,38 @@ int alb_get_field(alb_handle *h, int mode, float *t_out) {
 int alb_get_rgba(alb_handle *h, int mode, uint8_t *rgba) {
     if (h && !rgba) return h->fail(ALB_ERR_INVALID, "alb_get_rgba: output is NULL");
     return render_common(h, mode, nullptr, rgba);
+}
+
+int alb_get_macro_edges(alb_handle *h, float *lo2, float *hi2) {
+    NEED(h);
+    ARG(lo2 || hi2, "alb_get_macro_edges: both outputs are NULL");
+    int r = ensure_macro(h);
+    if (r) return r;
+    const size_t rowb = sizeof(float) * h->nx;
+    const float *srcs[2] = {h->ux, h->uy};
+    for (int k = 0; k < 2; k++) {
+        if (lo2) CK(cudaMemcpyAsync(lo2 + (size_t)k * h->nx, srcs[k] + (size_t)1 * h->pitch, rowb, cudaMemcpyDeviceToHost, h->stream));
+        if (hi2) CK(cudaMemcpyAsync(hi2 + (size_t)k * h->nx, srcs[k] + (size_t)h->nyl * h->pitch, rowb, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return check_wait_error(h);
+}
+
+int alb_set_macro_ghosts(alb_handle *h, const float *below2, const float *above2) {
+    NEED(h);
+    int r = ensure_macro(h);       // the ghost rows belong to the macroscopic fields of the CURRENT state
+    if (r) return r;
+    const size_t rowb = sizeof(float) * h->nx;
+    float *dsts[2] = {h->ux, h->uy};
+    for (int k = 0; k < 2; k++) {
+        if (below2) CK(cudaMemcpyAsync(dsts[k], below2 + (size_t)k * h->nx, rowb, cudaMemcpyHostToDevice, h->stream));
+        if (above2) CK(cudaMemcpyAsync(dsts[k] + (size_t)(h->nyl + 1) * h->pitch, above2 + (size_t)k * h->nx, rowb,
+                                       cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));    // caller memory
+    const bool need_lo = h->y0 > 0, need_hi = h->y0 + h->nyl < h->ny_global;
+    h->ghost_macro_valid = (!need_lo || below2) && (!need_hi || above2);
+    return ALB_OK;
 }
 
 int alb_forces_partial(alb_handle *h, double *out4) {
@@ -1518,7 +1558,8 @@ int alb_reynolds(const alb_handle *h, double *re) {
 
 int alb_stall_state(const alb_handle *h, int *state, int *sep_pct) {
     if (!h) return ALB_ERR_INVALID;
-    const int pct = (int)floor(h->sep_frac * 100 + 0.5);   // Math.round, HTML:869
+    const double x100 = h->sep_frac * 100, fl = floor(x100);
+    const int pct = (int)(fl + (x100 - fl >= 0.5 ? 1.0 : 0.0));   // Math.round (ties up; x - floor(x) is exact), HTML:869
     if (sep_pct) *sep_pct = pct;
     if (state) *state = pct < 5 ? 0 : (pct < 25 ? 1 : 2);  // HTML:872-884
     return ALB_OK;

@@ -220,8 +220,8 @@ cudaError_t launch_forces(const uint8_t *mask, const float *rho, const float *ux
                           int ny_global, int gy_first, int nyl, double *d_part, int nblocks,
                           cudaStream_t s);
 cudaError_t launch_render(const uint8_t *mask, const float *rho, const float *ux, const float *uy,
-                          int pitch, int nx, int ny, int mode, float u0, float maxS, float cpMin,
-                          float cpMax, float vortScale, float *t_out, uint8_t *rgba, cudaStream_t s);
+                          int pitch, int nx, int ny, int lo_ghost, int hi_ghost, int mode, float u0, float maxS,
+                          float cpMin, float cpMax, float vortScale, float *t_out, uint8_t *rgba, cudaStream_t s);
 cudaError_t launch_mass(const float *f, size_t plane, int pitch, int nx, int nyl, double *d_part,
                         int nblocks, cudaStream_t s);
 cudaError_t launch_state_hash(const float *f, size_t plane, int pitch, int nx, int nyl, int gy0,

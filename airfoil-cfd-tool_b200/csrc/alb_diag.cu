@@ -211,11 +211,13 @@ __device__ __forceinline__ void palette(const float (*C)[3], int nseg, float t, 
     for (int k = 0; k < 3; k++) rgb[k] = mixf(C[i][k] / 255.0f, C[i + 1][k] / 255.0f, u);
 }
 
-// HTML:395-422.  Whole lattice only (ghost rows are not valid macro data).
+// HTML:395-422.  ny = rows of this slab.  lo_ghost / hi_ghost: the row below the first / above the
+// last owned row belongs to a neighbouring slab and its ux, uy sit in the ghost rows of the arrays
+// (alb_set_macro_ghosts); otherwise the vorticity taps clamp to the edge like the page's textures.
 __global__ void render_kernel(const uint8_t *__restrict__ mask, const float *__restrict__ rho,
                               const float *__restrict__ ux, const float *__restrict__ uy, int pitch,
-                              int nx, int ny, int mode, float U0, float maxS, float cpMin, float cpMax,
-                              float vortScale, float *t_out, uint8_t *rgba) {
+                              int nx, int ny, int lo_ghost, int hi_ghost, int mode, float U0, float maxS, float cpMin,
+                              float cpMax, float vortScale, float *t_out, uint8_t *rgba) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= nx || y >= ny) return;
@@ -234,7 +236,8 @@ __global__ void render_kernel(const uint8_t *__restrict__ mask, const float *__r
         } else {
             // CLAMP_TO_EDGE neighbour taps (HTML:443-444, 411-414)
             const int xr = min(x + 1, nx - 1), xl = max(x - 1, 0);
-            const int yu = min(y + 1, ny - 1), yd = max(y - 1, 0);
+            const int yu = (y == ny - 1 && hi_ghost) ? ny : min(y + 1, ny - 1);
+            const int yd = (y == 0 && lo_ghost) ? -1 : max(y - 1, 0);
             const float dvydx = (uy[(size_t)(y + 1) * pitch + xr] - uy[(size_t)(y + 1) * pitch + xl]) * 0.5f;
             const float duxdy = (ux[(size_t)(yu + 1) * pitch + x] - ux[(size_t)(yd + 1) * pitch + x]) * 0.5f;
             const float vort = dvydx - duxdy;
@@ -402,11 +405,11 @@ cudaError_t launch_forces(const uint8_t *mask, const float *rho, const float *ux
 }
 
 cudaError_t launch_render(const uint8_t *mask, const float *rho, const float *ux, const float *uy,
-                          int pitch, int nx, int ny, int mode, float u0, float maxS, float cpMin,
-                          float cpMax, float vortScale, float *t_out, uint8_t *rgba, cudaStream_t s) {
+                          int pitch, int nx, int ny, int lo_ghost, int hi_ghost, int mode, float u0, float maxS,
+                          float cpMin, float cpMax, float vortScale, float *t_out, uint8_t *rgba, cudaStream_t s) {
     dim3 grid((nx + 255) / 256, ny);
-    render_kernel<<<grid, 256, 0, s>>>(mask, rho, ux, uy, pitch, nx, ny, mode, u0, maxS, cpMin, cpMax,
-                                       vortScale, t_out, rgba);
+    render_kernel<<<grid, 256, 0, s>>>(mask, rho, ux, uy, pitch, nx, ny, lo_ghost, hi_ghost, mode, u0, maxS, cpMin,
+                                       cpMax, vortScale, t_out, rgba);
     return cudaGetLastError();
 }
 

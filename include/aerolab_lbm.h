@@ -156,8 +156,19 @@ int alb_get_stats(const alb_handle *h, double *stats3);
 
 /* RENDER_FS_SRC.main, HTML:395-420: the scalar t that the palette is indexed
  * with (fp32, NaN in solids), using the sticky stats above and VORT_SCALE =
- * 0.06 (HTML:528).  Whole-lattice handles only (vorticity needs neighbours). */
-int alb_get_field(alb_handle *h, int mode, float *t_out /* ny*nx */);
+ * 0.06 (HTML:528).  On a slab the output holds the slab's ny_local rows.  Speed and Cp
+ * are cell-local; the vorticity taps of the first / last owned row reach into the
+ * neighbouring slab (HTML:411-418; CLAMP_TO_EDGE only at the lattice border), so on a
+ * slab mode 2 needs alb_set_macro_ghosts() after the last step, and the sticky stats
+ * must have been set to the lattice-wide values (alb_set_stats). */
+int alb_get_field(alb_handle *h, int mode, float *t_out /* ny_local*nx */);
+/* ux, uy of the first (lo2) and last (hi2) owned row of the current state, 2*nx floats
+ * each (nullable): what the neighbouring slabs need for their vorticity taps. */
+int alb_get_macro_edges(alb_handle *h, float *lo2, float *hi2);
+/* ux, uy of the row below the first owned row (below2 = the lower neighbour's hi2) and of
+ * the row above the last one (above2 = the upper neighbour's lo2), 2*nx floats each; NULL
+ * where the slab touches the lattice border.  Valid until the next step. */
+int alb_set_macro_ghosts(alb_handle *h, const float *below2, const float *above2);
 /* Same, passed through the reference palettes (HTML:371-393) to RGBA8. */
 int alb_get_rgba(alb_handle *h, int mode, uint8_t *rgba /* ny*nx*4 */);
 
@@ -273,8 +284,8 @@ int alb_set_external_halo(alb_handle *h, int on);
 /* Two LBM steps per pass over HBM (temporal blocking): the
  * deep interior of the lattice is advanced by a fused two-step kernel, everything
  * near borders, the body and slab edges by two list-driven single-step passes.
- * Bit-identical to single steps.  mode: -1 automatic (lattices at least 8192 wide
- * with 32 Mi cells or more),
+ * Bit-identical to single steps.  mode: -1 automatic (lattices at least 4096 wide
+ * with 8 Mi cells or more),
  * 0 never, 1 whenever a batch has three or more steps left.  All slabs of one
  * lattice must use the same mode.  The environment variable AEROLAB_LBM_DOUBLE
  * (0/1) sets the initial mode of new handles. */

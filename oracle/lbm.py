@@ -218,7 +218,8 @@ class OracleTunnel:
 
     def stall_state(self):
         """HTML:869-884."""
-        sep_pct = math.floor(self.sep_frac * 100 + 0.5)    # Math.round
+        x = self.sep_frac * 100
+        sep_pct = math.floor(x) + (1 if x - math.floor(x) >= 0.5 else 0)    # Math.round (ties towards +inf)
         if sep_pct < 5:
             return "Attached", sep_pct
         if sep_pct < 25:

@@ -124,6 +124,11 @@ def run_tunnel(page, nx, ny, u0, tau, mask, frames, steps_per_frame, forces_ever
     return init_vals, series, fields, tex, stats
 
 
+def to_unorm8(col):
+    """RGBA8 default framebuffer (OpenGL ES 3.0, 2.1.6.1): clamp to [0, 1], scale by 255, round to nearest."""
+    return np.floor(np.clip(col, 0, 1).astype(np.float32) * np.float32(255) + np.float32(0.5)).astype(np.uint8)
+
+
 def render(page, nx, ny, u0, mask, texC, stats):
     sh = glslrun.Shader(extract.shader(page, "RENDER_FS_SRC"))
     mask_tex = glslrun.Sampler((mask.astype(np.float32) / np.float32(255.0)).reshape(ny, nx, 1))
@@ -133,8 +138,7 @@ def render(page, nx, ny, u0, mask, texC, stats):
                    fieldMode=mode, U0=f32(u0), maxS=f32(stats[0]), cpMin=f32(stats[1]), cpMax=f32(stats[2]),
                    vortScale=f32(0.06))
         col = glslrun.run_pass(sh, nx, ny, uni)["fragColor"]
-        # RGBA8 default framebuffer: clamp, scale by 255, round to nearest
-        out[mode] = np.floor(np.clip(col, 0, 1).astype(np.float32) * np.float32(255) + np.float32(0.5)).astype(np.uint8)
+        out[mode] = to_unorm8(col)
         print("render mode", mode, flush=True)
     return out
 

@@ -117,7 +117,10 @@ MATH = {
     "PI": math.pi, "cos": math.cos, "sin": math.sin, "sqrt": lambda x: math.sqrt(x) if x >= 0 else math.nan,
     "atan": math.atan, "hypot": math.hypot, "ceil": lambda x: float(math.ceil(x)),
     "floor": lambda x: float(math.floor(x)), "max": lambda *a: float(max(a)), "min": lambda *a: float(min(a)),
-    "abs": abs, "round": lambda x: float(math.floor(x + 0.5)),
+    "abs": abs,
+    # Math.round: nearest integer, ties towards +infinity -- NOT floor(x + 0.5), whose sum rounds up for
+    # 0.49999999999999994 (x - floor(x) is exact)
+    "round": lambda x: float(math.floor(x) + (1.0 if x - math.floor(x) >= 0.5 else 0.0)),
 }
 
 

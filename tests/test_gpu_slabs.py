@@ -157,3 +157,28 @@ def test_state_hash_adds_up_over_slabs(al):
     assert_bitwise(whole.population_rows(40, 5), whole.populations()[:, 40:45], "population_rows")
     multi.close()
     whole.close()
+
+
+@pytest.mark.parametrize("devs", [[0, 0], [0, 0, 0]])
+def test_field_modes_on_slabs_equal_whole_lattice(al, devs):
+    """renderField (HTML:530-545) per slab: speed and Cp are cell-local, the vorticity taps of a
+    slab's first / last row (HTML:411-418) read the neighbour's edge row through the ghost rows."""
+    nx, ny = 640, 301
+    whole = al.WindTunnel(nx, ny, 0)
+    whole.load_shape("naca4412", alpha=12.0)
+    multi = al.LocalMultiTunnel(nx, ny, devs)
+    multi.load_shape("naca4412", alpha=12.0)
+    whole.step(150); multi.step(150)
+    sw, sm = whole.update_stats(), multi.update_stats()
+    assert sw["cpMin"] == sm["cpMin"] and sw["cpMax"] == sm["cpMax"] and sw["maxS"] == pytest.approx(sm["maxS"], rel=1e-14)
+    multi._sticky["maxS"] = sw["maxS"]; multi._push_stats()      # maxS: device hypot vs host combine, 1e-14
+    for mode in ("speed", "cp", "vort"):
+        assert_bitwise(multi.field(mode), whole.field(mode), f"field {mode}")
+        assert np.array_equal(multi.rgba(mode), whole.rgba(mode)), mode
+    # vorticity without the neighbours' rows is refused, not silently clamped
+    multi.step(1)
+    with pytest.raises(al.AerolabLbmError):
+        multi.slabs[0].field("vort")
+    multi.slabs[0].field("speed")
+    multi.close()
+    whole.close()
