@@ -194,6 +194,30 @@ __global__ void signal_kernel(int *peer_a, int *peer_b, int value) {
     __threadfence_system();
 }
 
+// With CUDA's lazy module loading (the default since 12.2) the FIRST launch of a kernel may need the
+// device to go idle.  A slab's wait_kernel spins until a neighbour signals; if the same host thread
+// that was going to step that neighbour is meanwhile stuck in the first launch of some kernel on
+// the waiting device, nothing ever moves (found with in-process slabs on two GPUs: 20 s timeouts
+// whenever a kernel variant had not run on the device before).  So every kernel is loaded when the
+// first handle on a device is created, before anything can spin.
+cudaError_t preload_all_kernels(int device) {
+    static std::mutex mu;
+    static bool done[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    if (device >= 0 && device < 64 && done[device]) return cudaSuccess;
+    cudaFuncAttributes attr;
+    cudaError_t e = cudaFuncGetAttributes(&attr, reinterpret_cast<const void *>(wait_kernel));
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&attr, reinterpret_cast<const void *>(signal_kernel));
+    if (e == cudaSuccess) e = preload_step_kernels();
+    if (e == cudaSuccess) e = preload_march_kernels();
+    if (e == cudaSuccess) e = preload_step2_kernels();
+    if (e == cudaSuccess) e = preload_diag_kernels();
+    if (e == cudaSuccess) e = preload_geometry_kernels();
+    if (e == cudaSuccess) e = preload_particle_kernels();
+    if (e == cudaSuccess && device >= 0 && device < 64) done[device] = true;
+    return e;
+}
+
 void drop_graph(alb_handle *h) {
     if (h->graph) {
         cudaGraphExecDestroy(h->graph);
@@ -572,6 +596,7 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
     int rc = ALB_OK;
     auto body = [&]() -> int {
         CK(cudaSetDevice(device));
+        CK(preload_all_kernels(device));
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -803,6 +828,12 @@ void halo_signal(alb_handle *h, long long steps_done, cudaStream_t st) {
                                    (int)steps_done);
 }
 
+// AEROLAB_LBM_DEFER_SIGNAL=0 (diagnosis only): send the closing signal of a batch at once, as round 1 did
+bool defer_closing_signal() {
+    static const bool on = !(getenv("AEROLAB_LBM_DEFER_SIGNAL") && atoi(getenv("AEROLAB_LBM_DEFER_SIGNAL")) == 0);
+    return on;
+}
+
 // The previous batch's closing signal: from here on the neighbours may overwrite the ghost rows of
 // what was this slab's previous state.
 void flush_pending_signal(alb_handle *h) {
@@ -844,7 +875,7 @@ int issue_step(alb_handle *h, int src_idx, int parity, bool halo, long long sync
         if (p.ngen > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     }
     if (halo) {
-        if (last_of_batch) h->pending_signal = sync_step + 1;
+        if (last_of_batch && defer_closing_signal()) h->pending_signal = sync_step + 1;
         else halo_signal(h, sync_step + 1, h->stream);
     }
     return ALB_OK;
@@ -895,7 +926,7 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
             h->launches++;
         }
         if (halo) {
-            if (pass == 1 && last_of_batch) h->pending_signal = sync_step + 2;
+            if (pass == 1 && last_of_batch && defer_closing_signal()) h->pending_signal = sync_step + 2;
             else halo_signal(h, sync_step + pass + 1, h->aux);
         }
         if (trace) CK(cudaEventRecord(h->tev[2 + 2 * pass], h->aux));      // pass finished and signalled

@@ -173,6 +173,14 @@ cudaError_t launch_particles_step(ParticleState *ps, unsigned *ctrs, int n, unsi
                                   const uint8_t *mask, const float *ux, const float *uy, int pitch, int nx, int ny,
                                   double U0, cudaStream_t s);
 
+// every file: load its kernels' device code now (called once per device from alb_create_slab)
+cudaError_t preload_step_kernels();
+cudaError_t preload_march_kernels();
+cudaError_t preload_step2_kernels();
+cudaError_t preload_diag_kernels();
+cudaError_t preload_geometry_kernels();
+cudaError_t preload_particle_kernels();
+
 // alb_step.cu -- one step per pass
 cudaError_t launch_step_fast(const StepParams &p, cudaStream_t s);
 cudaError_t launch_step_general(const StepParams &p, cudaStream_t s);

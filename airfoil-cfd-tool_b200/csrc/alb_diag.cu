@@ -434,4 +434,27 @@ cudaError_t launch_fill_init(float *f0, float *f1, size_t plane, const float *e,
     return cudaGetLastError();
 }
 
+
+// Force the device code of every kernel of this file to be loaded now (see preload_all_kernels in
+// alb_api.cu): with CUDA's lazy module loading the FIRST launch of a kernel may have to wait for the
+// device to go idle, which never happens while a slab's wait_kernel spins for a neighbour that the
+// same host thread was about to step.
+#define ALB_PRELOAD(fn)                                                           \
+    do {                                                                          \
+        cudaFuncAttributes a_;                                                    \
+        cudaError_t e_ = cudaFuncGetAttributes(&a_, reinterpret_cast<const void *>(fn)); \
+        if (e_ != cudaSuccess) return e_;                                         \
+    } while (0)
+
+cudaError_t preload_diag_kernels() {
+    ALB_PRELOAD(stats_kernel);
+    ALB_PRELOAD(forces_kernel);
+    ALB_PRELOAD(mass_kernel);
+    ALB_PRELOAD(hash_kernel);
+    ALB_PRELOAD(render_kernel);
+    ALB_PRELOAD(fill_kernel);
+    ALB_PRELOAD(frame_finalize_kernel);
+    return cudaSuccess;
+}
+
 }  // namespace alb

@@ -307,4 +307,25 @@ cudaError_t launch_build_lists(const uint16_t *info, const uint8_t *tclass, uint
     return cudaGetLastError();
 }
 
+
+// Force the device code of every kernel of this file to be loaded now (see preload_all_kernels in
+// alb_api.cu): with CUDA's lazy module loading the FIRST launch of a kernel may have to wait for the
+// device to go idle, which never happens while a slab's wait_kernel spins for a neighbour that the
+// same host thread was about to step.
+#define ALB_PRELOAD(fn)                                                           \
+    do {                                                                          \
+        cudaFuncAttributes a_;                                                    \
+        cudaError_t e_ = cudaFuncGetAttributes(&a_, reinterpret_cast<const void *>(fn)); \
+        if (e_ != cudaSuccess) return e_;                                         \
+    } while (0)
+
+cudaError_t preload_geometry_kernels() {
+    ALB_PRELOAD(raster_kernel);
+    ALB_PRELOAD(build_info_kernel);
+    ALB_PRELOAD(build_tclass_kernel);
+    ALB_PRELOAD(build_deep_kernel);
+    ALB_PRELOAD(build_lists_kernel);
+    return cudaSuccess;
+}
+
 }  // namespace alb

@@ -346,4 +346,24 @@ cudaError_t launch_march2(const Step2Params &p, int nsm, cudaStream_t s) {
     return p.diag ? launch_march2_t<true, DM_IEEE>(p, grid, s) : launch_march2_t<false, DM_IEEE>(p, grid, s);
 }
 
+
+// Force the device code of every kernel of this file to be loaded now (see preload_all_kernels in
+// alb_api.cu): with CUDA's lazy module loading the FIRST launch of a kernel may have to wait for the
+// device to go idle, which never happens while a slab's wait_kernel spins for a neighbour that the
+// same host thread was about to step.
+#define ALB_PRELOAD(fn)                                                           \
+    do {                                                                          \
+        cudaFuncAttributes a_;                                                    \
+        cudaError_t e_ = cudaFuncGetAttributes(&a_, reinterpret_cast<const void *>(fn)); \
+        if (e_ != cudaSuccess) return e_;                                         \
+    } while (0)
+
+cudaError_t preload_march_kernels() {
+    ALB_PRELOAD((march2_kernel<false, DM_FAST3>));
+    ALB_PRELOAD((march2_kernel<true, DM_FAST3>));
+    ALB_PRELOAD((march2_kernel<false, DM_IEEE>));
+    ALB_PRELOAD((march2_kernel<true, DM_IEEE>));
+    return cudaSuccess;
+}
+
 }  // namespace alb

@@ -170,4 +170,22 @@ cudaError_t launch_particles_step(ParticleState *ps, unsigned *ctrs, int n, unsi
     return cudaGetLastError();
 }
 
+
+// Force the device code of every kernel of this file to be loaded now (see preload_all_kernels in
+// alb_api.cu): with CUDA's lazy module loading the FIRST launch of a kernel may have to wait for the
+// device to go idle, which never happens while a slab's wait_kernel spins for a neighbour that the
+// same host thread was about to step.
+#define ALB_PRELOAD(fn)                                                           \
+    do {                                                                          \
+        cudaFuncAttributes a_;                                                    \
+        cudaError_t e_ = cudaFuncGetAttributes(&a_, reinterpret_cast<const void *>(fn)); \
+        if (e_ != cudaSuccess) return e_;                                         \
+    } while (0)
+
+cudaError_t preload_particle_kernels() {
+    ALB_PRELOAD(particles_init_kernel);
+    ALB_PRELOAD(particles_step_kernel);
+    return cudaSuccess;
+}
+
 }  // namespace alb

@@ -503,4 +503,40 @@ void host_feq0(float u0, float *out9) {
     }
 }
 
+
+// Force the device code of every kernel of this file to be loaded now (see preload_all_kernels in
+// alb_api.cu): with CUDA's lazy module loading the FIRST launch of a kernel may have to wait for the
+// device to go idle, which never happens while a slab's wait_kernel spins for a neighbour that the
+// same host thread was about to step.
+#define ALB_PRELOAD(fn)                                                           \
+    do {                                                                          \
+        cudaFuncAttributes a_;                                                    \
+        cudaError_t e_ = cudaFuncGetAttributes(&a_, reinterpret_cast<const void *>(fn)); \
+        if (e_ != cudaSuccess) return e_;                                         \
+    } while (0)
+
+cudaError_t preload_step_kernels() {
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_FAST, false, DM_FAST3>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_FAST, true, DM_FAST3>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_FAST, false, DM_IEEE>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_FAST, true, DM_IEEE>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_GENERAL, false, DM_FAST3>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_GENERAL, true, DM_FAST3>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_GENERAL, false, DM_IEEE>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_GENERAL, true, DM_IEEE>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_UNIFIED, false, DM_FAST3>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_UNIFIED, true, DM_FAST3>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_UNIFIED, false, DM_IEEE>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_UNIFIED, true, DM_IEEE>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_FAST_LIST, false, DM_FAST3>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_FAST_LIST, true, DM_FAST3>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_FAST_LIST, false, DM_IEEE>));
+    ALB_PRELOAD((step_kernel<MODE_STEP, KIND_FAST_LIST, true, DM_IEEE>));
+    ALB_PRELOAD((step_kernel<MODE_MACRO, KIND_FAST>));
+    ALB_PRELOAD((step_kernel<MODE_MACRO, KIND_GENERAL>));
+    ALB_PRELOAD((small_lattice_kernel<DM_FAST3>));
+    ALB_PRELOAD((small_lattice_kernel<DM_IEEE>));
+    return cudaSuccess;
+}
+
 }  // namespace alb

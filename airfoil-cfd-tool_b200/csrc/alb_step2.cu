@@ -122,4 +122,23 @@ cudaError_t launch_copy_tasks(const StepParams &p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+
+// Force the device code of every kernel of this file to be loaded now (see preload_all_kernels in
+// alb_api.cu): with CUDA's lazy module loading the FIRST launch of a kernel may have to wait for the
+// device to go idle, which never happens while a slab's wait_kernel spins for a neighbour that the
+// same host thread was about to step.
+#define ALB_PRELOAD(fn)                                                           \
+    do {                                                                          \
+        cudaFuncAttributes a_;                                                    \
+        cudaError_t e_ = cudaFuncGetAttributes(&a_, reinterpret_cast<const void *>(fn)); \
+        if (e_ != cudaSuccess) return e_;                                         \
+    } while (0)
+
+cudaError_t preload_step2_kernels() {
+    ALB_PRELOAD(copy_tasks_kernel);
+    ALB_PRELOAD(div_selftest_kernel);
+    ALB_PRELOAD(divtau_check_kernel);
+    return cudaSuccess;
+}
+
 }  // namespace alb

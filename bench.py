@@ -269,6 +269,9 @@ def main():
     ms_dev = comm.max_float(ms_dev)
     wall_ms = comm.max_float(wall_ms)
     glups = cells_global * args.steps / (ms_dev * 1e-3) / 1e9
+    # checksum of the state the timed region produced (before the e2e loops add their own steps): the
+    # same `warmup + steps` steps give the same nine words at every N
+    state_hash, steps_at_hash = tun.state_hash(), tun.steps
 
     # same-box calibration of the denominator: a plain device copy (what MEASURED_PEAKS.json holds)
     copy_here = None
@@ -346,7 +349,6 @@ def main():
         e2e_fields = dist_mod.bench_e2e_fields(tun, cells_global)
 
     forces = tun.forces()
-    state_hash = tun.state_hash()
     if rank == 0:
         line = {
             "metric": METRIC, "value": glups, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -369,7 +371,7 @@ def main():
                       "total_steps": tun.steps,
                       # position-dependent checksum of the population bit patterns (alb_state_hash), slabs
                       # added modulo 2^64: identical at every N for the same number of steps
-                      "state_hash": ["%016x" % int(v) for v in state_hash]},
+                      "state_hash": ["%016x" % int(v) for v in state_hash], "state_hash_after_steps": steps_at_hash},
         }
         print(json.dumps(line), flush=True)
     tun.close()
