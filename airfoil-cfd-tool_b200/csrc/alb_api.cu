@@ -97,6 +97,8 @@ struct alb_handle {
     int prev_idx = 1;             // buffer that holds the PREVIOUS state (what the lazy macro pass reads);
                                   // -1 after a batch that ended with a double step: not materialised
     int small_capacity = 0;       // cells the persistent small-lattice kernel can hold on this GPU
+    int band_rows = 0;            // rows per CTA of band_lattice_kernel (0: this lattice does not qualify)
+    void *band_inbox = nullptr;   // its L2-resident message words between neighbouring bands
     int nsm = 148;                // SMs of the device
     double u0 = 0.06, tau = 0.58;
     float u0f = 0, tauf = 0, inv_tau = 0;
@@ -496,6 +498,7 @@ void free_handle(alb_handle *h) {
     for (auto &l : h->lists) cudaFree(l);
     cudaFree(h->list_counts);
     cudaFree(h->s2_queue);
+    cudaFree(h->band_inbox);
     cudaFree(h->me);
     cudaFree(h->parts);
     cudaFree(h->d_frame);
@@ -665,6 +668,14 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         CK(cudaStreamSynchronize(h->stream));
         h->small_capacity = small_lattice_capacity(device);
         CK(cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device));
+        if (h->whole() && h->small_capacity > 0 && !(getenv("AEROLAB_LBM_BAND") && atoi(getenv("AEROLAB_LBM_BAND")) == 0)) {
+            h->band_rows = band_lattice_rows(h->nx, h->nyl, h->nsm);
+            if (h->band_rows > 0) {
+                const size_t bytes = band_inbox_bytes(h->nx, h->nyl, h->band_rows);
+                CK(cudaMalloc(&h->band_inbox, bytes));
+                CK(cudaMemset(h->band_inbox, 0, bytes));        // tag 0 is never a step tag
+            }
+        }
         h->use_graph = getenv("AEROLAB_LBM_NO_GRAPH") == nullptr;   // A/B switch for measurements
         if (const char *e = getenv("AEROLAB_LBM_DOUBLE")) h->double_mode = atoi(e) != 0 ? 1 : 0;
         if (const char *e = getenv("AEROLAB_LBM_TRACE")) {
@@ -1046,7 +1057,31 @@ static int step_batch(alb_handle *h, int nsteps) {
     const bool doubles = double_steps_enabled(h);
     const bool persistent = !doubles && h->whole() && !halo && !h->external_halo && nsteps >= 2 &&
                             (long long)h->nx * h->nyl <= h->small_capacity;
-    if (persistent) {
+    if (persistent && h->band_rows > 0 && h->parity == h->cur) {
+        // small lattice, state in registers for the whole batch (band_lattice_kernel): chunks of at
+        // most ME_RING / 2 steps, the last one also reduces the statistics / face sums of the final state
+        if (!h->diag_prearmed)
+            CK(cudaMemcpyAsync(h->d_diag, h->h_diag_init, sizeof(DiagAcc) * DIAG_SLOTS, cudaMemcpyHostToDevice, h->stream));
+        h->diag_prearmed = false;
+        int cur = h->cur;
+        for (int done_b = 0; done_b < nsteps;) {
+            int n = nsteps - done_b;
+            if (n > ME_RING / 2) n = ME_RING / 2;
+            if (nsteps - done_b - n == 1) n--;             // never leave a single step for the last chunk
+            StepParams p = make_params(h, cur);
+            if (done_b + n == nsteps) arm_diag(h, p);
+            CK(launch_band_lattice(p, h->f[0], h->f[1], cur, n, h->band_rows, h->band_inbox, h->sync_steps + done_b,
+                                   h->d_err, h->stream));
+            h->launches += 3;
+            cur = (cur + n) & 1;
+            done_b += n;
+        }
+        h->cur = (h->cur + nsteps) & 1;
+        h->parity = h->cur;
+        h->prev_idx = 1 - h->cur;
+        h->solid_synced = false;
+        left = 0;
+    } else if (persistent) {
         // small lattice: the whole batch of steps in ONE cooperative launch (grid barrier per
         // step); its last iteration also reduces the statistics / face sums of the final state
         // (measured: as fast as a kernel without that code, and no extra launch)

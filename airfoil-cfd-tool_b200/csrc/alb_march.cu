@@ -51,9 +51,14 @@
 #ifndef ALB_MARCH_UNIT_OVERHEAD
 #define ALB_MARCH_UNIT_OVERHEAD 3
 #endif
-// how many CTAs an SM works through per pass (1: persistent CTAs that hold their SM until the end)
+// how many CTAs an SM works through per pass (1: persistent CTAs that hold their SM until the end).
+// Every retirement is a chance for the list-driven passes on the aux stream to get an SM.  Measured
+// (profiles/r2_scaling_notes.md): configs[3] on one GPU 126.6 / 141.2 / 144.9 / 142.8 / 143.5 GLUPS with
+// 1 / 6 / 12 / 24 / 48 generations; two GPUs, 32768 x 2048 rows each (weak): 259.6 with 6, 288.7 with 24
+// (one GPU: 145.4) -- with few generations the passes, and through their flags the neighbouring GPU,
+// wait 0.2 ms of every 1.0 ms double step for the first CTAs to retire.
 #ifndef ALB_MARCH_GENERATIONS
-#define ALB_MARCH_GENERATIONS 6
+#define ALB_MARCH_GENERATIONS 24
 #endif
 // L2 eviction hints on the staged loads.  Neighbouring column segments share 8 columns (plus the
 // rest of the 64-byte fetch granule), and the two warps reach a given row at different times: the

@@ -410,6 +410,193 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
     }
 }
 
+
+// ---- small lattices, second generation: the state lives in REGISTERS for the whole batch ----------
+// small_lattice_kernel (above) round-trips the 1.84 MB state of the reference's 320x160 lattice
+// through L2 on every step and crosses a grid-wide barrier per step: 2.9 us per step, all of it
+// latency.  Here a CTA owns a band of R full rows, one thread per cell, and a cell's nine
+// populations never leave the thread's registers between steps:
+//   * streaming inside the band goes through a double-buffered shared-memory copy of the band
+//     (one __syncthreads per step);
+//   * the rows a band needs from the band below / above travel through a small L2-resident inbox
+//     as 8-byte words {value, step tag} -- the reader polls the word itself until the tag is the
+//     current step, so data and flag arrive together (one L2 round trip, no fence, no grid barrier),
+//     and a band only ever waits for its two neighbours;
+//   * the inbox is double buffered by step parity: a neighbour can overwrite a word only two steps
+//     later, which it cannot reach before this band has published its next step, i.e. after every
+//     thread here has read the word;
+//   * the last two states of the batch are written to the two global buffers, so everything else
+//     in the library (lazy macroscopic pass, getters, diagnostics) finds what a sequence of single
+//     steps would have left.
+// Momentum-exchange sums go straight into the history ring slot of their step (bands are not in
+// lock step, so the two-accumulator scheme of the streaming kernels does not apply; the host zeroes
+// the slots of the batch before the launch and fixes MeState up afterwards).  Same
+// moments_clamped()/collide() -> bit-identical.  All CTAs must be co-resident (cooperative launch).
+struct BandWord { float v; int tag; };
+__device__ __forceinline__ void band_put(BandWord *w, float v, int tag) {
+    asm volatile("st.volatile.global.v2.b32 [%0], {%1, %2};" ::"l"(w), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ float band_get(const BandWord *w, int tag, int *err) {
+    unsigned v, t;
+    for (int spin = 0;; spin++) {
+        asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(w) : "memory");
+        if ((int)t == tag) break;
+        if (spin > (1 << 24)) {      // seconds: a neighbour is gone -- give up instead of hanging the GPU
+            *err = 1;
+            break;
+        }
+    }
+    return __uint_as_float(v);
+}
+
+constexpr int BAND_MAX_THREADS = 768;       // 80 registers per thread: no spills
+template <int DM>
+__global__ void __launch_bounds__(BAND_MAX_THREADS)
+band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, int cur, int nsteps, int R,
+                    BandWord *inbox, long long step_base, int *err) {
+    extern __shared__ float band_sm[];                  // [2][9][R][nx]
+    const int nx = p.nx, band = blockIdx.x, nbands = gridDim.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int r = tid / nx, x = tid - r * nx;
+    const int j = band * R + r;                          // lattice row (0-based)
+    const bool active = r < R && j < p.nyl;
+    const int rows_here = min(R, p.nyl - band * R);      // rows of this band
+    const size_t plane = p.plane;
+    const size_t c = (size_t)(j + 1) * p.pitch + x;
+    const unsigned info = active ? p.info[c] : (unsigned)(CT_EQUIL << INFO_TYPE_SHIFT);
+    const int type = (info >> INFO_TYPE_SHIFT) & INFO_TYPE_MASK;
+    const unsigned links = type == CT_FLUID ? (info & 0xffu) : 0u;
+    const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+    const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+    const int ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+    // inbox[band][side][parity][k][x]; side 0: the three populations arriving from the band below
+    // (f2, f5, f6 of its top row), side 1: from the band above (f4, f7, f8 of its bottom row)
+    auto box = [&](int b, int side, int par) { return inbox + ((((size_t)b * 2 + side) * 2 + par) * 3) * nx; };
+    const int up_k[9] = {-1, -1, 0, -1, -1, 1, 2, -1, -1};    // slot of population i in a side-0 message
+    const int dn_k[9] = {-1, -1, -1, -1, 0, -1, -1, 1, 2};    // ... in a side-1 message
+    float f[9];
+    {
+        const float *src = cur ? f1 : f0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) f[i] = active ? __ldcg(src + i * plane + c) : 0.0f;
+    }
+    const size_t sm_plane = (size_t)R * nx;
+    for (int s = 0; s < nsteps; s++) {
+        const int par = s & 1, tag = (int)(step_base + s + 1);
+        float *sm = band_sm + (size_t)par * 9 * sm_plane;
+        if (s == nsteps - 1 && active) {
+            // the state before the last step goes to the buffer that will hold the previous state
+            float *prev = ((cur + nsteps - 1) & 1) ? f1 : f0;
+            [[maybe_unused]] float *const dst_base = prev;
+#pragma unroll
+            for (int i = 0; i < 9; i++) { ALB_CHECK_DST(prev + i * plane + c, 1); prev[i * plane + c] = f[i]; }
+        }
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) sm[i * sm_plane + r * nx + x] = f[i];
+            if (r == rows_here - 1 && band + 1 < nbands) {
+                BandWord *o = box(band + 1, 0, par);
+                band_put(o + 0 * nx + x, f[2], tag);
+                band_put(o + 1 * nx + x, f[5], tag);
+                band_put(o + 2 * nx + x, f[6], tag);
+            }
+            if (r == 0 && band > 0) {
+                BandWord *o = box(band - 1, 1, par);
+                band_put(o + 0 * nx + x, f[4], tag);
+                band_put(o + 1 * nx + x, f[7], tag);
+                band_put(o + 2 * nx + x, f[8], tag);
+            }
+        }
+        __syncthreads();
+        long long me_fx = 0, me_fy = 0;
+        bool hit = false;
+        const bool diag_now = p.diag != nullptr && s == nsteps - 1;   // statistics of the final state
+        DiagLocal dl;
+        if (active) {
+            float g[9];
+            float rho = 1.0f, ux = p.u0, uy = 0.0f;                    // equilibrium border values
+            if (type == CT_FLUID) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) {
+                    if (i > 0 && (links & (1u << (i - 1)))) {
+                        const float b = f[opp[i]];                     // HTML:329-330: my own opposite population
+                        g[i] = b;
+                        const long long q = __double2ll_rn((double)b * 0x1p41);
+                        me_fx += -ex[i] * q;
+                        me_fy += -ey[i] * q;
+                    } else {
+                        const int rs = r - ey[i], xs = x - ex[i];      // interior fluid: xs is inside the row
+                        if (rs < 0) g[i] = band_get(box(band, 0, par) + up_k[i] * nx + xs, tag, err);
+                        else if (rs >= rows_here) g[i] = band_get(box(band, 1, par) + dn_k[i] * nx + xs, tag, err);
+                        else g[i] = sm[i * sm_plane + rs * nx + xs];
+                    }
+                }
+                const Moments m = moments_clamped(g);
+                collide<DM>(g, m, p.tau, p.inv_tau);
+                hit = m.hit;
+                rho = m.rho; ux = m.ux; uy = m.uy;
+            } else if (type == CT_SOLID) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) g[i] = f[opp[i]];
+            } else if (type == CT_OUTLET) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) g[i] = sm[i * sm_plane + r * nx + x - 1];
+                if (diag_now) moments_plain(g, rho, ux, uy);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 9; i++) g[i] = p.feq0[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 9; i++) f[i] = g[i];
+            if (diag_now && type != CT_SOLID && !(info & INFO_PAD)) {
+                diag_cell(p, dl, rho, ux, uy);
+                diag_faces(dl, info & 0xffu, rho, ux);
+            }
+        }
+        if (diag_now) diag_flush(p, dl, lane);
+        if (__any_sync(FULL, links != 0)) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                me_fx += __shfl_xor_sync(FULL, me_fx, d);
+                me_fy += __shfl_xor_sync(FULL, me_fy, d);
+            }
+            if (lane == 0) {
+                long long *slot = p.me->ring[(step_base + s) % ME_RING];
+                if (me_fx) atomicAdd(reinterpret_cast<unsigned long long *>(slot), (unsigned long long)me_fx);
+                if (me_fy) atomicAdd(reinterpret_cast<unsigned long long *>(slot + 1), (unsigned long long)me_fy);
+            }
+        }
+        if (hit && p.clamp_hits) atomicAdd(p.clamp_hits, 1ull);
+    }
+    if (active) {
+        float *dst = ((cur + nsteps) & 1) ? f1 : f0;
+        [[maybe_unused]] float *const dst_base = dst;
+#pragma unroll
+        for (int i = 0; i < 9; i++) { ALB_CHECK_DST(dst + i * plane + c, 1); dst[i * plane + c] = f[i]; }
+    }
+}
+
+// momentum-exchange bookkeeping around a band_lattice_kernel batch (see MeState): before -- commit the
+// pending sums of the previous step to the ring and clear both accumulators; after -- the batch's
+// sums sit in the ring already: advance the counter and mirror the last step into the accumulator a
+// streaming step would have left it in (frame_finalize_kernel reads it there)
+__global__ void me_before_band_kernel(MeState *m, int parity) {
+    if (m->pending) {
+        const long long c = m->count;
+        m->ring[c % ME_RING][0] = m->acc[parity ^ 1][0];
+        m->ring[c % ME_RING][1] = m->acc[parity ^ 1][1];
+        m->count = c + 1;
+    }
+    m->acc[0][0] = m->acc[0][1] = m->acc[1][0] = m->acc[1][1] = 0;
+    m->pending = 0;
+}
+__global__ void me_after_band_kernel(MeState *m, long long count, int last_parity) {
+    m->count = count;
+    m->acc[last_parity][0] = m->ring[(count - 1) % ME_RING][0];
+    m->acc[last_parity][1] = m->ring[(count - 1) % ME_RING][1];
+    m->pending = 0;
+}
+
 }  // namespace
 
 // The fast kernel and the general kernel of one step read the same source state and write
@@ -464,6 +651,50 @@ cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int 
     void *args[] = {&pp, &f0, &f1, &cur, &nsteps};
     const void *fn = p.div_mode == DM_FAST3 ? (const void *)small_lattice_kernel<DM_FAST3> : (const void *)small_lattice_kernel<DM_IEEE>;
     return cudaLaunchCooperativeKernel(fn, dim3(nblocks), dim3(BLOCK_THREADS), args, 0, s);
+}
+
+// Rows per band of band_lattice_kernel for this lattice on a device with nsm SMs, or 0 when the
+// lattice does not qualify: one thread per cell and at most 768 threads per CTA, one band per SM
+// (every band spins on its neighbours, so all must be resident), the band twice in shared memory.
+int band_lattice_rows(int nx, int nyl, int nsm) {
+    if (nx < 3 || nyl < 3 || nsm < 1) return 0;
+    const int R = (nyl + nsm - 1) / nsm;
+    if ((long long)R * nx > BAND_MAX_THREADS) return 0;
+    if (2ull * 9 * R * nx * sizeof(float) > 200 * 1024) return 0;
+    return R;
+}
+size_t band_inbox_bytes(int nx, int nyl, int R) {
+    const size_t nbands = (nyl + R - 1) / R;
+    return nbands * 2 * 2 * 3 * (size_t)nx * sizeof(BandWord);
+}
+
+// nsteps <= ME_RING / 2 steps of the whole lattice in one launch; step_base = number of steps taken so
+// far (== MeState::count once the pending step is committed); parity = momentum-exchange slot of the
+// NEXT streaming step (== cur on a handle that never ran a double step)
+cudaError_t launch_band_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps, int R, void *inbox,
+                                long long step_base, int *err, cudaStream_t s) {
+    me_before_band_kernel<<<1, 1, 0, s>>>(p.me, p.parity);
+    // zero the ring slots of this batch (at most two ranges)
+    {
+        const long long first = step_base % ME_RING;
+        const long long n1 = first + nsteps <= ME_RING ? nsteps : ME_RING - first;
+        cudaError_t e = cudaMemsetAsync(&p.me->ring[first][0], 0, sizeof(long long) * 2 * n1, s);
+        if (e == cudaSuccess && n1 < nsteps) e = cudaMemsetAsync(&p.me->ring[0][0], 0, sizeof(long long) * 2 * (nsteps - n1), s);
+        if (e != cudaSuccess) return e;
+    }
+    const int nbands = (p.nyl + R - 1) / R;
+    const int threads = (R * p.nx + 31) / 32 * 32;
+    const size_t smem = 2ull * 9 * R * p.nx * sizeof(float);
+    const void *fn = p.div_mode == DM_FAST3 ? (const void *)band_lattice_kernel<DM_FAST3> : (const void *)band_lattice_kernel<DM_IEEE>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    StepParams pp = p;
+    BandWord *ib = reinterpret_cast<BandWord *>(inbox);
+    void *args[] = {&pp, &f0, &f1, &cur, &nsteps, &R, &ib, &step_base, &err};
+    e = cudaLaunchCooperativeKernel(fn, dim3(nbands), dim3(threads), args, smem, s);
+    if (e != cudaSuccess) return e;
+    me_after_band_kernel<<<1, 1, 0, s>>>(p.me, step_base + nsteps, (cur + nsteps - 1) & 1);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_macro(const StepParams &p, cudaStream_t s) {
@@ -536,6 +767,10 @@ cudaError_t preload_step_kernels() {
     ALB_PRELOAD((step_kernel<MODE_MACRO, KIND_GENERAL>));
     ALB_PRELOAD((small_lattice_kernel<DM_FAST3>));
     ALB_PRELOAD((small_lattice_kernel<DM_IEEE>));
+    ALB_PRELOAD((band_lattice_kernel<DM_FAST3>));
+    ALB_PRELOAD((band_lattice_kernel<DM_IEEE>));
+    ALB_PRELOAD(me_before_band_kernel);
+    ALB_PRELOAD(me_after_band_kernel);
     return cudaSuccess;
 }
 
