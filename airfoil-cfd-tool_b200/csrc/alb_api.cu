@@ -97,7 +97,7 @@ struct alb_handle {
     int prev_idx = 1;             // buffer that holds the PREVIOUS state (what the lazy macro pass reads);
                                   // -1 after a batch that ended with a double step: not materialised
     int small_capacity = 0;       // cells the persistent small-lattice kernel can hold on this GPU
-    int band_rows = 0;            // rows per CTA of band_lattice_kernel (0: this lattice does not qualify)
+    int band_rows = 0;            // cells per CTA (strip) of band_lattice_kernel (0: this lattice does not qualify)
     void *band_inbox = nullptr;   // its L2-resident message words between neighbouring bands
     int nsm = 148;                // SMs of the device
     double u0 = 0.06, tau = 0.58;

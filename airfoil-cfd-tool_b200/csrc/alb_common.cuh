@@ -189,7 +189,7 @@ cudaError_t launch_macro(const StepParams &p, cudaStream_t s);
 cudaError_t launch_step_fast_list(const StepParams &p, cudaStream_t s);   // p.gen_list/p.ngen = the list
 int small_lattice_capacity(int device);
 cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps, cudaStream_t s);
-int band_lattice_rows(int nx, int nyl, int nsm);            // 0: the lattice does not qualify
+int band_lattice_rows(int nx, int nyl, int nsm);            // cells per strip; 0: the lattice does not qualify
 size_t band_inbox_bytes(int nx, int nyl, int R);
 cudaError_t launch_band_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps, int R, void *inbox,
                                 long long step_base, int *err, cudaStream_t s);

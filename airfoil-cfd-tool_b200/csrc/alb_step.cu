@@ -414,21 +414,24 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
 // ---- small lattices, second generation: the state lives in REGISTERS for the whole batch ----------
 // small_lattice_kernel (above) round-trips the 1.84 MB state of the reference's 320x160 lattice
 // through L2 on every step and crosses a grid-wide barrier per step: 2.9 us per step, all of it
-// latency.  Here a CTA owns a band of R full rows, one thread per cell, and a cell's nine
-// populations never leave the thread's registers between steps:
-//   * streaming inside the band goes through a double-buffered shared-memory copy of the band
+// latency.  Here the cells, in row-major order, are cut into one contiguous STRIP of L cells per SM
+// (L >= nx + 2, so a strip's pull sources lie in itself or in the strip before / after it), one
+// thread per cell, and a cell's nine populations never leave the thread's registers between steps:
+//   * streaming inside the strip goes through a double-buffered shared-memory copy of the strip
 //     (one __syncthreads per step);
-//   * the rows a band needs from the band below / above travel through a small L2-resident inbox
-//     as 8-byte words {value, step tag} -- the reader polls the word itself until the tag is the
-//     current step, so data and flag arrive together (one L2 round trip, no fence, no grid barrier),
-//     and a band only ever waits for its two neighbours;
-//   * the inbox is double buffered by step parity: a neighbour can overwrite a word only two steps
-//     later, which it cannot reach before this band has published its next step, i.e. after every
-//     thread here has read the word;
+//   * a population whose reader sits in the neighbouring strip travels through an L2-resident inbox
+//     as an 8-byte word {value, step tag}: the reader polls the word itself until the tag is the
+//     current step, so data and flag arrive together (one L2 round trip, no fence, no grid-wide
+//     barrier), and a strip only ever waits for its two neighbours;
+//   * the inbox is double buffered by step parity.  A word is rewritten two steps later; its writer
+//     cannot get there before it has polled -- UNCONDITIONALLY, whatever the cell types -- the words
+//     that the readers of its own word publish one step later, i.e. after they have read it.  (The
+//     first version polled only where a fluid cell needed the value; an all-border strip then never
+//     waited for anybody, ran ahead and overwrote words that had not been read.)
 //   * the last two states of the batch are written to the two global buffers, so everything else
 //     in the library (lazy macroscopic pass, getters, diagnostics) finds what a sequence of single
 //     steps would have left.
-// Momentum-exchange sums go straight into the history ring slot of their step (bands are not in
+// Momentum-exchange sums go straight into the history ring slot of their step (strips are not in
 // lock step, so the two-accumulator scheme of the streaming kernels does not apply; the host zeroes
 // the slots of the batch before the launch and fixes MeState up afterwards).  Same
 // moments_clamped()/collide() -> bit-identical.  All CTAs must be co-resident (cooperative launch).
@@ -436,54 +439,52 @@ struct BandWord { float v; int tag; };
 __device__ __forceinline__ void band_put(BandWord *w, float v, int tag) {
     asm volatile("st.volatile.global.v2.b32 [%0], {%1, %2};" ::"l"(w), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }
-__device__ __forceinline__ float band_get(const BandWord *w, int tag, int *err) {
-    unsigned v, t;
-    for (int spin = 0;; spin++) {
-        asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(w) : "memory");
-        if ((int)t == tag) break;
-        if (spin > (1 << 24)) {      // seconds: a neighbour is gone -- give up instead of hanging the GPU
-            *err = 1;
-            break;
-        }
-    }
-    return __uint_as_float(v);
-}
-
-constexpr int BAND_MAX_THREADS = 768;       // 80 registers per thread: no spills
+constexpr int BAND_MAX_THREADS = 512;       // 128 registers per thread: the polled words of a round live in registers
 template <int DM>
 __global__ void __launch_bounds__(BAND_MAX_THREADS)
-band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, int cur, int nsteps, int R,
+band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, int cur, int nsteps, int L,
                     BandWord *inbox, long long step_base, int *err) {
-    extern __shared__ float band_sm[];                  // [2][9][R][nx]
-    const int nx = p.nx, band = blockIdx.x, nbands = gridDim.x;
+    extern __shared__ float band_sm[];                  // [2][9][L]
+    const int nx = p.nx, ncell = p.nx * p.nyl;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int r = tid / nx, x = tid - r * nx;
-    const int j = band * R + r;                          // lattice row (0-based)
-    const bool active = r < R && j < p.nyl;
-    const int rows_here = min(R, p.nyl - band * R);      // rows of this band
+    const int base = blockIdx.x * L;                     // first cell of this strip
+    const int cell = base + tid;                         // row-major index over the owned rows
+    const bool active = tid < L && cell < ncell;
+    const int end = min(base + L, ncell);                // one past the last cell of this strip
+    const int y = active ? cell / nx : 0, x = active ? cell - y * nx : 0;
     const size_t plane = p.plane;
-    const size_t c = (size_t)(j + 1) * p.pitch + x;
+    const size_t c = (size_t)(y + 1) * p.pitch + x;
     const unsigned info = active ? p.info[c] : (unsigned)(CT_EQUIL << INFO_TYPE_SHIFT);
     const int type = (info >> INFO_TYPE_SHIFT) & INFO_TYPE_MASK;
     const unsigned links = type == CT_FLUID ? (info & 0xffu) : 0u;
     const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
     const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
     const int ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
-    // inbox[band][side][parity][k][x]; side 0: the three populations arriving from the band below
-    // (f2, f5, f6 of its top row), side 1: from the band above (f4, f7, f8 of its bottom row)
-    auto box = [&](int b, int side, int par) { return inbox + ((((size_t)b * 2 + side) * 2 + par) * 3) * nx; };
-    const int up_k[9] = {-1, -1, 0, -1, -1, 1, 2, -1, -1};    // slot of population i in a side-0 message
-    const int dn_k[9] = {-1, -1, -1, -1, 0, -1, -1, 1, 2};    // ... in a side-1 message
+    // Population i of this cell is read by cell + e_i (pull) and, all nine, by cell + 1 when that is
+    // the outlet cell of the row (HTML:301-312): it is published through the inbox when such a
+    // reader lies in another strip.  Symmetrically, population i is pulled from cell - e_i: from
+    // shared memory when that cell is in this strip, else from the inbox.
+    unsigned pub = 0, rem = 0;
+    int src_cell[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const int d = cell + ey[i] * nx + ex[i], sc = cell - ey[i] * nx - ex[i];
+        src_cell[i] = sc;
+        if (active && i > 0 && d >= 0 && d < ncell && (d < base || d >= end)) pub |= 1u << i;
+        if (active && i > 0 && sc >= 0 && sc < ncell && (sc < base || sc >= end)) rem |= 1u << i;
+    }
+    if (active && cell + 1 < ncell && cell + 1 >= end) pub |= 0x1ffu;          // a possible outlet reader in the next strip
+    const bool outlet_remote = active && type == CT_OUTLET && cell - 1 < base;
     float f[9];
     {
         const float *src = cur ? f1 : f0;
 #pragma unroll
         for (int i = 0; i < 9; i++) f[i] = active ? __ldcg(src + i * plane + c) : 0.0f;
     }
-    const size_t sm_plane = (size_t)R * nx;
     for (int s = 0; s < nsteps; s++) {
         const int par = s & 1, tag = (int)(step_base + s + 1);
-        float *sm = band_sm + (size_t)par * 9 * sm_plane;
+        float *sm = band_sm + (size_t)par * 9 * L;
+        BandWord *box = inbox + (size_t)par * 9 * ncell;          // [9][ncell], indexed by SOURCE cell
         if (s == nsteps - 1 && active) {
             // the state before the last step goes to the buffer that will hold the previous state
             float *prev = ((cur + nsteps - 1) & 1) ? f1 : f0;
@@ -493,18 +494,9 @@ band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, 
         }
         if (active) {
 #pragma unroll
-            for (int i = 0; i < 9; i++) sm[i * sm_plane + r * nx + x] = f[i];
-            if (r == rows_here - 1 && band + 1 < nbands) {
-                BandWord *o = box(band + 1, 0, par);
-                band_put(o + 0 * nx + x, f[2], tag);
-                band_put(o + 1 * nx + x, f[5], tag);
-                band_put(o + 2 * nx + x, f[6], tag);
-            }
-            if (r == 0 && band > 0) {
-                BandWord *o = box(band - 1, 1, par);
-                band_put(o + 0 * nx + x, f[4], tag);
-                band_put(o + 1 * nx + x, f[7], tag);
-                band_put(o + 2 * nx + x, f[8], tag);
+            for (int i = 0; i < 9; i++) {
+                sm[i * L + tid] = f[i];
+                if (pub & (1u << i)) band_put(box + (size_t)i * ncell + cell, f[i], tag);
             }
         }
         __syncthreads();
@@ -513,22 +505,45 @@ band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, 
         const bool diag_now = p.diag != nullptr && s == nsteps - 1;   // statistics of the final state
         DiagLocal dl;
         if (active) {
+            // pull, whatever the cell type: the polls are also what keeps a strip from running ahead
             float g[9];
+            g[0] = f[0];
+#pragma unroll
+            for (int i = 1; i < 9; i++) {
+                const int sc = src_cell[i];
+                g[i] = (!(rem & (1u << i)) && sc >= base && sc < end) ? sm[i * L + (sc - base)] : 0.0f;   // 0: outside the lattice, unused
+            }
+            // remote words: all loads of a round are in flight together (one L2 round trip per round,
+            // not one per word); a word whose tag is not the current step yet is asked for again
+            unsigned pend = rem;
+            for (int spin = 0; pend; spin++) {
+                unsigned v[9], tg[9];
+#pragma unroll
+                for (int i = 1; i < 9; i++)
+                    if (pend & (1u << i))
+                        asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];"
+                                     : "=r"(v[i]), "=r"(tg[i]) : "l"(box + (size_t)i * ncell + src_cell[i]) : "memory");
+#pragma unroll
+                for (int i = 1; i < 9; i++)
+                    if ((pend & (1u << i)) && (int)tg[i] == tag) {
+                        g[i] = __uint_as_float(v[i]);
+                        pend &= ~(1u << i);
+                    }
+                if (spin > (1 << 22)) {      // seconds: a neighbour is gone -- give up instead of hanging the GPU
+                    *err = 1;
+                    break;
+                }
+            }
             float rho = 1.0f, ux = p.u0, uy = 0.0f;                    // equilibrium border values
             if (type == CT_FLUID) {
 #pragma unroll
-                for (int i = 0; i < 9; i++) {
-                    if (i > 0 && (links & (1u << (i - 1)))) {
+                for (int i = 1; i < 9; i++) {
+                    if (links & (1u << (i - 1))) {
                         const float b = f[opp[i]];                     // HTML:329-330: my own opposite population
                         g[i] = b;
                         const long long q = __double2ll_rn((double)b * 0x1p41);
                         me_fx += -ex[i] * q;
                         me_fy += -ey[i] * q;
-                    } else {
-                        const int rs = r - ey[i], xs = x - ex[i];      // interior fluid: xs is inside the row
-                        if (rs < 0) g[i] = band_get(box(band, 0, par) + up_k[i] * nx + xs, tag, err);
-                        else if (rs >= rows_here) g[i] = band_get(box(band, 1, par) + dn_k[i] * nx + xs, tag, err);
-                        else g[i] = sm[i * sm_plane + rs * nx + xs];
                     }
                 }
                 const Moments m = moments_clamped(g);
@@ -539,8 +554,30 @@ band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, 
 #pragma unroll
                 for (int i = 0; i < 9; i++) g[i] = f[opp[i]];
             } else if (type == CT_OUTLET) {
+                if (!outlet_remote) {
 #pragma unroll
-                for (int i = 0; i < 9; i++) g[i] = sm[i * sm_plane + r * nx + x - 1];
+                    for (int i = 0; i < 9; i++) g[i] = sm[i * L + tid - 1];
+                } else {
+                    unsigned pend9 = 0x1ffu;
+                    for (int spin = 0; pend9; spin++) {
+                        unsigned v[9], tg[9];
+#pragma unroll
+                        for (int i = 0; i < 9; i++)
+                            if (pend9 & (1u << i))
+                                asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];"
+                                             : "=r"(v[i]), "=r"(tg[i]) : "l"(box + (size_t)i * ncell + cell - 1) : "memory");
+#pragma unroll
+                        for (int i = 0; i < 9; i++)
+                            if ((pend9 & (1u << i)) && (int)tg[i] == tag) {
+                                g[i] = __uint_as_float(v[i]);
+                                pend9 &= ~(1u << i);
+                            }
+                        if (spin > (1 << 22)) {
+                            *err = 1;
+                            break;
+                        }
+                    }
+                }
                 if (diag_now) moments_plain(g, rho, ux, uy);
             } else {
 #pragma unroll
@@ -653,19 +690,20 @@ cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int 
     return cudaLaunchCooperativeKernel(fn, dim3(nblocks), dim3(BLOCK_THREADS), args, 0, s);
 }
 
-// Rows per band of band_lattice_kernel for this lattice on a device with nsm SMs, or 0 when the
-// lattice does not qualify: one thread per cell and at most 768 threads per CTA, one band per SM
-// (every band spins on its neighbours, so all must be resident), the band twice in shared memory.
+// Cells per strip (= threads per CTA) of band_lattice_kernel for this lattice on a device with nsm
+// SMs, or 0 when the lattice does not qualify: one strip per SM at most (every strip spins on its
+// neighbours, so all must be resident), at least nx + 2 cells per strip (then every pull source lies
+// in the strip itself or in the one before / after it), one thread per cell.
 int band_lattice_rows(int nx, int nyl, int nsm) {
     if (nx < 3 || nyl < 3 || nsm < 1) return 0;
-    const int R = (nyl + nsm - 1) / nsm;
-    if ((long long)R * nx > BAND_MAX_THREADS) return 0;
-    if (2ull * 9 * R * nx * sizeof(float) > 200 * 1024) return 0;
-    return R;
+    const long long ncell = (long long)nx * nyl;
+    long long L = (ncell + nsm - 1) / nsm;
+    if (L < nx + 2) L = nx + 2;
+    if (L > BAND_MAX_THREADS) return 0;
+    return (int)L;
 }
-size_t band_inbox_bytes(int nx, int nyl, int R) {
-    const size_t nbands = (nyl + R - 1) / R;
-    return nbands * 2 * 2 * 3 * (size_t)nx * sizeof(BandWord);
+size_t band_inbox_bytes(int nx, int nyl, int /*L*/) {
+    return 2ull * 9 * (size_t)nx * nyl * sizeof(BandWord);
 }
 
 // nsteps <= ME_RING / 2 steps of the whole lattice in one launch; step_base = number of steps taken so
@@ -682,9 +720,10 @@ cudaError_t launch_band_lattice(const StepParams &p, float *f0, float *f1, int c
         if (e == cudaSuccess && n1 < nsteps) e = cudaMemsetAsync(&p.me->ring[0][0], 0, sizeof(long long) * 2 * (nsteps - n1), s);
         if (e != cudaSuccess) return e;
     }
-    const int nbands = (p.nyl + R - 1) / R;
-    const int threads = (R * p.nx + 31) / 32 * 32;
-    const size_t smem = 2ull * 9 * R * p.nx * sizeof(float);
+    const int L = R;                                           // cells per strip
+    const int nbands = (p.nx * p.nyl + L - 1) / L;
+    const int threads = (L + 31) / 32 * 32;
+    const size_t smem = 2ull * 9 * L * sizeof(float);
     const void *fn = p.div_mode == DM_FAST3 ? (const void *)band_lattice_kernel<DM_FAST3> : (const void *)band_lattice_kernel<DM_IEEE>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -1,7 +1,7 @@
 """GPU parity of band_lattice_kernel, the register-resident path for small lattices (the reference's
 default 320x160, HTML:76): populations, macroscopic fields, momentum-exchange history across
 launch chunks, clamp hits, statistics and the frame loop are bit-identical to the oracle, for
-lattices that do and do not divide evenly into bands, with solids on every border."""
+lattices that do and do not divide evenly into strips, with solids on every border."""
 import numpy as np
 import pytest
 
@@ -20,11 +20,13 @@ def al(built_lib):
 
 
 @pytest.mark.parametrize("nx,ny,batches", [
-    (320, 160, (2, 3, 40, 7)),          # the page's lattice: 80 bands of 2 rows
-    (320, 161, (5, 6)),                 # the last band has one row
-    (97, 31, (4, 9)),                   # one row per band, odd width
-    (700, 200, (3, 8)),                 # 2 rows of 700 = 1400 threads: does not qualify -> grid-barrier kernel
-    (250, 444, (6, 5)),                 # three rows per band
+    (320, 160, (2, 3, 40, 7)),          # the page's lattice: 148 strips of 346 cells
+    (320, 161, (5, 6)),                 # the last strip is short and holds only border cells
+    (97, 31, (4, 9)),                   # strips of nx + 2 cells: fewer strips than SMs
+    (700, 200, (3, 8)),                 # 946 cells per SM: does not qualify -> grid-barrier kernel
+    (250, 444, (6, 5)),                 # 750 cells per SM: grid-barrier kernel again
+    (200, 300, (6, 5)),                 # 406 cells per strip: two rows and a bit
+    (64, 9, (7, 2, 2)),                 # a handful of strips, every one touching both border rows
 ])
 def test_band_kernel_bitwise(al, nx, ny, batches):
     rng = np.random.default_rng(nx * ny)

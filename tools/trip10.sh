@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out
+timeout 600 python -m pytest tests/test_gpu_band.py -q -x > $O/t10_band.log 2>&1; echo "rc=$?" >> $O/t10_band.log
+python bench.py --workload "configs[1]" --steps 20000 --warmup 2000 --no-cpu-baseline > $O/t10_c1_band.json 2> $O/t10_c1_band.err
+
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:band_lattice -s 1 -c 1 -o $O/r2d_band_c1 \
+  python bench.py --workload "configs[1]" --steps 2000 --warmup 200 --no-cpu-baseline --no-e2e > $O/t10_ncu3.log 2>&1
+echo done
