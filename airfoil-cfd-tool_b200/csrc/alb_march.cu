@@ -231,16 +231,20 @@ march2_kernel(const __grid_constant__ Step2Params p) {
                 q[5] = *reinterpret_cast<const float4 *>(cs + 1 * 128);
                 q[6] = *reinterpret_cast<const float4 *>(cs + 2 * 128);
                 q[4] = o[4]; q[7] = o[7]; q[8] = o[8];
-                float mac[4][3];
-                const unsigned hm = collide_quad<DM, ALB_QUAD_GB>(q, p.tau, p.inv_tau, DIAG ? mac : nullptr);
+                unsigned hm;
+                if (DIAG) {
+                    // the statistics of the state being written ride along: rho, ux, uy and |u|^2 are consumed
+                    // where the collision has them (deep cells have no faces)
+                    hm = collide_quad<DM, ALB_QUAD_GB>(q, p.tau, p.inv_tau, [&](int, float rho, float ux, float uy, float uu) {
+                        if (st) diag_cell_m2(p, dl, rho, ux, uy, uu);
+                    });
+                } else {
+                    hm = collide_quad<DM, ALB_QUAD_GB>(q, p.tau, p.inv_tau);
+                }
                 if (st) {
                     hits += __popc(hm);
 #pragma unroll
                     for (int i = 0; i < 9; i++) ST4(d + i * plane, q[i]);
-                    if (DIAG) {
-#pragma unroll
-                        for (int c = 0; c < 4; c++) diag_cell(p, dl, mac[c][0], mac[c][1], mac[c][2]);
-                    }
                 }
             }
             // carry: this row's f0,f1,f3 in registers, its f2,f5,f6 in the slot just read
