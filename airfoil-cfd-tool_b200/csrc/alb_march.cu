@@ -223,13 +223,23 @@ march2_kernel(const __grid_constant__ Step2Params p) {
             cp_async_commit();                           // one group per row, empty or not
             // ---- step 2 of row a-1: f0,f1,f3 of its own row, f2,f5,f6 of row a-2, f4,f7,f8 of row a ----
             const bool st = (tfb & TF_DEEP) && own;
+            const bool any_st = __any_sync(FULL, st);
             float *const cs = car + k * M_CARRY;         // holds f2,f5,f6 of row a-2; receives those of row a
-            if (__any_sync(FULL, st)) {
-                float4 q[9];
-                q[0] = wn0; q[1] = wn1; q[3] = wn3;
+            float4 q[9];
+            if (any_st) {
                 q[2] = *reinterpret_cast<const float4 *>(cs + 0 * 128);
                 q[5] = *reinterpret_cast<const float4 *>(cs + 1 * 128);
                 q[6] = *reinterpret_cast<const float4 *>(cs + 2 * 128);
+            }
+            // this row's f2,f5,f6 go into the slot just read BEFORE step 2 runs: twelve registers fewer
+            // are live across the second collision
+            if (have) {
+                *reinterpret_cast<float4 *>(cs + 0 * 128) = o[2];
+                *reinterpret_cast<float4 *>(cs + 1 * 128) = o[5];
+                *reinterpret_cast<float4 *>(cs + 2 * 128) = o[6];
+            }
+            if (any_st) {
+                q[0] = wn0; q[1] = wn1; q[3] = wn3;
                 q[4] = o[4]; q[7] = o[7]; q[8] = o[8];
                 unsigned hm;
                 if (DIAG) {
@@ -247,12 +257,9 @@ march2_kernel(const __grid_constant__ Step2Params p) {
                     for (int i = 0; i < 9; i++) ST4(d + i * plane, q[i]);
                 }
             }
-            // carry: this row's f0,f1,f3 in registers, its f2,f5,f6 in the slot just read
+            // carry: this row's f0,f1,f3 stay in registers for the next iteration
             if (have) {
                 wn0 = o[0]; wn1 = o[1]; wn3 = o[3];
-                *reinterpret_cast<float4 *>(cs + 0 * 128) = o[2];
-                *reinterpret_cast<float4 *>(cs + 1 * 128) = o[5];
-                *reinterpret_cast<float4 *>(cs + 2 * 128) = o[6];
             }
             tfb = (a >= y0 && a < y1) ? tf0 : 0u;
             tf0 = tf1; tf1 = tf2; tf2 = tf3;
