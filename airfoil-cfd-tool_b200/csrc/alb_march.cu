@@ -103,6 +103,28 @@ __device__ __forceinline__ float4 shr(const float4 &v) {   // populations arrivi
     return make_float4(v.y, v.z, v.w, __shfl_down_sync(FULL, v.x, 1));
 }
 
+// Fused statistics of the state being written (DIAG variant; same result as diag_cell() in
+// alb_lbm.cuh).  The per-cell code inside the collision must stay branch-free and must not drag
+// the arg-max bookkeeping through the register allocator (the first version did both: 233 MOVs and
+// 90 branches in the loop body, +28 % on the double step that ends a frame).  So the hot part is five
+// registers -- rho window extrema, the pre-filter level and the current candidate's velocity -- and a
+// cell that may be a new arg-max (rare: within 1e-6 of the level and not the candidate itself) goes
+// through a call into the cold part, whose state lives in local memory.
+struct DiagCold {
+    double m2;          // largest ux^2 + uy^2 (exact in double) among cells with s < 4; -1: none
+    float m2f, bux, buy;
+};
+__device__ __noinline__ void diag_candidate(const Step2Params &p, DiagCold &c, float ux, float uy, float m2f) {
+    const double m2 = __dadd_rn(__dmul_rn((double)ux, (double)ux), __dmul_rn((double)uy, (double)uy));
+    if (m2 > c.m2 && m2 < p.m2_hi) {
+        if (m2 >= p.m2_lo && !(speed_ratio(ux, uy, p.U0d) < 4.0)) return;
+        c.m2f = fmaxf(c.m2f, m2f);   // only ACCEPTED cells (s < 4) may raise the pre-filter level
+        c.m2 = m2;
+        c.bux = ux;
+        c.buy = uy;
+    }
+}
+
 template <bool DIAG, int DM>
 #if ALB_MARCH_MAXNREG
 __global__ void __maxnreg__(ALB_MARCH_MAXNREG)
@@ -136,7 +158,9 @@ march2_kernel(const __grid_constant__ Step2Params p) {
 #endif
     const int total_warps = gridDim.x * M_WARPS;
     unsigned hits = 0;
-    [[maybe_unused]] DiagLocal dl;
+    [[maybe_unused]] float d_rmin = INFINITY, d_rmax = -INFINITY, d_thr = -1.0f, d_bux = 0.f, d_buy = 0.f;
+    [[maybe_unused]] DiagCold dcold;
+    dcold.m2 = -1.0; dcold.m2f = -1.0f; dcold.bux = 0.f; dcold.buy = 0.f;
 
     // units come from the queue; a warp takes at most p.quota of them, so that CTAs retire while the
     // pass is under way and the list-driven passes on the (high-priority) aux stream find SMs
@@ -246,7 +270,16 @@ march2_kernel(const __grid_constant__ Step2Params p) {
                     // the statistics of the state being written ride along: rho, ux, uy and |u|^2 are consumed
                     // where the collision has them (deep cells have no faces)
                     hm = collide_quad<DM, ALB_QUAD_GB>(q, p.tau, p.inv_tau, [&](int, float rho, float ux, float uy, float uu) {
-                        if (st) diag_cell_m2(p, dl, rho, ux, uy, uu);
+                        const bool in_window = st && rho >= p.rho_lo && rho <= p.rho_hi;
+                        d_rmin = fminf(d_rmin, in_window ? rho : INFINITY);
+                        d_rmax = fmaxf(d_rmax, in_window ? rho : -INFINITY);
+                        // uu >= level also drops NaN; above the cap s >= 4 for sure
+                        if (st && uu >= d_thr && uu <= p.m2f_cap && !(ux == d_bux && uy == d_buy)) {
+                            diag_candidate(p, dcold, ux, uy, uu);
+                            d_thr = dcold.m2f * (1.0f - 1e-6f);
+                            d_bux = dcold.bux;
+                            d_buy = dcold.buy;
+                        }
                     });
                 } else {
                     hm = collide_quad<DM, ALB_QUAD_GB>(q, p.tau, p.inv_tau);
@@ -268,7 +301,12 @@ march2_kernel(const __grid_constant__ Step2Params p) {
         cp_async_wait<0>();
         unit = __shfl_sync(FULL, next_unit, 0);
     }
-    if (DIAG) diag_flush<false>(p, dl, lane);
+    if (DIAG) {
+        DiagLocal dl;
+        dl.rmin = d_rmin; dl.rmax = d_rmax;
+        dl.m2 = dcold.m2; dl.m2f = dcold.m2f; dl.bux = dcold.bux; dl.buy = dcold.buy;
+        diag_flush<false>(p, dl, lane);
+    }
     if (hits && p.clamp_hits) atomicAdd(p.clamp_hits, (unsigned long long)hits);
     // the last warp to leave re-arms the queue for the next launch (stream order does the rest)
     if (lane == 0) {
