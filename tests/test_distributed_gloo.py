@@ -26,8 +26,9 @@ def test_gloo_slabs_match_whole_lattice(tmp_path, world, ny):
     out = str(tmp_path / "result.npz")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(free_port()), WORLD_SIZE=str(world),
                OMP_NUM_THREADS="2")
+    nframes = 7
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_gloo_worker.py"), str(nx), str(ny),
-                               str(nsteps), out], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                               str(nsteps), out, str(nframes)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT) for r in range(world)]
     logs = []
     for p in procs:
@@ -42,7 +43,29 @@ def test_gloo_slabs_match_whole_lattice(tmp_path, world, ny):
     o = olbm.OracleTunnel(nx, ny)
     o.apply_geometry(ogeo.SHAPES["naca4412"](), 10.0)
     o.step(nsteps)
+    # the frame loop of the decomposed lattice (per-slab partial records -> all-gather ->
+    # combine_frame_partials) against the page's frame loop on the whole lattice
+    rows = []
+    for f in range(1, nframes + 1):
+        o.step(4)
+        o.update_fields()
+        row = dict(maxS=o.max_s, cpMin=o.cp_min, cpMax=o.cp_max, CL=np.nan, CD=np.nan, sep=o.sep_frac, CL_me=o.me_coeffs()[0])
+        if f % 3 == 0:
+            o.compute_forces()
+        if o.cl_smooth is not None:
+            row.update(CL=o.cl_smooth, CD=o.cd_smooth)
+        row["sep"] = o.sep_frac
+        rows.append(row)
     r = np.load(out)
+    for k, row in enumerate(rows):
+        assert (r["series_maxS"][k], r["series_cpMin"][k], r["series_cpMax"][k]) == (row["maxS"], row["cpMin"], row["cpMax"]), k
+        assert r["series_CL_me"][k] == pytest.approx(row["CL_me"], rel=1e-15), k
+        if np.isnan(row["CL"]):
+            assert np.isnan(r["series_CL"][k])
+        else:
+            assert r["series_CL"][k] == pytest.approx(row["CL"], rel=1e-12)
+            assert r["series_CD"][k] == pytest.approx(row["CD"], rel=1e-12)
+        assert r["series_sep_frac"][k] == pytest.approx(row["sep"], rel=1e-12, abs=1e-15)
     assert_bitwise(r["F"], o.F, "gloo slabs vs whole lattice")
     assert tuple(r["me"]) == tuple(o.me_hist[-1])
     assert float(r["mass"][0]) == pytest.approx(olbm.total_mass(o.F), rel=1e-13)
