@@ -42,7 +42,7 @@ EXPORTS = [
     "alb_reynolds", "alb_stall_state",
     "alb_run_frames", "alb_frames_enqueue", "alb_frames_collect",
     "alb_particles_init", "alb_particles_resize", "alb_particles_step", "alb_particles_get",
-    "alb_create_multi", "alb_step_multi", "alb_connect_local", "alb_ipc_export", "alb_ipc_connect", "alb_halo_prime", "alb_halo_ptrs",
+    "alb_create_multi", "alb_step_multi", "alb_destroy_multi", "alb_connect_local", "alb_ipc_export", "alb_ipc_connect", "alb_halo_prime", "alb_halo_ptrs",
     "alb_set_external_halo", "alb_set_double_steps", "alb_selftest_division", "alb_launch_count", "alb_get_double_steps", "alb_debug_step2_plan", "alb_get_div_mode", "alb_set_div_mode",
 ]
 
@@ -128,6 +128,7 @@ def lib():
     L.alb_particles_get.argtypes = [H, vp, ip]
     L.alb_create_multi.argtypes = [C.c_int, C.c_int, ip, C.c_int, C.POINTER(H)]
     L.alb_step_multi.argtypes = [C.POINTER(H), C.c_int, C.c_int]
+    L.alb_destroy_multi.argtypes = [C.POINTER(H), C.c_int]
     L.alb_connect_local.argtypes = [H, H, H]
     L.alb_ipc_export.argtypes = [H, vp]
     L.alb_ipc_connect.argtypes = [H, vp, vp]

@@ -712,11 +712,12 @@ class LocalMultiTunnel:
         return series
 
     def close(self):
-        # quiesce every slab before any block is freed: neighbours store halo rows and flags into it
-        for t in self.slabs:
-            t.sync()
-        for t in self.slabs:
-            t.close()
+        # alb_destroy_multi drains every slab before any block is freed: neighbours store halo rows
+        # and flags into it
+        if self.slabs:
+            check(self._lib.alb_destroy_multi(self._handles, len(self.slabs)))
+            for t in self.slabs:
+                t._h = C.c_void_p()          # the handles are gone: WindTunnel.close()/__del__ must not free them again
         self.slabs = []
 
 

@@ -1792,6 +1792,20 @@ int alb_step_multi(alb_handle **slabs, int nslabs, int nsteps) {
     return ALB_OK;
 }
 
+int alb_destroy_multi(alb_handle **slabs, int nslabs) {
+    if (!slabs || nslabs < 0) return ALB_ERR_INVALID;
+    for (int k = 0; k < nslabs; k++)
+        if (slabs[k] && cudaSetDevice(slabs[k]->device) == cudaSuccess && slabs[k]->stream) {
+            cudaStreamSynchronize(slabs[k]->stream);
+            if (slabs[k]->aux) cudaStreamSynchronize(slabs[k]->aux);
+        }
+    for (int k = 0; k < nslabs; k++) {
+        if (slabs[k]) free_handle(slabs[k]);
+        slabs[k] = nullptr;
+    }
+    return ALB_OK;
+}
+
 int alb_ipc_export(alb_handle *h, void *blob) {
     NEED(h);
     ARG(blob, "alb_ipc_export: blob is NULL");

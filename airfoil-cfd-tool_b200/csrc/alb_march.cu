@@ -45,6 +45,9 @@
 #ifndef ALB_MARCH_WARPS
 #define ALB_MARCH_WARPS 16
 #endif
+#ifndef ALB_MARCH_WARPS_DIAG
+#define ALB_MARCH_WARPS_DIAG 12
+#endif
 #ifndef ALB_MARCH_HS_MAX
 #define ALB_MARCH_HS_MAX 32
 #endif
@@ -81,7 +84,9 @@ constexpr int M_WARPS = ALB_MARCH_WARPS;      // warps per CTA, one CTA per SM
 constexpr int M_OUT = 120;                    // output columns per warp (lanes 1..30)
 constexpr int M_STAGE = 9 * 128;              // floats of one staged step-1 row (9 planes x 128 columns)
 constexpr int M_CARRY = 3 * 128;              // floats of one carried row (f2, f5, f6 of an intermediate row)
-constexpr int M_WARP_SMEM = 2 * M_STAGE + 2 * M_CARRY;   // floats of shared memory per warp
+constexpr int M_DSLOT = 4 * 2 * 32;             // floats: candidate (ux, uy) of each of the four cells of a quad, per lane
+constexpr int M_DCOLD = 4 * 32;                 // floats: per lane the best candidate's exact |u|^2 (double) and fp32 |u|^2
+constexpr int M_WARP_SMEM = 2 * M_STAGE + 2 * M_CARRY + M_DSLOT + M_DCOLD;   // floats of shared memory per warp
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(unsigned dst, const float *src, [[maybe_unused]] unsigned long long policy) {
@@ -104,39 +109,36 @@ __device__ __forceinline__ float4 shr(const float4 &v) {   // populations arrivi
 }
 
 // Fused statistics of the state being written (DIAG variant; same result as diag_cell() in
-// alb_lbm.cuh).  The per-cell code inside the collision must stay branch-free and must not drag
-// the arg-max bookkeeping through the register allocator (the first version did both: 233 MOVs and
-// 90 branches in the loop body, +28 % on the double step that ends a frame).  So the hot part is five
-// registers -- rho window extrema, the pre-filter level and the current candidate's velocity -- and a
-// cell that may be a new arg-max (rare: within 1e-6 of the level and not the candidate itself) goes
-// through a call into the cold part, whose state lives in local memory.
-struct DiagCold {
-    double m2;          // largest ux^2 + uy^2 (exact in double) among cells with s < 4; -1: none
-    float m2f, bux, buy;
+// alb_lbm.cuh).  The per-cell code inside the collision must stay branch-free, call-free and must not
+// drag the arg-max bookkeeping through the register allocator (earlier versions: the values kept in
+// registers across the collision, then a cold call -- both +26..28 % on the double step that ends a
+// frame).  So the hot part is five registers (rho window extrema, the pre-filter level, the current
+// candidate's velocity); a cell that may be a new arg-max (rare: within 1e-6 of the level and not the
+// candidate itself) only drops its velocity into a private shared-memory slot and sets a bit, and
+// the exact fp64 comparison runs after the collision of the quad, outside the hot basic block.
+// Warps per CTA and registers per thread of the two variants.  The plain kernel runs 16 warps at 128
+// registers (the whole register file).  The DIAG variant needs a few more live values; at 128
+// registers it spilled 52 bytes per thread, and the reloads -- local memory, long scoreboard -- cost
+// 22 % (ncu, profiles/r2e: long-scoreboard 2.44 instead of 0.52 warps per issue).  The register file is
+// split over the four schedulers (16 K registers each), so the choices are 4 warps per scheduler at
+// <= 128 registers or 3 at <= 168 (14 warps at 144 registers do not launch): the DIAG variant runs 12
+// warps and does not spill.
+template <bool DIAG> struct MarchShape {
+    static constexpr int warps = DIAG ? ALB_MARCH_WARPS_DIAG : M_WARPS;
+    static constexpr int regs = ALB_MARCH_MAXNREG ? ALB_MARCH_MAXNREG : (16384 / (((warps + 3) / 4) * 32)) / 8 * 8;
 };
-__device__ __noinline__ void diag_candidate(const Step2Params &p, DiagCold &c, float ux, float uy, float m2f) {
-    const double m2 = __dadd_rn(__dmul_rn((double)ux, (double)ux), __dmul_rn((double)uy, (double)uy));
-    if (m2 > c.m2 && m2 < p.m2_hi) {
-        if (m2 >= p.m2_lo && !(speed_ratio(ux, uy, p.U0d) < 4.0)) return;
-        c.m2f = fmaxf(c.m2f, m2f);   // only ACCEPTED cells (s < 4) may raise the pre-filter level
-        c.m2 = m2;
-        c.bux = ux;
-        c.buy = uy;
-    }
-}
 
 template <bool DIAG, int DM>
-#if ALB_MARCH_MAXNREG
-__global__ void __maxnreg__(ALB_MARCH_MAXNREG)
-#else
-__global__ void __launch_bounds__(M_WARPS * 32, 1)
-#endif
+__global__ void __maxnreg__(MarchShape<DIAG>::regs)
 march2_kernel(const __grid_constant__ Step2Params p) {
     extern __shared__ float4 smem4[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // this lane's own 16 bytes of every row of the warp's private buffers
     float *const stg = reinterpret_cast<float *>(smem4) + (size_t)warp * M_WARP_SMEM + lane * 4;   // [2][9][128]
     float *const car = stg + 2 * M_STAGE;                                                           // [2][3][128]
+    // DIAG: this lane's candidate slots [4][2] and cold state {m2 lo, m2 hi, m2f}, stride 32 floats
+    [[maybe_unused]] float *const dsl = reinterpret_cast<float *>(smem4) + (size_t)warp * M_WARP_SMEM + 2 * M_STAGE + 2 * M_CARRY + lane;
+    [[maybe_unused]] float *const dco = dsl + M_DSLOT;
     const unsigned stg_u32 = smem_u32(stg);
     const size_t plane = p.plane;
     const int pitch = p.pitch, tpr = p.tpr;
@@ -156,11 +158,14 @@ march2_kernel(const __grid_constant__ Step2Params p) {
         policy = (lane < 2 || lane >= 30) ? keep : stream;
     }
 #endif
-    const int total_warps = gridDim.x * M_WARPS;
+    const int total_warps = gridDim.x * MarchShape<DIAG>::warps;
     unsigned hits = 0;
     [[maybe_unused]] float d_rmin = INFINITY, d_rmax = -INFINITY, d_thr = -1.0f, d_bux = 0.f, d_buy = 0.f;
-    [[maybe_unused]] DiagCold dcold;
-    dcold.m2 = -1.0; dcold.m2f = -1.0f; dcold.bux = 0.f; dcold.buy = 0.f;
+    if (DIAG) {
+        dco[0] = __int_as_float(__double2loint(-1.0));      // exact |u|^2 of the best candidate so far: none
+        dco[32] = __int_as_float(__double2hiint(-1.0));
+        dco[64] = -1.0f;                                    // its fp32 |u|^2 (the pre-filter level)
+    }
 
     // units come from the queue; a warp takes at most p.quota of them, so that CTAs retire while the
     // pass is under way and the list-driven passes on the (high-priority) aux stream find SMs
@@ -269,18 +274,41 @@ march2_kernel(const __grid_constant__ Step2Params p) {
                 if (DIAG) {
                     // the statistics of the state being written ride along: rho, ux, uy and |u|^2 are consumed
                     // where the collision has them (deep cells have no faces)
-                    hm = collide_quad<DM, ALB_QUAD_GB>(q, p.tau, p.inv_tau, [&](int, float rho, float ux, float uy, float uu) {
+                    unsigned cand = 0;
+                    hm = collide_quad<DM, ALB_QUAD_GB>(q, p.tau, p.inv_tau, [&](int c, float rho, float ux, float uy, float uu) {
                         const bool in_window = st && rho >= p.rho_lo && rho <= p.rho_hi;
                         d_rmin = fminf(d_rmin, in_window ? rho : INFINITY);
                         d_rmax = fmaxf(d_rmax, in_window ? rho : -INFINITY);
-                        // uu >= level also drops NaN; above the cap s >= 4 for sure
+                        // uu >= level also drops NaN; above the cap s >= 4 for sure; a velocity that IS the
+                        // candidate (a uniform free stream is bitwise uniform) cannot change the maximum
                         if (st && uu >= d_thr && uu <= p.m2f_cap && !(ux == d_bux && uy == d_buy)) {
-                            diag_candidate(p, dcold, ux, uy, uu);
-                            d_thr = dcold.m2f * (1.0f - 1e-6f);
-                            d_bux = dcold.bux;
-                            d_buy = dcold.buy;
+                            dsl[(c * 2 + 0) * 32] = ux;
+                            dsl[(c * 2 + 1) * 32] = uy;
+                            cand |= 1u << c;
                         }
                     });
+                    if (cand) {
+                        // exact comparison of the flagged cells, in cell order (diag_cell() of alb_lbm.cuh)
+                        double best = __hiloint2double(__float_as_int(dco[32]), __float_as_int(dco[0]));
+                        float best_f = dco[64];
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            if (!(cand & (1u << c))) continue;
+                            const float ux = dsl[(c * 2 + 0) * 32], uy = dsl[(c * 2 + 1) * 32];
+                            const double m2 = __dadd_rn(__dmul_rn((double)ux, (double)ux), __dmul_rn((double)uy, (double)uy));
+                            if (m2 > best && m2 < p.m2_hi) {
+                                if (m2 >= p.m2_lo && !(speed_ratio(ux, uy, p.U0d) < 4.0)) continue;
+                                best_f = fmaxf(best_f, ux * ux + uy * uy);   // only ACCEPTED cells raise the level
+                                best = m2;
+                                d_bux = ux;
+                                d_buy = uy;
+                            }
+                        }
+                        dco[0] = __int_as_float(__double2loint(best));
+                        dco[32] = __int_as_float(__double2hiint(best));
+                        dco[64] = best_f;
+                        d_thr = best_f * (1.0f - 1e-6f);
+                    }
                 } else {
                     hm = collide_quad<DM, ALB_QUAD_GB>(q, p.tau, p.inv_tau);
                 }
@@ -304,7 +332,8 @@ march2_kernel(const __grid_constant__ Step2Params p) {
     if (DIAG) {
         DiagLocal dl;
         dl.rmin = d_rmin; dl.rmax = d_rmax;
-        dl.m2 = dcold.m2; dl.m2f = dcold.m2f; dl.bux = dcold.bux; dl.buy = dcold.buy;
+        dl.m2 = __hiloint2double(__float_as_int(dco[32]), __float_as_int(dco[0]));
+        dl.m2f = dco[64]; dl.bux = d_bux; dl.buy = d_buy;
         diag_flush<false>(p, dl, lane);
     }
     if (hits && p.clamp_hits) atomicAdd(p.clamp_hits, (unsigned long long)hits);
@@ -319,7 +348,7 @@ march2_kernel(const __grid_constant__ Step2Params p) {
     }
 }
 
-constexpr size_t MARCH_SMEM = sizeof(float) * (size_t)M_WARPS * M_WARP_SMEM;
+template <bool DIAG> constexpr size_t MARCH_SMEM = sizeof(float) * (size_t)MarchShape<DIAG>::warps * M_WARP_SMEM;
 
 }  // namespace
 
@@ -376,28 +405,28 @@ void march_plan(Step2Params &p, int nsm) {
 int march_out_width() { return M_OUT; }
 
 template <bool DIAG, int DM>
-cudaError_t launch_march2_t(const Step2Params &p, int grid, cudaStream_t s) {
+cudaError_t launch_march2_t(const Step2Params &p, cudaStream_t s) {
+    // one CTA per SM at a time; every warp takes at most p.quota units from the queue, so the grid
+    // must offer at least nunits / quota warps
+    const long long need_warps = ((long long)p.nunits + p.quota - 1) / p.quota;
+    const int grid = (int)((need_warps + MarchShape<DIAG>::warps - 1) / MarchShape<DIAG>::warps);
     static bool configured[64] = {};       // the attribute is per device (and per instantiation)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(march2_kernel<DIAG, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(march2_kernel<DIAG, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM<DIAG>);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    march2_kernel<DIAG, DM><<<grid, M_WARPS * 32, MARCH_SMEM, s>>>(p);
+    march2_kernel<DIAG, DM><<<grid, MarchShape<DIAG>::warps * 32, MARCH_SMEM<DIAG>, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_march2(const Step2Params &p, int nsm, cudaStream_t s) {
     if (p.nunits <= 0) return cudaSuccess;
-    // one CTA per SM at a time; every warp takes at most p.quota units from the queue, so the grid
-    // must offer at least nunits / quota warps (and never fewer CTAs than SMs that can be filled)
-    const long long need_warps = ((long long)p.nunits + p.quota - 1) / p.quota;
-    int grid = (int)((need_warps + M_WARPS - 1) / M_WARPS);
     (void)nsm;
-    if (p.div_mode == DM_FAST3) return p.diag ? launch_march2_t<true, DM_FAST3>(p, grid, s) : launch_march2_t<false, DM_FAST3>(p, grid, s);
-    return p.diag ? launch_march2_t<true, DM_IEEE>(p, grid, s) : launch_march2_t<false, DM_IEEE>(p, grid, s);
+    if (p.div_mode == DM_FAST3) return p.diag ? launch_march2_t<true, DM_FAST3>(p, s) : launch_march2_t<false, DM_FAST3>(p, s);
+    return p.diag ? launch_march2_t<true, DM_IEEE>(p, s) : launch_march2_t<false, DM_IEEE>(p, s);
 }
 
 

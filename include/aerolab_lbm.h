@@ -261,6 +261,11 @@ int alb_connect_local(alb_handle *h, alb_handle *lo, alb_handle *hi);
  * (alb_forces_partial, alb_stats_partial, alb_get_me_history) add up. */
 int alb_create_multi(int nx, int ny, const int *devices, int ndev, alb_handle **out_slabs);
 int alb_step_multi(alb_handle **slabs, int nslabs, int nsteps);
+/* Destroy connected slabs together: every slab's work is drained first (a neighbour may
+ * still be storing halo rows and flags into a slab's memory), then all are freed.
+ * Destroying ONE slab of a connected set with alb_destroy is only safe when its
+ * neighbours are idle and are never stepped again. */
+int alb_destroy_multi(alb_handle **slabs, int nslabs);
 /* Cross-process neighbours through CUDA IPC: export a blob, exchange it by any
  * means (torch.distributed all_gather in the Python package), connect. */
 int alb_ipc_export(alb_handle *h, void *blob /* ALB_IPC_BYTES */);
