@@ -462,7 +462,7 @@ class WindTunnel:
         """Tiling of the fused two-step kernel for this slab (``alb_debug_step2_plan``)."""
         out = (C.c_int * 5)()
         check(self._lib.alb_debug_step2_plan(self.nx, self.ny_local, int(nsm), out))
-        return dict(nseg=out[0], wo=out[1], hs=out[2], nunits=out[3], wi=out[4])
+        return dict(nseg=out[0], wo=out[1], hs=out[2], nunits=out[3], warps=out[4])
 
     def set_double_steps(self, mode: int):
         """-1 automatic, 0 never, 1 always: two steps per pass over HBM (bit-identical results)."""

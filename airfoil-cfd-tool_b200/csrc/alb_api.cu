@@ -1920,7 +1920,7 @@ int alb_debug_step2_plan(int nx, int ny_local, int nsm, int *out5) {
     out5[1] = q.wo;
     out5[2] = q.hs;
     out5[3] = q.nunits;
-    out5[4] = march_out_width() + 8;
+    out5[4] = march_warps_per_cta();
     return ALB_OK;
 }
 

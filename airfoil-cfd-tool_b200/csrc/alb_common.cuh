@@ -200,6 +200,7 @@ cudaError_t launch_copy_tasks(const StepParams &p, cudaStream_t s);       // dst
 // alb_march.cu -- two steps per pass, one independent warp per unit (the default two-step kernel)
 void march_plan(Step2Params &p, int nsm);
 int march_out_width();     // output columns per warp
+int march_warps_per_cta();
 cudaError_t launch_march2(const Step2Params &p, int nsm, cudaStream_t s);
 cudaError_t launch_div_selftest(unsigned long long seed, int nblocks, int iters, unsigned long long *d_out3, cudaStream_t s);
 // mismatches of the three-instruction x / tau against IEEE division over all fp32 x with 2^-40 <= |x| < 2^8

@@ -36,14 +36,17 @@
 
 #include "alb_lbm.cuh"
 
-// Shape knobs: warps per CTA (one CTA per SM; 16 x 128 registers = the whole register file), the
-// tallest row segment the planner may choose, and the fixed cost of starting a unit (pipeline fill)
-// in row-steps.  Short segments win although they recompute two rows each: neighbouring column
+// Shape knobs: warps per CTA (one CTA per SM), the tallest row segment the planner may choose, and
+// the fixed cost of starting a unit (pipeline fill) in row-steps.  The register file is split over
+// the four schedulers (16 K registers each), so a CTA of 16 warps gets 128 registers per thread and
+// one of 12 warps 168.  At 128 the plain kernel spills 8 bytes and the DIAG variant 52, whose
+// reloads (local memory, long scoreboard) cost it 22 %; at 12 warps neither spills and the plain
+// kernel is 3 % faster as well (6.61 vs 6.83 ms per pass at configs[3], profiles/r2f vs r2c).  Short segments win although they recompute two rows each: neighbouring column
 // segments re-read each other's edge columns, and the less two warps can drift apart the more of
 // those re-reads hit L2 (measured at configs[3]: 24 rows 144.1, 32 rows 144.8, 48 rows 142.6, 64 rows
 // 140.8, 96 rows 138.3, 171 rows 135.5 GLUPS).
 #ifndef ALB_MARCH_WARPS
-#define ALB_MARCH_WARPS 16
+#define ALB_MARCH_WARPS 12
 #endif
 #ifndef ALB_MARCH_WARPS_DIAG
 #define ALB_MARCH_WARPS_DIAG 12
@@ -116,13 +119,9 @@ __device__ __forceinline__ float4 shr(const float4 &v) {   // populations arrivi
 // candidate's velocity); a cell that may be a new arg-max (rare: within 1e-6 of the level and not the
 // candidate itself) only drops its velocity into a private shared-memory slot and sets a bit, and
 // the exact fp64 comparison runs after the collision of the quad, outside the hot basic block.
-// Warps per CTA and registers per thread of the two variants.  The plain kernel runs 16 warps at 128
-// registers (the whole register file).  The DIAG variant needs a few more live values; at 128
-// registers it spilled 52 bytes per thread, and the reloads -- local memory, long scoreboard -- cost
-// 22 % (ncu, profiles/r2e: long-scoreboard 2.44 instead of 0.52 warps per issue).  The register file is
-// split over the four schedulers (16 K registers each), so the choices are 4 warps per scheduler at
-// <= 128 registers or 3 at <= 168 (14 warps at 144 registers do not launch): the DIAG variant runs 12
-// warps and does not spill.
+// Warps per CTA and registers per thread of the two variants (see the knobs at the top of the file):
+// 3 warps per scheduler at <= 168 registers, no spills.  (14 warps at 144 registers do not launch: a
+// scheduler's 16 K registers hold 3 such warps, not 4.)
 template <bool DIAG> struct MarchShape {
     static constexpr int warps = DIAG ? ALB_MARCH_WARPS_DIAG : M_WARPS;
     static constexpr int regs = ALB_MARCH_MAXNREG ? ALB_MARCH_MAXNREG : (16384 / (((warps + 3) / 4) * 32)) / 8 * 8;
@@ -403,6 +402,7 @@ void march_plan(Step2Params &p, int nsm) {
 }
 
 int march_out_width() { return M_OUT; }
+int march_warps_per_cta() { return M_WARPS; }
 
 template <bool DIAG, int DM>
 cudaError_t launch_march2_t(const Step2Params &p, cudaStream_t s) {

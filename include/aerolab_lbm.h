@@ -309,7 +309,8 @@ int alb_get_double_steps(const alb_handle *h, int *mode, int *active);
  * an nx-wide slab of ny_local rows on a GPU with nsm SMs.  out5 = {column segments
  * (over columns [128, pitch-128): the first and last 128-cell task of a row hold the
  * inlet / outlet and are never deep), output columns per segment, rows per segment,
- * units (= column segments x row segments; one warp each), columns a unit reads}. */
+ * units (= column segments x row segments; one warp each), warps per CTA (one CTA per SM)}.
+ * A unit reads 128 columns and writes the middle 120. */
 int alb_debug_step2_plan(int nx, int ny_local, int nsm, int *out5);
 /* Number of CUDA kernels the step batches of this handle have launched so far
  * (alb_step / alb_run_frames; kernels inside replayed CUDA graphs included). */

@@ -12,7 +12,7 @@ import pytest
 def plan(lib, nx, nyl, nsm=148):
     out = (C.c_int * 5)()
     assert lib.alb_debug_step2_plan(nx, nyl, nsm, out) == 0
-    return dict(nseg=out[0], wo=out[1], hs=out[2], nunits=out[3], wi=out[4])
+    return dict(nseg=out[0], wo=out[1], hs=out[2], nunits=out[3], warps=out[4], wi=128)
 
 
 @pytest.mark.parametrize("nx", [128, 130, 320, 384, 385, 504, 505, 633, 1100, 2048, 4096, 8191, 8192, 32768, 100000])
@@ -20,7 +20,7 @@ def plan(lib, nx, nyl, nsm=148):
 def test_plan_covers_the_lattice(built_lib, nx, nyl):
     p = plan(built_lib, nx, nyl)
     pitch = (nx + 127) // 128 * 128
-    assert p["wo"] == 120 and p["wi"] == 128
+    assert p["wo"] == 120 and p["warps"] in (12, 16)
     rows = nyl - 2
     if pitch < 384:
         assert p["nseg"] == 0 and p["nunits"] == 0          # no task can be deep: first and last task hold the borders
@@ -39,10 +39,10 @@ def test_plan_covers_the_lattice(built_lib, nx, nyl):
 
 @pytest.mark.parametrize("nx,nyl", [(32768, 16384), (32768, 2048), (4096, 2048), (2048, 1024)])
 def test_plan_balances_the_warps(built_lib, nx, nyl):
-    # units per persistent warp (148 SMs x 16 warps): the pass lasts ceil(units / warps) units, so the
+    # units per warp slot (148 SMs x warps per CTA): the pass lasts ceil(units / warps) units, so the
     # chosen height must keep the overhead of the last partial round and of the two extra step-1 rows small
     p = plan(built_lib, nx, nyl)
-    warps = 148 * 16
+    warps = 148 * p["warps"]
     rounds = -(-p["nunits"] // warps)
     ideal = (nx - 256) / 120 * (nyl - 2) * 2 / warps        # row-steps per warp if the work split perfectly
     model = rounds * (2 * p["hs"] + 2)
