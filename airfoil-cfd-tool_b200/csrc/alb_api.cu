@@ -78,7 +78,7 @@ struct alb_handle {
     int *gen_list = nullptr;      // TC_GENERAL tasks of this slab, [0] of gen_count = how many
     int *gen_count = nullptr;
     int ngen = 0;
-    // two steps per pass (step2_kernel): task flags, the four task lists of the two-pass path
+    // two steps per pass (march2_kernel): task flags, the four task lists of the two-pass path
     uint8_t *tflags = nullptr, *deep_tmp = nullptr;
     int *lists[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // see launch_build_lists
     int *list_counts = nullptr;
@@ -459,7 +459,7 @@ void print_trace(alb_handle *h) {
     if (!h->trace_armed) return;
     h->trace_armed = false;
     if (cudaEventSynchronize(h->tev[6]) != cudaSuccess) return;
-    const char *names[7] = {"fork", "pass1 flags in", "pass1 done", "pass2 flags in", "pass2 done", "step2_kernel done", "joined"};
+    const char *names[7] = {"fork", "pass1 flags in", "pass1 done", "pass2 flags in", "pass2 done", "march2_kernel done", "joined"};
     fprintf(stderr, "[alb trace] device %d rows %d..%d, double step at step %lld:", h->device, h->y0, h->y0 + h->nyl - 1,
             h->trace_step);
     for (int k = 1; k < 7; k++) {
@@ -893,11 +893,11 @@ int issue_step(alb_handle *h, int src_idx, int parity, bool halo, long long sync
 }
 
 // Enqueue TWO steps that read buffer src_idx and leave the result in buffer 1 - src_idx.
-//   main stream: step2_kernel -- every deep task, two steps per pass over HBM (36 B per cell update)
+//   main stream: march2_kernel -- every deep task, two steps per pass over HBM (36 B per cell update)
 //   aux stream:  the two-pass path for everything else: pass 1 writes the intermediate state of the
 //                shallow tasks and their neighbours into f[2], pass 2 advances the shallow tasks from
 //                f[2] into the destination.  The slab halo (edge rows are always shallow) is pushed
-//                by these passes exactly as by single steps, so step2_kernel needs no flags at all:
+//                by these passes exactly as by single steps, so march2_kernel needs no flags at all:
 //                next to a neighbouring slab TWO edge rows are shallow and it never reads a ghost row.
 int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sync_step, bool copy_solid,
                  bool diag = false, bool last_of_batch = false) {

@@ -111,7 +111,7 @@ struct StepParams {
     size_t peer_hi_row;      // float offset of its lower ghost row (row 0)
 };
 
-// Task flags of the two-steps-per-pass path (see step2_kernel in alb_step2.cu), one byte per warp
+// Task flags of the two-steps-per-pass path (see march2_kernel in alb_march.cu), one byte per warp
 // task [nrows][tpr]:
 //   TF_DEEP  every cell of the task and every cell within one cell of it is a plain interior fluid
 //            cell (type fluid, no solid pull source) and the row is not a slab edge row: the fused

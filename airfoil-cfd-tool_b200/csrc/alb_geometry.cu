@@ -199,7 +199,7 @@ __global__ void build_tclass_kernel(const uint16_t *__restrict__ info, uint8_t *
 }
 
 
-// ---- task sets of the two-steps-per-pass path (step2_kernel, alb_step2.cu) -----------------------
+// ---- task sets of the two-steps-per-pass path (march2_kernel, alb_march.cu) ----------------------
 // A cell is "plain" when its info word is 0: interior fluid, no solid pull source, not padding.
 // A task is deep when every cell within one cell of it (its own 128 cells, the last cell of the
 // task to its left, the first cell of the task to its right, in rows j-1, j, j+1) is plain, and

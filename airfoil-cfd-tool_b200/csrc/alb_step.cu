@@ -36,7 +36,7 @@ namespace {
 // paths in one launch -- for lattices so small that the step is launch-latency bound and
 // occupancy is irrelevant.
 // KIND_FAST_LIST: the fast path over a compacted task list (pass 1 / pass 2 of the two-pass path that
-// accompanies step2_kernel); entries may carry LIST_NOHIT.
+// accompanies march2_kernel); entries may carry LIST_NOHIT.
 constexpr int KIND_FAST = 0, KIND_GENERAL = 1, KIND_UNIFIED = 2, KIND_FAST_LIST = 3;
 
 // DIAG (step mode): also accumulate the autoscale statistics and pressure-face sums of the state

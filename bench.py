@@ -293,7 +293,7 @@ def main():
             copy_here = None
 
     # roofline of the dominant kernel: per launch, this rank's cells.  Algorithmic traffic is
-    # 72 B per cell update.  With double steps the dominant kernel (step2_kernel)
+    # 72 B per cell update.  With double steps the dominant kernel (march2_kernel)
     # performs TWO updates per cell and launch while reading and writing the state once, so the
     # algorithmic rate can exceed the DRAM peak; `traffic` (ncu, per launch) and `dram_frac` show
     # what actually crosses the HBM interface.

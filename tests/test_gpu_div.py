@@ -1,5 +1,5 @@
 """The fused kernels compute ux = jx/rho, uy = jy/rho with a shared reciprocal (div_pair in
-alb_step2.cu) instead of two generic divisions.  Inside its accepted operand range it must equal
+alb_lbm.cuh) instead of two generic divisions.  Inside its accepted operand range it must equal
 IEEE division bit for bit; outside it must decline (the kernels then divide for real)."""
 import pytest
 

@@ -1,4 +1,4 @@
-"""GPU parity of the two-steps-per-pass path (step2_kernel + the list-driven two-pass path).
+"""GPU parity of the two-steps-per-pass path (march2_kernel + the list-driven two-pass path).
 
 `set_double_steps(1)` forces it on lattices far below the automatic threshold, so the oracle
 finishes in seconds.  The bar is the same as for single steps: populations, macroscopic fields,
@@ -45,10 +45,10 @@ def compare_diagnostics(t, o, total, what):
 
 
 @pytest.mark.parametrize("nx,ny,shape,alpha,batches", [
-    (320, 160, "naca0012", 5.0, (3, 4, 21)),          # one strip, two row segments
-    (1200, 300, "naca4412", 10.0, (5, 12, 9)),        # three strips, three segments, graph replay
+    (320, 160, "naca0012", 5.0, (3, 4, 21)),          # one column segment (384 columns: a single task can be deep)
+    (1200, 300, "naca4412", 10.0, (5, 12, 9)),        # eight column segments, graph replay
     (333, 171, "naca2412", 12.0, (3, 7)),             # padded pitch
-    (2048, 520, "clark_y", 6.0, (11, 10)),            # five strips
+    (2048, 520, "clark_y", 6.0, (11, 10)),            # fifteen column segments
     (1536, 66, "naca0012", 0.0, (4, 5)),              # fewer rows than one segment
     (130, 7, "naca0012", 3.0, (3, 3, 3)),             # hardly any deep task
     (700, 5, "naca0012", 3.0, (9,)),                  # three deep rows at most
