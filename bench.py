@@ -209,6 +209,9 @@ def main():
                          "each slab (auto: measured for strong scaling on more than one GPU with the p2p halo)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-weak", action="store_true",
+                    help="skip the weak-scaling companion measurement (32768 x 2048*N) that strong-scaling runs of "
+                         "configs[3] append to their line")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -349,32 +352,56 @@ def main():
         e2e_fields = dist_mod.bench_e2e_fields(tun, cells_global)
 
     forces = tun.forces()
+    total_steps = tun.steps
+    decomposition = (f"{world} y-slab(s), one-row population halo ({args.halo}), rows per GPU {balance}: {tun.rows}")
+
+    # ---- weak-scaling companion (north_star: "strong and weak scaling") ------------------------------
+    # the default line is strong scaling; the same run also times the fixed-work-per-GPU lattice
+    # (configs[3] width, 2048 rows per GPU), so both curves come from one driver invocation per N
+    weak = None
+    if args.scaling == "strong" and args.workload == "configs[3]" and not args.no_weak:
+        tun.close()
+        tun = None
+        comm.barrier()
+        wny = 2048 * world
+        wt = dist_mod.DistributedTunnel(nx, wny, comm, device=local_rank, halo=args.halo)
+        wt.load_shape(shape, alpha=alpha)
+        wt.step(args.warmup)
+        wt.sync()
+        comm.barrier()
+        wt.step(args.steps)
+        wms = comm.max_float(wt.last_step_ms())
+        whash = wt.state_hash()
+        weak = {"value": nx * wny * args.steps / (wms * 1e-3) / 1e9, "unit": UNIT, "scaling": "weak",
+                "lattice": [nx, wny], "rows_per_gpu": 2048, "ms_per_step": wms / args.steps, "steps": args.steps,
+                "state_hash": ["%016x" % int(v) for v in whash]}
+        wt.close()
     if rank == 0:
         line = {
             "metric": METRIC, "value": glups, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {shape} alpha={alpha} on {nx}x{ny}, U0={U0}, tau={TAU}",
-                       "decomposition": f"{world} y-slab(s), one-row population halo ({args.halo}), rows per GPU "
-                                        f"{balance}: {tun.rows}",
+                       "decomposition": decomposition,
                        "l2": "populations (2 x %.1f GB per GPU) are far larger than the 126 MB L2; no flush needed"
                              % (36.0 * cells_local / 1e9),
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_fields": e2e_fields,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_fields": e2e_fields, "weak_scaling": weak,
             # counted by the library (alb_launch_count): kernels launched on this rank in the timed
             # region, kernels inside replayed CUDA graphs included
             "gpu_launches": int(launches),
             "clocks": clocks,
             "check": {"CL_me": forces.get("CL_me"), "CD_me": forces.get("CD_me"),
                       "CL_pressure_raw": forces.get("CL_raw"), "CD_pressure_raw": forces.get("CD_raw"),
-                      "total_steps": tun.steps,
+                      "total_steps": total_steps,
                       # position-dependent checksum of the population bit patterns (alb_state_hash), slabs
                       # added modulo 2^64: identical at every N for the same number of steps
                       "state_hash": ["%016x" % int(v) for v in state_hash], "state_hash_after_steps": steps_at_hash},
         }
         print(json.dumps(line), flush=True)
-    tun.close()
+    if tun is not None:
+        tun.close()
     comm.shutdown()
 
 
