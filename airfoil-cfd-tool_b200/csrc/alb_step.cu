@@ -725,8 +725,16 @@ cudaError_t launch_band_lattice(const StepParams &p, float *f0, float *f1, int c
     const int threads = (L + 31) / 32 * 32;
     const size_t smem = 2ull * 9 * L * sizeof(float);
     const void *fn = p.div_mode == DM_FAST3 ? (const void *)band_lattice_kernel<DM_FAST3> : (const void *)band_lattice_kernel<DM_IEEE>;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    // the attribute is per device and kernel, and only ever grows
+    static size_t configured[64][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaError_t e = cudaSuccess;
+    if (dev < 0 || dev >= 64 || configured[dev][p.div_mode == DM_FAST3 ? 0 : 1] < smem) {
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev][p.div_mode == DM_FAST3 ? 0 : 1] = smem;
+    }
     StepParams pp = p;
     BandWord *ib = reinterpret_cast<BandWord *>(inbox);
     void *args[] = {&pp, &f0, &f1, &cur, &nsteps, &R, &ib, &step_base, &err};
