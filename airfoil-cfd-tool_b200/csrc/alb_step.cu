@@ -414,43 +414,51 @@ small_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1,
 // ---- small lattices, second generation: the state lives in REGISTERS for the whole batch ----------
 // small_lattice_kernel (above) round-trips the 1.84 MB state of the reference's 320x160 lattice
 // through L2 on every step and crosses a grid-wide barrier per step: 2.9 us per step, all of it
-// latency.  Here the cells, in row-major order, are cut into one contiguous STRIP of L cells per SM
-// (L >= nx + 2, so a strip's pull sources lie in itself or in the strip before / after it), one
-// thread per cell, and a cell's nine populations never leave the thread's registers between steps:
-//   * streaming inside the strip goes through a double-buffered shared-memory copy of the strip
-//     (one __syncthreads per step);
-//   * a population whose reader sits in the neighbouring strip travels through an L2-resident inbox
-//     as an 8-byte word {value, step tag}: the reader polls the word itself until the tag is the
-//     current step, so data and flag arrive together (one L2 round trip, no fence, no grid-wide
-//     barrier), and a strip only ever waits for its two neighbours;
+// latency.  Here one thread owns one cell for the whole batch and the cell's nine populations never
+// leave its registers; streaming is MESSAGE PASSING through an L2-resident inbox:
+//   * every step a thread publishes its populations as 8-byte words {value, step tag} into
+//     inbox[parity][i][cell] and pulls population i from inbox[parity][i][cell - e_i], polling each
+//     word until its tag is the current step -- data and flag arrive together (one L2 round trip, no
+//     fence), there is no barrier of any kind (no grid barrier, no __syncthreads, no shared memory)
+//     and a thread only ever waits for its eight neighbours.  All words of a round are requested
+//     together; a word that has not arrived is asked for again;
 //   * the inbox is double buffered by step parity.  A word is rewritten two steps later; its writer
-//     cannot get there before it has polled -- UNCONDITIONALLY, whatever the cell types -- the words
-//     that the readers of its own word publish one step later, i.e. after they have read it.  (The
-//     first version polled only where a fluid cell needed the value; an all-border strip then never
-//     waited for anybody, ran ahead and overwrote words that had not been read.)
+//     cannot get there before it has polled -- UNCONDITIONALLY, whatever the cell types -- the word
+//     that the reader of its own word publishes one step later, i.e. after the reader has read it:
+//     population i of cell c is read by cell c + e_i, and c pulls population opp(i) from that very
+//     cell.  (An earlier version polled only where a fluid cell needed the value; all-border threads
+//     then ran ahead and overwrote unread words.)  The outlet cell copies all nine populations of
+//     its left neighbour, which in turn pulls f3 from the outlet cell: same argument;
 //   * the last two states of the batch are written to the two global buffers, so everything else
 //     in the library (lazy macroscopic pass, getters, diagnostics) finds what a sequence of single
 //     steps would have left.
-// Momentum-exchange sums go straight into the history ring slot of their step (strips are not in
+// Measured on the way (320x160): CTA row bands + shared memory + one poll at a time 2.71 us per step;
+// one row-major strip per SM, batched polls 2.35 us (714 instructions per warp and step, of which 125
+// are the collision: the shared-memory / inbox case distinctions and the barrier cost the rest).
+// Momentum-exchange sums go straight into the history ring slot of their step (threads are not in
 // lock step, so the two-accumulator scheme of the streaming kernels does not apply; the host zeroes
 // the slots of the batch before the launch and fixes MeState up afterwards).  Same
 // moments_clamped()/collide() -> bit-identical.  All CTAs must be co-resident (cooperative launch).
 struct BandWord { float v; int tag; };
+// GPU-scope relaxed accesses: the 8-byte word is written and read as ONE access, so value and tag
+// travel together and no ordering between different words is needed (volatile would compile to
+// system-scope accesses)
 __device__ __forceinline__ void band_put(BandWord *w, float v, int tag) {
-    asm volatile("st.volatile.global.v2.b32 [%0], {%1, %2};" ::"l"(w), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(w), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }
-constexpr int BAND_MAX_THREADS = 512;       // 128 registers per thread: the polled words of a round live in registers
+__device__ __forceinline__ void band_poll(const BandWord *w, unsigned &v, unsigned &t) {
+    asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(w) : "memory");
+}
+
+constexpr int BAND_MAX_THREADS = 384;       // 3 warps per scheduler: up to 168 registers per thread
 template <int DM>
 __global__ void __launch_bounds__(BAND_MAX_THREADS)
 band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, int cur, int nsteps, int L,
                     BandWord *inbox, long long step_base, int *err) {
-    extern __shared__ float band_sm[];                  // [2][9][L]
     const int nx = p.nx, ncell = p.nx * p.nyl;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int base = blockIdx.x * L;                     // first cell of this strip
-    const int cell = base + tid;                         // row-major index over the owned rows
+    const int cell = blockIdx.x * L + tid;               // row-major index over the owned rows
     const bool active = tid < L && cell < ncell;
-    const int end = min(base + L, ncell);                // one past the last cell of this strip
     const int y = active ? cell / nx : 0, x = active ? cell - y * nx : 0;
     const size_t plane = p.plane;
     const size_t c = (size_t)(y + 1) * p.pitch + x;
@@ -460,21 +468,20 @@ band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, 
     const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
     const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
     const int ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
-    // Population i of this cell is read by cell + e_i (pull) and, all nine, by cell + 1 when that is
-    // the outlet cell of the row (HTML:301-312): it is published through the inbox when such a
-    // reader lies in another strip.  Symmetrically, population i is pulled from cell - e_i: from
-    // shared memory when that cell is in this strip, else from the inbox.
-    unsigned pub = 0, rem = 0;
-    int src_cell[9];
+    // word index (within one parity's [9][ncell] block) this thread publishes population i to, and the
+    // one it pulls population i from; bit i of `rem`: that source cell exists (row-major arithmetic:
+    // at the ends of a row the "neighbour" is a cell of the adjacent row -- a border cell never uses
+    // the value, but it polls it all the same, which is what keeps the pairing symmetric)
+    unsigned rem = 0;
+    int pidx[9], ridx[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) {
-        const int d = cell + ey[i] * nx + ex[i], sc = cell - ey[i] * nx - ex[i];
-        src_cell[i] = sc;
-        if (active && i > 0 && d >= 0 && d < ncell && (d < base || d >= end)) pub |= 1u << i;
-        if (active && i > 0 && sc >= 0 && sc < ncell && (sc < base || sc >= end)) rem |= 1u << i;
+        const int sc = cell - ey[i] * nx - ex[i];
+        pidx[i] = i * ncell + cell;
+        ridx[i] = i * ncell + sc;
+        if (active && i > 0 && sc >= 0 && sc < ncell) rem |= 1u << i;
     }
-    if (active && cell + 1 < ncell && cell + 1 >= end) pub |= 0x1ffu;          // a possible outlet reader in the next strip
-    const bool outlet_remote = active && type == CT_OUTLET && cell - 1 < base;
+    const bool outlet = active && type == CT_OUTLET && cell > 0;
     float f[9];
     {
         const float *src = cur ? f1 : f0;
@@ -482,9 +489,8 @@ band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, 
         for (int i = 0; i < 9; i++) f[i] = active ? __ldcg(src + i * plane + c) : 0.0f;
     }
     for (int s = 0; s < nsteps; s++) {
-        const int par = s & 1, tag = (int)(step_base + s + 1);
-        float *sm = band_sm + (size_t)par * 9 * L;
-        BandWord *box = inbox + (size_t)par * 9 * ncell;          // [9][ncell], indexed by SOURCE cell
+        const int tag = (int)(step_base + s + 1);
+        BandWord *box = inbox + (size_t)(s & 1) * 9 * ncell;      // [9][ncell], indexed by SOURCE cell
         if (s == nsteps - 1 && active) {
             // the state before the last step goes to the buffer that will hold the previous state
             float *prev = ((cur + nsteps - 1) & 1) ? f1 : f0;
@@ -492,37 +498,24 @@ band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, 
 #pragma unroll
             for (int i = 0; i < 9; i++) { ALB_CHECK_DST(prev + i * plane + c, 1); prev[i * plane + c] = f[i]; }
         }
-        if (active) {
-#pragma unroll
-            for (int i = 0; i < 9; i++) {
-                sm[i * L + tid] = f[i];
-                if (pub & (1u << i)) band_put(box + (size_t)i * ncell + cell, f[i], tag);
-            }
-        }
-        __syncthreads();
         long long me_fx = 0, me_fy = 0;
         bool hit = false;
         const bool diag_now = p.diag != nullptr && s == nsteps - 1;   // statistics of the final state
         DiagLocal dl;
         if (active) {
-            // pull, whatever the cell type: the polls are also what keeps a strip from running ahead
+#pragma unroll
+            for (int i = 0; i < 9; i++) band_put(box + pidx[i], f[i], tag);
+            // pull, whatever the cell type (see above): all words of a round are in flight together
             float g[9];
             g[0] = f[0];
 #pragma unroll
-            for (int i = 1; i < 9; i++) {
-                const int sc = src_cell[i];
-                g[i] = (!(rem & (1u << i)) && sc >= base && sc < end) ? sm[i * L + (sc - base)] : 0.0f;   // 0: outside the lattice, unused
-            }
-            // remote words: all loads of a round are in flight together (one L2 round trip per round,
-            // not one per word); a word whose tag is not the current step yet is asked for again
+            for (int i = 1; i < 9; i++) g[i] = 0.0f;                   // sources outside the lattice: border cells, unused
             unsigned pend = rem;
             for (int spin = 0; pend; spin++) {
                 unsigned v[9], tg[9];
 #pragma unroll
                 for (int i = 1; i < 9; i++)
-                    if (pend & (1u << i))
-                        asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];"
-                                     : "=r"(v[i]), "=r"(tg[i]) : "l"(box + (size_t)i * ncell + src_cell[i]) : "memory");
+                    if (pend & (1u << i)) band_poll(box + ridx[i], v[i], tg[i]);
 #pragma unroll
                 for (int i = 1; i < 9; i++)
                     if ((pend & (1u << i)) && (int)tg[i] == tag) {
@@ -536,14 +529,16 @@ band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, 
             }
             float rho = 1.0f, ux = p.u0, uy = 0.0f;                    // equilibrium border values
             if (type == CT_FLUID) {
+                if (links) {
 #pragma unroll
-                for (int i = 1; i < 9; i++) {
-                    if (links & (1u << (i - 1))) {
-                        const float b = f[opp[i]];                     // HTML:329-330: my own opposite population
-                        g[i] = b;
-                        const long long q = __double2ll_rn((double)b * 0x1p41);
-                        me_fx += -ex[i] * q;
-                        me_fy += -ey[i] * q;
+                    for (int i = 1; i < 9; i++) {
+                        if (links & (1u << (i - 1))) {
+                            const float b = f[opp[i]];                 // HTML:329-330: my own opposite population
+                            g[i] = b;
+                            const long long q = __double2ll_rn((double)b * 0x1p41);
+                            me_fx += -ex[i] * q;
+                            me_fy += -ey[i] * q;
+                        }
                     }
                 }
                 const Moments m = moments_clamped(g);
@@ -553,29 +548,23 @@ band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, 
             } else if (type == CT_SOLID) {
 #pragma unroll
                 for (int i = 0; i < 9; i++) g[i] = f[opp[i]];
-            } else if (type == CT_OUTLET) {
-                if (!outlet_remote) {
+            } else if (outlet) {
+                // HTML:301-312: all nine populations of (x-1, y), previous state
+                unsigned pend9 = 0x1ffu;
+                for (int spin = 0; pend9; spin++) {
+                    unsigned v[9], tg[9];
 #pragma unroll
-                    for (int i = 0; i < 9; i++) g[i] = sm[i * L + tid - 1];
-                } else {
-                    unsigned pend9 = 0x1ffu;
-                    for (int spin = 0; pend9; spin++) {
-                        unsigned v[9], tg[9];
+                    for (int i = 0; i < 9; i++)
+                        if (pend9 & (1u << i)) band_poll(box + (pidx[i] - 1), v[i], tg[i]);
 #pragma unroll
-                        for (int i = 0; i < 9; i++)
-                            if (pend9 & (1u << i))
-                                asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];"
-                                             : "=r"(v[i]), "=r"(tg[i]) : "l"(box + (size_t)i * ncell + cell - 1) : "memory");
-#pragma unroll
-                        for (int i = 0; i < 9; i++)
-                            if ((pend9 & (1u << i)) && (int)tg[i] == tag) {
-                                g[i] = __uint_as_float(v[i]);
-                                pend9 &= ~(1u << i);
-                            }
-                        if (spin > (1 << 22)) {
-                            *err = 1;
-                            break;
+                    for (int i = 0; i < 9; i++)
+                        if ((pend9 & (1u << i)) && (int)tg[i] == tag) {
+                            g[i] = __uint_as_float(v[i]);
+                            pend9 &= ~(1u << i);
                         }
+                    if (spin > (1 << 22)) {
+                        *err = 1;
+                        break;
                     }
                 }
                 if (diag_now) moments_plain(g, rho, ux, uy);
@@ -690,15 +679,14 @@ cudaError_t launch_small_lattice(const StepParams &p, float *f0, float *f1, int 
     return cudaLaunchCooperativeKernel(fn, dim3(nblocks), dim3(BLOCK_THREADS), args, 0, s);
 }
 
-// Cells per strip (= threads per CTA) of band_lattice_kernel for this lattice on a device with nsm
-// SMs, or 0 when the lattice does not qualify: one strip per SM at most (every strip spins on its
-// neighbours, so all must be resident), at least nx + 2 cells per strip (then every pull source lies
-// in the strip itself or in the one before / after it), one thread per cell.
+// Cells per CTA (= threads) of band_lattice_kernel for this lattice on a device with nsm SMs, or 0
+// when the lattice does not qualify: one thread per cell, one CTA per SM at most (every thread spins
+// on its neighbours, so all must be resident), the cells spread evenly over the SMs.
 int band_lattice_rows(int nx, int nyl, int nsm) {
     if (nx < 3 || nyl < 3 || nsm < 1) return 0;
     const long long ncell = (long long)nx * nyl;
     long long L = (ncell + nsm - 1) / nsm;
-    if (L < nx + 2) L = nx + 2;
+    if (L < 32) L = 32;
     if (L > BAND_MAX_THREADS) return 0;
     return (int)L;
 }
@@ -720,21 +708,12 @@ cudaError_t launch_band_lattice(const StepParams &p, float *f0, float *f1, int c
         if (e == cudaSuccess && n1 < nsteps) e = cudaMemsetAsync(&p.me->ring[0][0], 0, sizeof(long long) * 2 * (nsteps - n1), s);
         if (e != cudaSuccess) return e;
     }
-    const int L = R;                                           // cells per strip
+    const int L = R;                                           // cells per CTA
     const int nbands = (p.nx * p.nyl + L - 1) / L;
     const int threads = (L + 31) / 32 * 32;
-    const size_t smem = 2ull * 9 * L * sizeof(float);
+    const size_t smem = 0;
     const void *fn = p.div_mode == DM_FAST3 ? (const void *)band_lattice_kernel<DM_FAST3> : (const void *)band_lattice_kernel<DM_IEEE>;
-    // the attribute is per device and kernel, and only ever grows
-    static size_t configured[64][2] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaError_t e = cudaSuccess;
-    if (dev < 0 || dev >= 64 || configured[dev][p.div_mode == DM_FAST3 ? 0 : 1] < smem) {
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) configured[dev][p.div_mode == DM_FAST3 ? 0 : 1] = smem;
-    }
     StepParams pp = p;
     BandWord *ib = reinterpret_cast<BandWord *>(inbox);
     void *args[] = {&pp, &f0, &f1, &cur, &nsteps, &R, &ib, &step_base, &err};

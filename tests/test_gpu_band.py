@@ -1,7 +1,7 @@
 """GPU parity of band_lattice_kernel, the register-resident path for small lattices (the reference's
 default 320x160, HTML:76): populations, macroscopic fields, momentum-exchange history across
 launch chunks, clamp hits, statistics and the frame loop are bit-identical to the oracle, for
-lattices that do and do not divide evenly into strips, with solids on every border."""
+lattices that do and do not divide evenly over the SMs, with solids on every border."""
 import numpy as np
 import pytest
 
@@ -20,13 +20,13 @@ def al(built_lib):
 
 
 @pytest.mark.parametrize("nx,ny,batches", [
-    (320, 160, (2, 3, 40, 7)),          # the page's lattice: 148 strips of 346 cells
-    (320, 161, (5, 6)),                 # the last strip is short and holds only border cells
-    (97, 31, (4, 9)),                   # strips of nx + 2 cells: fewer strips than SMs
+    (320, 160, (2, 3, 40, 7)),          # the page's lattice: 148 CTAs of 346 cells
+    (320, 161, (5, 6)),                 # the last CTA is short and holds only border cells
+    (97, 31, (4, 9)),                   # 32 cells per CTA: fewer CTAs than SMs
     (700, 200, (3, 8)),                 # 946 cells per SM: does not qualify -> grid-barrier kernel
     (250, 444, (6, 5)),                 # 750 cells per SM: grid-barrier kernel again
-    (200, 300, (6, 5)),                 # 406 cells per strip: two rows and a bit
-    (64, 9, (7, 2, 2)),                 # a handful of strips, every one touching both border rows
+    (200, 280, (6, 5)),                 # 379 cells per CTA
+    (64, 9, (7, 2, 2)),                 # tiny: most threads are border cells that poll without using the values
 ])
 def test_band_kernel_bitwise(al, nx, ny, batches):
     rng = np.random.default_rng(nx * ny)
