@@ -606,15 +606,22 @@ band_lattice_kernel(const __grid_constant__ StepParams p, float *f0, float *f1, 
 // pending sums of the previous step to the ring and clear both accumulators; after -- the batch's
 // sums sit in the ring already: advance the counter and mirror the last step into the accumulator a
 // streaming step would have left it in (frame_finalize_kernel reads it there)
-__global__ void me_before_band_kernel(MeState *m, int parity) {
-    if (m->pending) {
-        const long long c = m->count;
-        m->ring[c % ME_RING][0] = m->acc[parity ^ 1][0];
-        m->ring[c % ME_RING][1] = m->acc[parity ^ 1][1];
-        m->count = c + 1;
+__global__ void me_before_band_kernel(MeState *m, int parity, long long step_base, int nsteps) {
+    if (threadIdx.x == 0) {
+        if (m->pending) {
+            const long long c = m->count;          // == step_base - 1: not among the slots zeroed below
+            m->ring[c % ME_RING][0] = m->acc[parity ^ 1][0];
+            m->ring[c % ME_RING][1] = m->acc[parity ^ 1][1];
+            m->count = c + 1;
+        }
+        m->acc[0][0] = m->acc[0][1] = m->acc[1][0] = m->acc[1][1] = 0;
+        m->pending = 0;
     }
-    m->acc[0][0] = m->acc[0][1] = m->acc[1][0] = m->acc[1][1] = 0;
-    m->pending = 0;
+    // the ring slots of this batch collect atomic sums: zero them
+    for (int s = threadIdx.x; s < nsteps; s += blockDim.x) {
+        m->ring[(step_base + s) % ME_RING][0] = 0;
+        m->ring[(step_base + s) % ME_RING][1] = 0;
+    }
 }
 __global__ void me_after_band_kernel(MeState *m, long long count, int last_parity) {
     m->count = count;
@@ -699,15 +706,7 @@ size_t band_inbox_bytes(int nx, int nyl, int /*L*/) {
 // NEXT streaming step (== cur on a handle that never ran a double step)
 cudaError_t launch_band_lattice(const StepParams &p, float *f0, float *f1, int cur, int nsteps, int R, void *inbox,
                                 long long step_base, int *err, cudaStream_t s) {
-    me_before_band_kernel<<<1, 1, 0, s>>>(p.me, p.parity);
-    // zero the ring slots of this batch (at most two ranges)
-    {
-        const long long first = step_base % ME_RING;
-        const long long n1 = first + nsteps <= ME_RING ? nsteps : ME_RING - first;
-        cudaError_t e = cudaMemsetAsync(&p.me->ring[first][0], 0, sizeof(long long) * 2 * n1, s);
-        if (e == cudaSuccess && n1 < nsteps) e = cudaMemsetAsync(&p.me->ring[0][0], 0, sizeof(long long) * 2 * (nsteps - n1), s);
-        if (e != cudaSuccess) return e;
-    }
+    me_before_band_kernel<<<1, 256, 0, s>>>(p.me, p.parity, step_base, nsteps);
     const int L = R;                                           // cells per CTA
     const int nbands = (p.nx * p.nyl + L - 1) / L;
     const int threads = (L + 31) / 32 * 32;
