@@ -407,7 +407,8 @@ int rebuild_info(alb_handle *h) {
     // the host needs the number of general tasks to size that kernel's grid (mask changes are rare)
     CK(cudaMemcpyAsync(&h->ngen, h->gen_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(launch_build_lists(h->info, h->tclass, h->deep_tmp, h->tflags, h->lists, h->list_counts, h->pitch, h->nrows,
-                          h->y0 > 0 ? 1 : 0, h->y0 + h->nyl < h->ny_global ? 1 : 0, h->stream));
+                          h->y0 > 0 ? 1 : 0, h->y0 + h->nyl < h->ny_global ? 1 : 0,
+                          march_edges_enabled(h->nx, h->pitch), h->stream));
     CK(cudaMemcpyAsync(h->nlist, h->list_counts, 5 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     h->solid_synced = false;
     CK(cudaStreamSynchronize(h->stream));
@@ -957,6 +958,9 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
     q.div_mode = h->div_mode;
     q.clamp_hits = h->clamp_hits;
     q.queue = h->s2_queue;
+    q.edges = march_edges_enabled(h->nx, h->pitch) ? 1 : 0;
+    q.u0 = h->u0f;
+    memcpy(q.feq0, h->feq0, sizeof q.feq0);
     if (diag) arm_diag2(h, q);
     // no flags here: next to a neighbouring slab two edge rows are shallow, the fused kernel never
     // reads a ghost row, and the GPUs only meet in the short list-driven passes
@@ -1915,6 +1919,7 @@ int alb_debug_step2_plan(int nx, int ny_local, int nsm, int *out5) {
     memset(&q, 0, sizeof q);
     q.pitch = (nx + TASK_CELLS - 1) / TASK_CELLS * TASK_CELLS;
     q.nyl = ny_local;
+    q.edges = march_edges_enabled(nx, q.pitch) ? 1 : 0;
     march_plan(q, nsm);
     out5[0] = q.nseg;
     out5[1] = q.wo;

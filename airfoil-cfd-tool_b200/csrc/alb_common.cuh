@@ -135,8 +135,10 @@ struct Step2Params {
     // queue {next unit, warps that have finished}, both zero between launches
     int nseg, nunits;
     int quota;               // units a warp may take before it retires
+    int edges;               // the first / last task of a row can be deep (nx a multiple of 128, see build_deep_kernel)
     int *queue;
     float tau, inv_tau;
+    float u0, feq0[9];       // inlet state (HTML:314-322), edges only
     int div_mode;            // as in StepParams
     unsigned long long *clamp_hits;
     // fused statistics of the state being written (nullable), same meaning as in StepParams
@@ -216,9 +218,10 @@ cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tcla
 
 // lists[5] = pass-1 fast, pass-1 general, pass-2 fast, pass-2 general, all-solid (copied, not stepped);
 // counts = int[5] (device)
+bool march_edges_enabled(int nx, int pitch);
 cudaError_t launch_build_lists(const uint16_t *info, const uint8_t *tclass, uint8_t *deep_tmp, uint8_t *tflags,
                                int *const lists[5], int *counts, int pitch, int nrows, int lo_nb, int hi_nb,
-                               cudaStream_t s);
+                               bool edges, cudaStream_t s);
 
 // alb_diag.cu
 struct DiagScratch {

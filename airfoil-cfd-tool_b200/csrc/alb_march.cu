@@ -89,7 +89,8 @@ constexpr int M_STAGE = 9 * 128;              // floats of one staged step-1 row
 constexpr int M_CARRY = 3 * 128;              // floats of one carried row (f2, f5, f6 of an intermediate row)
 constexpr int M_DSLOT = 4 * 2 * 32;             // floats: candidate (ux, uy) of each of the four cells of a quad, per lane
 constexpr int M_DCOLD = 4 * 32;                 // floats: per lane the best candidate's exact |u|^2 (double) and fp32 |u|^2
-constexpr int M_WARP_SMEM = 2 * M_STAGE + 2 * M_CARRY + M_DSLOT + M_DCOLD;   // floats of shared memory per warp
+constexpr int M_EDGE = 32;                      // floats: outlet bookkeeping of lane 31 (two staged scalars and nine carried values per row parity)
+constexpr int M_WARP_SMEM = 2 * M_STAGE + 2 * M_CARRY + M_DSLOT + M_DCOLD + M_EDGE;   // floats of shared memory per warp
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(unsigned dst, const float *src, [[maybe_unused]] unsigned long long policy) {
@@ -98,6 +99,9 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const float *src, [[may
 #else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 #endif
+}
+__device__ __forceinline__ void cp_async4(unsigned dst, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -138,12 +142,15 @@ march2_kernel(const __grid_constant__ Step2Params p) {
     // DIAG: this lane's candidate slots [4][2] and cold state {m2 lo, m2 hi, m2f}, stride 32 floats
     [[maybe_unused]] float *const dsl = reinterpret_cast<float *>(smem4) + (size_t)warp * M_WARP_SMEM + 2 * M_STAGE + 2 * M_CARRY + lane;
     [[maybe_unused]] float *const dco = dsl + M_DSLOT;
+    // outlet bookkeeping (lane 31 of a unit that holds the last columns of the row): eg[2 k + {0,1}] = f6, f7 of
+    // the cell left of the outlet, source state, row of stage k; eg[4 + 9 k + i] = intermediate f_i of that cell
+    float *const eg = reinterpret_cast<float *>(smem4) + (size_t)warp * M_WARP_SMEM + 2 * M_STAGE + 2 * M_CARRY + M_DSLOT + M_DCOLD;
     const unsigned stg_u32 = smem_u32(stg);
+    const unsigned eg_u32 = smem_u32(eg);
     const size_t plane = p.plane;
     const int pitch = p.pitch, tpr = p.tpr;
     [[maybe_unused]] const float *const src = p.src;
     [[maybe_unused]] float *const dst_base = p.dst;
-    const bool own = lane >= 1 && lane <= 30;
     unsigned long long policy = 0;
 #if ALB_MARCH_L2HINT
     {
@@ -179,7 +186,28 @@ march2_kernel(const __grid_constant__ Step2Params p) {
         const int rowseg = unit / p.nseg, s = unit - rowseg * p.nseg;
         const int y0 = 2 + rowseg * p.hs;                // owned output rows [y0, y1)
         const int y1 = min(y0 + p.hs, p.nyl);
-        const int gx = 124 + M_OUT * s + lane * 4;       // this lane's quad; the warp writes columns [c0 + 4, c0 + 124)
+        // this lane's quad and whether it is one the unit writes.  Without edges: segment s stages columns
+        // [124 + 120 s, +128) and writes the middle 120.  With edges (march_plan): segment 0 stages [0, 128) and
+        // writes [0, 124) with the inlet cell patched; the last one stages [pitch - 128, pitch) and writes
+        // [pitch - 124, pitch) with the outlet cell patched; the ones between write 120 columns from 124 + 120 (s-1)
+        // on (the last of them clipped where the last segment begins)
+        int gx = 124 + M_OUT * s + lane * 4;
+        bool own = lane >= 1 && lane <= 30;
+        unsigned excl = 0;                               // cells of this quad that are not plain: bit 0 inlet, bit 3 outlet
+        if (p.edges) {
+            if (s == 0) {
+                gx = lane * 4;
+                own = lane <= 30;
+                excl = lane == 0 ? 1u : 0u;
+            } else if (s == p.nseg - 1) {
+                gx = pitch - 128 + lane * 4;
+                own = lane >= 1;
+                excl = lane == 31 ? 8u : 0u;
+            } else {
+                gx = M_OUT * s + lane * 4;
+                own = own && gx < pitch - 124;
+            }
+        }
         const uint8_t *const tfl = p.tflags + (gx >> 7);
         // task flags of rows a, a+1, a+2 (pipelined; rows beyond y1 are of no interest to this unit)
         auto row_flags = [&](int a) -> unsigned { return a <= y1 ? (unsigned)tfl[(size_t)a * tpr] : 0u; };
@@ -193,6 +221,13 @@ march2_kernel(const __grid_constant__ Step2Params p) {
                 const float *gi = g + i * plane - (ptrdiff_t)ey[i] * pitch;
                 ALB_CHECK_SRC(gi, 4);
                 cp_async16(d + i * 512u, gi, policy);
+            }
+            if (excl & 8u) {
+                // the outlet cell's intermediate state is the SOURCE state of its left neighbour (HTML:301-312); the
+                // neighbour's step 2 pulls f3, f6, f7 of it: f3 of this row is staged above, f6 and f7 are not
+                const float *g6 = p.src + 6 * plane + (size_t)a * pitch + (pitch - 2);
+                cp_async4(eg_u32 + (unsigned)(k * 2 + 0) * 4u, g6);
+                cp_async4(eg_u32 + (unsigned)(k * 2 + 1) * 4u, g6 + plane);
             }
         };
         int a = y0 - 1;
@@ -237,7 +272,25 @@ march2_kernel(const __grid_constant__ Step2Params p) {
                 o[8] = shl(v8);
                 const unsigned hm = collide_quad<DM>(o, p.tau, p.inv_tau);
                 // clamp hits of step 1: every deep cell is owned by exactly one unit
-                if ((tf0 & TF_DEEP) && own && a >= y0 && a < y1) hits += __popc(hm);
+                if ((tf0 & TF_DEEP) && own && a >= y0 && a < y1) hits += __popc(hm & ~excl);
+                if (excl) {
+                    if (excl & 1u) {
+                        // inlet cell: equilibrium at (1, U0, 0), HTML:314-322
+                        o[0].x = p.feq0[0]; o[1].x = p.feq0[1]; o[2].x = p.feq0[2];
+                        o[3].x = p.feq0[3]; o[4].x = p.feq0[4]; o[5].x = p.feq0[5];
+                        o[6].x = p.feq0[6]; o[7].x = p.feq0[7]; o[8].x = p.feq0[8];
+                    } else {
+                        // the intermediate state of the cell left of the outlet is what the outlet cell holds after
+                        // step 2; its own intermediate state matters only through what that neighbour pulls from it
+                        float *const oc = eg + 4 + k * 9;
+                        oc[0] = o[0].z; oc[1] = o[1].z; oc[2] = o[2].z;
+                        oc[3] = o[3].z; oc[4] = o[4].z; oc[5] = o[5].z;
+                        oc[6] = o[6].z; oc[7] = o[7].z; oc[8] = o[8].z;
+                        o[3].w = sp[3 * 128 + 2];
+                        o[6].w = eg[k * 2 + 0];
+                        o[7].w = eg[k * 2 + 1];
+                    }
+                }
                 // what later rows pull from this one, x-shifts applied now
                 o[1] = shl(o[1]);
                 o[3] = shr(o[3]);
@@ -275,17 +328,35 @@ march2_kernel(const __grid_constant__ Step2Params p) {
                     // where the collision has them (deep cells have no faces)
                     unsigned cand = 0;
                     hm = collide_quad<DM, ALB_QUAD_GB>(q, p.tau, p.inv_tau, [&](int c, float rho, float ux, float uy, float uu) {
-                        const bool in_window = st && rho >= p.rho_lo && rho <= p.rho_hi;
+                        const bool stc = st && !((excl >> c) & 1u);
+                        const bool in_window = stc && rho >= p.rho_lo && rho <= p.rho_hi;
                         d_rmin = fminf(d_rmin, in_window ? rho : INFINITY);
                         d_rmax = fmaxf(d_rmax, in_window ? rho : -INFINITY);
                         // uu >= level also drops NaN; above the cap s >= 4 for sure; a velocity that IS the
                         // candidate (a uniform free stream is bitwise uniform) cannot change the maximum
-                        if (st && uu >= d_thr && uu <= p.m2f_cap && !(ux == d_bux && uy == d_buy)) {
+                        if (stc && uu >= d_thr && uu <= p.m2f_cap && !(ux == d_bux && uy == d_buy)) {
                             dsl[(c * 2 + 0) * 32] = ux;
                             dsl[(c * 2 + 1) * 32] = uy;
                             cand |= 1u << c;
                         }
                     });
+                    if (excl && st) {
+                        // the inlet / outlet cell of this quad: its macroscopic values do not come from a collision;
+                        // it goes through the exact comparison below unconditionally
+                        float rho = 1.0f, ux = p.u0, uy = 0.0f;
+                        const int c = (excl & 1u) ? 0 : 3;
+                        if (excl & 8u) {
+                            const float *const oc = eg + 4 + (k ^ 1) * 9;
+                            const float f[9] = {oc[0], oc[1], oc[2], oc[3], oc[4], oc[5], oc[6], oc[7], oc[8]};
+                            moments_plain(f, rho, ux, uy);
+                        }
+                        const bool in_window = rho >= p.rho_lo && rho <= p.rho_hi;
+                        d_rmin = fminf(d_rmin, in_window ? rho : INFINITY);
+                        d_rmax = fmaxf(d_rmax, in_window ? rho : -INFINITY);
+                        dsl[(c * 2 + 0) * 32] = ux;
+                        dsl[(c * 2 + 1) * 32] = uy;
+                        cand |= 1u << c;
+                    }
                     if (cand) {
                         // exact comparison of the flagged cells, in cell order (diag_cell() of alb_lbm.cuh)
                         double best = __hiloint2double(__float_as_int(dco[32]), __float_as_int(dco[0]));
@@ -312,7 +383,17 @@ march2_kernel(const __grid_constant__ Step2Params p) {
                     hm = collide_quad<DM, ALB_QUAD_GB>(q, p.tau, p.inv_tau);
                 }
                 if (st) {
-                    hits += __popc(hm);
+                    hits += __popc(hm & ~excl);
+                    if (excl & 1u) {
+                        q[0].x = p.feq0[0]; q[1].x = p.feq0[1]; q[2].x = p.feq0[2];
+                        q[3].x = p.feq0[3]; q[4].x = p.feq0[4]; q[5].x = p.feq0[5];
+                        q[6].x = p.feq0[6]; q[7].x = p.feq0[7]; q[8].x = p.feq0[8];
+                    } else if (excl) {
+                        const float *const oc = eg + 4 + (k ^ 1) * 9;
+                        q[0].w = oc[0]; q[1].w = oc[1]; q[2].w = oc[2];
+                        q[3].w = oc[3]; q[4].w = oc[4]; q[5].w = oc[5];
+                        q[6].w = oc[6]; q[7].w = oc[7]; q[8].w = oc[8];
+                    }
 #pragma unroll
                     for (int i = 0; i < 9; i++) ST4(d + i * plane, q[i]);
                 }
@@ -357,7 +438,10 @@ template <bool DIAG> constexpr size_t MARCH_SMEM = sizeof(float) * (size_t)March
 // 2) plus a fixed start-up; the persistent warps take units from a queue, so the pass lasts about
 // ceil(units / warps) units -- pick the segment height that minimises it.
 void march_plan(Step2Params &p, int nsm) {
-    p.nseg = p.pitch >= 3 * TASK_CELLS ? (p.pitch - 2 * TASK_CELLS + M_OUT - 1) / M_OUT : 0;
+    if (p.edges)   // [0, 124) | 120 columns each from 124 on | [pitch - 124, pitch)
+        p.nseg = 2 + (p.pitch > 248 ? (p.pitch - 248 + M_OUT - 1) / M_OUT : 0);
+    else
+        p.nseg = p.pitch >= 3 * TASK_CELLS ? (p.pitch - 2 * TASK_CELLS + M_OUT - 1) / M_OUT : 0;
     const int rows = p.nyl - 2;
     p.nstrips = p.nseg;
     p.wo = M_OUT;
@@ -399,6 +483,18 @@ void march_plan(Step2Params &p, int nsm) {
     const long long per_warp = (p.nunits + warps - 1) / warps;
     p.quota = (int)((per_warp + gen_env - 1) / gen_env);
     if (p.quota < 1) p.quota = 1;
+}
+
+// The inlet and outlet columns can be part of the fused kernel's domain when the row has no padding
+// (the outlet cell is the last cell of the last task) and the two do not share a task.  All slabs of
+// a lattice decide alike: the rule looks at the global width and the environment only.
+bool march_edges_enabled(int nx, int pitch) {
+    static int env = -1;
+    if (env < 0) {
+        const char *e = getenv("AEROLAB_LBM_MARCH_EDGES");
+        env = e ? atoi(e) : 1;
+    }
+    return env != 0 && nx == pitch && pitch >= 2 * TASK_CELLS;
 }
 
 int march_out_width() { return M_OUT; }

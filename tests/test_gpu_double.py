@@ -200,3 +200,85 @@ def test_double_steps_restart(al):
     t2.step(8)
     assert_bitwise(t2.populations(), o.F, "fresh tunnel restarted from the dump")
     t.close(); t2.close()
+
+
+@pytest.mark.parametrize("nx,ny,dens", [
+    (256, 40, 0.0),                     # two tasks per row: inlet segment, outlet segment and a clipped one between
+    (384, 70, 0.001),
+    (512, 33, 0.0),
+    (1280, 130, 0.0005),
+    (2048, 48, 0.0),
+])
+def test_double_steps_inlet_and_outlet_columns(al, nx, ny, dens):
+    """Rows without padding (nx a multiple of 128): the inlet column x = 0 and the outlet column
+    x = nx-1 are part of the fused kernel's domain (alb_march.cu patches the one special cell).
+    A perturbed state makes the outlet copy (HTML:301-312) visible; solids next to and on the two
+    columns leave some edge tasks to the list-driven passes."""
+    rng = np.random.default_rng(nx * 131 + ny)
+    u0, tau = 0.09, 0.58
+    m = (rng.random((ny, nx)) < dens).astype(np.uint8) * 255
+    if ny >= 40:
+        m[ny // 4, 1] = 255                  # touches the inlet column
+        m[ny // 4 + 6, 0] = 255              # on it
+        m[ny // 2, nx - 2] = 255             # the cell the outlet copies from
+        m[ny // 2 + 7, nx - 1] = 255         # on the outlet column
+        m[3 * ny // 4:3 * ny // 4 + 3, nx // 2:nx // 2 + 9] = 255
+    F, _, _, _ = olbm.init(nx, ny, u0)
+    F *= (np.float32(1.0) + np.float32(4e-3) * (rng.random(F.shape, dtype=np.float32) - np.float32(0.5)))
+    t = al.WindTunnel(nx, ny, 0, u0=u0, tau=tau)
+    t.set_double_steps(1)
+    plan = t.step2_plan()
+    assert plan["nseg"] == 2 + max(0, -(-(nx - 248) // 120)), plan
+    t.set_mask(m)
+    t.set_populations(F)
+    G = np.empty_like(F)
+    rho = np.empty((ny, nx), np.float32); ux = np.empty_like(rho); uy = np.empty_like(rho)
+    me, hits, total = [], 0, 0
+    for n in (2, 7, 12, 1, 4):
+        t.step(n)
+        for _ in range(n):
+            fx, fy, h = olbm.step(m, F, G, rho, ux, uy, tau, u0)
+            F, G = G, F
+            me.append((fx, fy)); hits += h
+        total += n
+        assert_bitwise(t.populations(), F, f"{nx}x{ny} populations after {total} steps")
+    r, x, y = t.macro()
+    assert_bitwise(r, rho, "rho"); assert_bitwise(x, ux, "ux"); assert_bitwise(y, uy, "uy")
+    assert np.array_equal(t.me_history(total), np.array(me, dtype=np.int64))
+    assert t.clamp_hits() == hits
+    # the statistics fused into the double step that ends a frame see the two columns too
+    t.close()
+    pair = []
+    for mode in (0, 1):
+        s = al.WindTunnel(nx, ny, 0, u0=u0, tau=tau)
+        s.set_double_steps(mode)
+        s.set_mask(m)
+        s.set_populations(F)
+        pair.append((s, s.run_frames(5, None, 4, 2)))
+    (a, ra), (b, rb) = pair
+    for k in ra:
+        assert np.array_equal(ra[k], rb[k], equal_nan=True), k
+    assert_bitwise(a.populations(), b.populations(), "frame loop populations")
+    a.close(); b.close()
+
+
+def test_double_steps_outlet_column_extreme_cell(al):
+    """The statistics' arg-max lies ON the outlet column / the rho extrema on it: the fused kernel must
+    account for the patched cells exactly like the macroscopic pass does."""
+    nx, ny, u0, tau = 512, 64, 0.06, 0.6
+    F, _, _, _ = olbm.init(nx, ny, u0)
+    # a fast, dense blob left of the outlet: two steps later its copy sits in the outlet column
+    F[:, 20:24, nx - 4:nx - 1] *= np.float32(1.05)
+    F[1, 20:24, nx - 4:nx - 1] *= np.float32(1.6)
+    F[:, 40:42, 1:3] *= np.float32(0.97)
+    a = al.WindTunnel(nx, ny, 0, u0=u0, tau=tau)
+    b = al.WindTunnel(nx, ny, 0, u0=u0, tau=tau)
+    a.set_double_steps(0); b.set_double_steps(1)
+    for t in (a, b):
+        t.set_populations(F)
+    ra = a.run_frames(4, None, 2, 1)
+    rb = b.run_frames(4, None, 2, 1)
+    for k in ra:
+        assert np.array_equal(ra[k], rb[k], equal_nan=True), (k, ra[k], rb[k])
+    assert_bitwise(a.populations(), b.populations(), "populations")
+    a.close(); b.close()

@@ -2,8 +2,12 @@
 
 march2_kernel hands (row segment x column segment) units to independent warps.  A warp stages 128
 columns and writes the middle 120, so: the column segments must cover every column that can be
-deep, [128, pitch - 128), no staged column may lie outside the row, and the row segments must
-cover rows 2 .. ny_local-1."""
+deep, no staged column may lie outside the row, and the row segments must cover rows
+2 .. ny_local-1.  Rows with padding (nx not a multiple of 128) or of a single task: the first and
+the last task hold the borders and cannot be deep, the segments cover [128, pitch - 128).  Rows
+without padding: the inlet and outlet columns are part of the domain; the first segment stages
+[0, 128) and writes [0, 124), the last stages [pitch - 128, pitch) and writes [pitch - 124, pitch),
+the ones between write 120 columns each from column 124 on."""
 import ctypes as C
 
 import pytest
@@ -22,6 +26,19 @@ def test_plan_covers_the_lattice(built_lib, nx, nyl):
     pitch = (nx + 127) // 128 * 128
     assert p["wo"] == 120 and p["warps"] in (12, 16)
     rows = nyl - 2
+    if nx == pitch and pitch >= 256:
+        nmid = p["nseg"] - 2
+        assert nmid >= 0
+        assert 124 + nmid * p["wo"] >= pitch - 124              # the middle segments reach the last segment's columns ...
+        assert nmid == 0 or 124 + (nmid - 1) * p["wo"] < pitch - 124   # ... and none of them is empty
+        assert nmid == 0 or 120 * nmid + p["wi"] <= pitch       # middle segment s stages [120 s, 120 s + 128)
+        if rows > 0:
+            nsegs = -(-rows // p["hs"])
+            assert p["hs"] >= 1 and p["nunits"] == p["nseg"] * nsegs
+            assert nsegs * p["hs"] >= rows > (nsegs - 1) * p["hs"]
+        else:
+            assert p["nunits"] == 0
+        return
     if pitch < 384:
         assert p["nseg"] == 0 and p["nunits"] == 0          # no task can be deep: first and last task hold the borders
         return
@@ -44,7 +61,7 @@ def test_plan_balances_the_warps(built_lib, nx, nyl):
     p = plan(built_lib, nx, nyl)
     warps = 148 * p["warps"]
     rounds = -(-p["nunits"] // warps)
-    ideal = (nx - 256) / 120 * (nyl - 2) * 2 / warps        # row-steps per warp if the work split perfectly
+    ideal = nx / 120 * (nyl - 2) * 2 / warps                # row-steps per warp if the work split perfectly
     model = rounds * (2 * p["hs"] + 2)
     assert model <= 1.25 * ideal + 8, (p, model, ideal)
 
