@@ -107,7 +107,8 @@ struct alb_handle {
     float feq0[9];
     cudaStream_t stream = nullptr;
     cudaStream_t aux = nullptr;   // runs the general-task kernel concurrently with the fast kernel
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux2 = nullptr;  // double steps: the general-task kernel of a pass beside its fast-list kernel
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
     bool timed = false;
     long long steps = 0;          // user-visible step count
     long long sync_steps = 0;     // monotonic, drives the halo flags and the ME ring
@@ -524,7 +525,10 @@ void free_handle(alb_handle *h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_fork2) cudaEventDestroy(h->ev_fork2);
+    if (h->ev_join2) cudaEventDestroy(h->ev_join2);
     if (h->aux) cudaStreamDestroy(h->aux);
+    if (h->aux2) cudaStreamDestroy(h->aux2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -615,6 +619,12 @@ int alb_create_slab(int nx, int ny_global, int y0, int ny_local, int device, alb
         const char *aux_prio = getenv("AEROLAB_LBM_AUX_PRIO");
         CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking,
                                         aux_prio && atoi(aux_prio) == 0 ? prio_lo : prio_hi));
+        if (!(getenv("AEROLAB_LBM_AUX2") && atoi(getenv("AEROLAB_LBM_AUX2")) == 0)) {   // A/B switch for measurements
+            CK(cudaStreamCreateWithPriority(&h->aux2, cudaStreamNonBlocking,
+                                            aux_prio && atoi(aux_prio) == 0 ? prio_lo : prio_hi));
+            CK(cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
+        }
         CK(cudaEventCreate(&h->ev0));
         CK(cudaEventCreate(&h->ev1));
         CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -921,12 +931,23 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
         }
         if (diag && pass == 1) arm_diag(h, p);
         if (trace) CK(cudaEventRecord(h->tev[1 + 2 * pass], h->aux));      // the neighbours' flags have arrived
+        // the two kernels of a pass write disjoint tasks (and the momentum-exchange sums of a step go to an
+        // accumulator that its own bookkeeping does not touch, as in single steps): side by side
+        const bool side = h->aux2 && h->nlist[2 * pass + 1] > 0;
+        if (side) {
+            CK(cudaEventRecord(h->ev_fork2, h->aux));
+            CK(cudaStreamWaitEvent(h->aux2, h->ev_fork2, 0));
+        }
         p.gen_list = h->lists[2 * pass];
         p.ngen = h->nlist[2 * pass];
         CK(launch_step_fast_list(p, h->aux));
         p.gen_list = h->lists[2 * pass + 1];
         p.ngen = h->nlist[2 * pass + 1];
-        CK(launch_step_general(p, h->aux));
+        CK(launch_step_general(p, side ? h->aux2 : h->aux));
+        if (side) {
+            CK(cudaEventRecord(h->ev_join2, h->aux2));
+            CK(cudaStreamWaitEvent(h->aux, h->ev_join2, 0));
+        }
         h->launches += 1 + (p.ngen > 0 ? 1 : 0) + (halo ? 2 : 0);
         if (pass == 1 && copy_solid && h->nlist[4] > 0) {
             // all-solid tasks return to their state after two steps: copy, unless the destination
