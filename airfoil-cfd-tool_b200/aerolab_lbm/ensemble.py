@@ -42,9 +42,9 @@ def run_cases(coords, alphas: Sequence[float], nx: int = 2048, ny: int = 1024, s
     for a in alphas:
         t = WindTunnel(nx, ny, device, u0=u0, tau=tau)
         # Several cases sharing a GPU: two steps per pass also pays below the size at which one lattice
-        # alone switches to it (measured, four 2048x1024 cases on one B200, 20,000 steps: 79.2 vs 74.2
-        # GLUPS aggregate) -- the other cases fill the SMs while one case's short list-driven passes run.
-        # Bit-identical either way.  AEROLAB_LBM_DOUBLE in the environment still decides if set.
+        # alone switches to it (about two million cells) -- the other cases fill the SMs while one case's
+        # short list-driven passes run.  Bit-identical either way.  AEROLAB_LBM_DOUBLE in the environment
+        # still decides if set.
         if len(alphas) >= 2 and nx >= 1024 and "AEROLAB_LBM_DOUBLE" not in os.environ:
             t.set_double_steps(1)
         t.load_coords(coords, alpha=float(a))

@@ -25,10 +25,12 @@ constexpr int DIAG_BLOCKS = 148 * 4;          // fixed reduction grid -> determi
 constexpr int UNIFIED_MAX_TASKS = 148 * 2 * 8;   // one wave of the unified kernel (2 CTAs/SM x 8 tasks)
 constexpr long long WAIT_TIMEOUT_NS = 20LL * 1000 * 1000 * 1000;
 // Lattices at least this wide and this large advance two steps per pass (see step_batch).  Measured
-// with march2_kernel: 32768x16384 141-145 vs 94 GLUPS; 4096x2048 112 vs 85; 2048x1024 71 vs 74 (one eighth
-// of its tasks sit in the first / last task column and go through the two list-driven passes) -> single steps.
-constexpr int DOUBLE_MIN_NX = 4096;
-constexpr long long DOUBLE_MIN_CELLS = 8LL << 20;
+// with march2_kernel (tools/sweep_double.py, single vs double steps, GLUPS): 1536x768 83 / 79, 2048x512
+// 84 / 73, 2000x1000 73 / 79, 2048x1024 75 / 98, 1024x4096 74 / 110, 4096x2048 85 / 123, 32768x16384
+// 94 / 147-153.  Below two million cells the state lives in L2 and the launches of the list-driven passes
+// cost more than the saved traffic.
+constexpr int DOUBLE_MIN_NX = 1024;
+constexpr long long DOUBLE_MIN_CELLS = 1900000;
 
 thread_local std::string g_create_error;
 
@@ -409,7 +411,7 @@ int rebuild_info(alb_handle *h) {
     CK(cudaMemcpyAsync(&h->ngen, h->gen_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(launch_build_lists(h->info, h->tclass, h->deep_tmp, h->tflags, h->lists, h->list_counts, h->pitch, h->nrows,
                           h->y0 > 0 ? 1 : 0, h->y0 + h->nyl < h->ny_global ? 1 : 0,
-                          march_edges_enabled(h->nx, h->pitch), h->stream));
+                          march_edges_enabled(h->nx, h->pitch) ? h->nx : 0, h->stream));
     CK(cudaMemcpyAsync(h->nlist, h->list_counts, 5 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     h->solid_synced = false;
     CK(cudaStreamSynchronize(h->stream));
@@ -980,6 +982,7 @@ int issue_double(alb_handle *h, int src_idx, int parity, bool halo, long long sy
     q.clamp_hits = h->clamp_hits;
     q.queue = h->s2_queue;
     q.edges = march_edges_enabled(h->nx, h->pitch) ? 1 : 0;
+    q.nx = h->nx;
     q.u0 = h->u0f;
     memcpy(q.feq0, h->feq0, sizeof q.feq0);
     if (diag) arm_diag2(h, q);
@@ -1941,6 +1944,7 @@ int alb_debug_step2_plan(int nx, int ny_local, int nsm, int *out5) {
     q.pitch = (nx + TASK_CELLS - 1) / TASK_CELLS * TASK_CELLS;
     q.nyl = ny_local;
     q.edges = march_edges_enabled(nx, q.pitch) ? 1 : 0;
+    q.nx = nx;
     march_plan(q, nsm);
     out5[0] = q.nseg;
     out5[1] = q.wo;

@@ -135,7 +135,7 @@ struct Step2Params {
     // queue {next unit, warps that have finished}, both zero between launches
     int nseg, nunits;
     int quota;               // units a warp may take before it retires
-    int edges;               // the first / last task of a row can be deep (nx a multiple of 128, see build_deep_kernel)
+    int edges, nx;           // the first / last task of a row can be deep (see build_deep_kernel); lattice width
     int *queue;
     float tau, inv_tau;
     float u0, feq0[9];       // inlet state (HTML:314-322), edges only
@@ -221,7 +221,7 @@ cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tcla
 bool march_edges_enabled(int nx, int pitch);
 cudaError_t launch_build_lists(const uint16_t *info, const uint8_t *tclass, uint8_t *deep_tmp, uint8_t *tflags,
                                int *const lists[5], int *counts, int pitch, int nrows, int lo_nb, int hi_nb,
-                               bool edges, cudaStream_t s);
+                               int edges_nx, cudaStream_t s);
 
 // alb_diag.cu
 struct DiagScratch {

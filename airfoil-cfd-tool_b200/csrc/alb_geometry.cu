@@ -207,29 +207,34 @@ __global__ void build_tclass_kernel(const uint16_t *__restrict__ info, uint8_t *
 // intermediate state, or are the equilibrium border rows of a whole lattice).
 // With a neighbouring slab below / above (lo_nb / hi_nb) the first / last TWO rows stay shallow, so
 // that the fused kernel never reads a ghost row and needs no synchronisation with the neighbours.
-// edges (nx a multiple of 128, at least two tasks per row): the first and the last task of a row
-// qualify as well when their one special cell is exactly the inlet cell x = 0 (equilibrium, no
-// solid next to it) or the outlet cell x = nx-1 (ditto) and everything else is plain; the fused
-// kernel patches that one cell (alb_march.cu).  Without them a 2048-wide lattice leaves an eighth
-// of its cells to the list-driven passes.
+// edges_nx > 0 (the lattice width, when march_edges_enabled() says so): the first and the last task of a
+// row qualify as well when their one special cell is exactly the inlet cell x = 0 (equilibrium, no
+// solid next to it) or the outlet cell x = nx-1 (ditto), everything before the outlet is plain and
+// everything after it padding; the fused kernel patches that one cell (alb_march.cu) and never
+// writes padding (which holds the equilibrium constants in every buffer anyway).  Without them a
+// 2048-wide lattice leaves an eighth of its cells to the list-driven passes.
 __device__ __forceinline__ bool edge_task_plain(const uint16_t *row, int special, unsigned special_info) {
     bool ok = true;
-    for (int c = 0; c < TASK_CELLS; c++) ok = ok && row[c] == (c == special ? special_info : 0u);
+    for (int c = 0; c < special; c++) ok = ok && row[c] == 0u;
+    ok = ok && row[special] == special_info;
+    const unsigned after = special == 0 ? 0u : ((CT_EQUIL << INFO_TYPE_SHIFT) | INFO_PAD);
+    for (int c = special + 1; c < TASK_CELLS; c++) ok = ok && row[c] == after;
     return ok;
 }
 
 __global__ void build_deep_kernel(const uint16_t *__restrict__ info, const uint8_t *__restrict__ tclass,
-                                  uint8_t *__restrict__ deep, int pitch, int nrows, int lo_nb, int hi_nb, bool edges) {
+                                  uint8_t *__restrict__ deep, int pitch, int nrows, int lo_nb, int hi_nb, int edges_nx) {
     const int tpr = pitch / TASK_CELLS;
     const int task = blockIdx.x * blockDim.x + threadIdx.x;
     if (task >= tpr * nrows) return;
     const int j = task / tpr, s = task - j * tpr;
+    const bool edges = edges_nx > 0;
     bool d = j >= 2 + lo_nb && j <= nrows - 3 - hi_nb && (edges || (s >= 1 && s <= tpr - 2));
     if (d) {
         for (int jj = j - 1; jj <= j + 1; jj++) {
             const uint16_t *row = info + (size_t)jj * pitch + s * TASK_CELLS;
             if (s == 0) d = d && edge_task_plain(row, 0, CT_EQUIL << INFO_TYPE_SHIFT);
-            else if (s == tpr - 1) d = d && edge_task_plain(row, TASK_CELLS - 1, CT_OUTLET << INFO_TYPE_SHIFT);
+            else if (s == tpr - 1) d = d && edge_task_plain(row, edges_nx - 1 - s * TASK_CELLS, CT_OUTLET << INFO_TYPE_SHIFT);
             else d = d && tclass[jj * tpr + s] == TC_FLUID;
             if (s > 0) d = d && row[-1] == 0;
             if (s < tpr - 1) d = d && row[TASK_CELLS] == 0;
@@ -309,9 +314,9 @@ cudaError_t launch_build_info(const uint8_t *mask, uint16_t *info, uint8_t *tcla
 
 cudaError_t launch_build_lists(const uint16_t *info, const uint8_t *tclass, uint8_t *deep_tmp, uint8_t *tflags,
                                int *const lists[5], int *counts, int pitch, int nrows, int lo_nb, int hi_nb,
-                               bool edges, cudaStream_t s) {
+                               int edges_nx, cudaStream_t s) {
     const int tpr = pitch / TASK_CELLS, ntask = tpr * nrows;
-    build_deep_kernel<<<(ntask + 255) / 256, 256, 0, s>>>(info, tclass, deep_tmp, pitch, nrows, lo_nb, hi_nb, edges);
+    build_deep_kernel<<<(ntask + 255) / 256, 256, 0, s>>>(info, tclass, deep_tmp, pitch, nrows, lo_nb, hi_nb, edges_nx);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(counts, 0, 5 * sizeof(int), s);

@@ -188,8 +188,8 @@ march2_kernel(const __grid_constant__ Step2Params p) {
         const int y1 = min(y0 + p.hs, p.nyl);
         // this lane's quad and whether it is one the unit writes.  Without edges: segment s stages columns
         // [124 + 120 s, +128) and writes the middle 120.  With edges (march_plan): segment 0 stages [0, 128) and
-        // writes [0, 124) with the inlet cell patched; the last one stages [pitch - 128, pitch) and writes
-        // [pitch - 124, pitch) with the outlet cell patched; the ones between write 120 columns from 124 + 120 (s-1)
+        // writes [0, 124) with the inlet cell patched; the last one stages [nx - 128, nx) and writes
+        // [nx - 124, nx) with the outlet cell patched; the ones between write 120 columns from 124 + 120 (s-1)
         // on (the last of them clipped where the last segment begins)
         int gx = 124 + M_OUT * s + lane * 4;
         bool own = lane >= 1 && lane <= 30;
@@ -200,12 +200,12 @@ march2_kernel(const __grid_constant__ Step2Params p) {
                 own = lane <= 30;
                 excl = lane == 0 ? 1u : 0u;
             } else if (s == p.nseg - 1) {
-                gx = pitch - 128 + lane * 4;
+                gx = p.nx - 128 + lane * 4;
                 own = lane >= 1;
                 excl = lane == 31 ? 8u : 0u;
             } else {
                 gx = M_OUT * s + lane * 4;
-                own = own && gx < pitch - 124;
+                own = own && gx < p.nx - 124;
             }
         }
         const uint8_t *const tfl = p.tflags + (gx >> 7);
@@ -225,7 +225,7 @@ march2_kernel(const __grid_constant__ Step2Params p) {
             if (excl & 8u) {
                 // the outlet cell's intermediate state is the SOURCE state of its left neighbour (HTML:301-312); the
                 // neighbour's step 2 pulls f3, f6, f7 of it: f3 of this row is staged above, f6 and f7 are not
-                const float *g6 = p.src + 6 * plane + (size_t)a * pitch + (pitch - 2);
+                const float *g6 = p.src + 6 * plane + (size_t)a * pitch + (p.nx - 2);
                 cp_async4(eg_u32 + (unsigned)(k * 2 + 0) * 4u, g6);
                 cp_async4(eg_u32 + (unsigned)(k * 2 + 1) * 4u, g6 + plane);
             }
@@ -438,8 +438,8 @@ template <bool DIAG> constexpr size_t MARCH_SMEM = sizeof(float) * (size_t)March
 // 2) plus a fixed start-up; the persistent warps take units from a queue, so the pass lasts about
 // ceil(units / warps) units -- pick the segment height that minimises it.
 void march_plan(Step2Params &p, int nsm) {
-    if (p.edges)   // [0, 124) | 120 columns each from 124 on | [pitch - 124, pitch)
-        p.nseg = 2 + (p.pitch > 248 ? (p.pitch - 248 + M_OUT - 1) / M_OUT : 0);
+    if (p.edges)   // [0, 124) | 120 columns each from 124 on | [nx - 124, nx)
+        p.nseg = 2 + (p.nx > 248 ? (p.nx - 248 + M_OUT - 1) / M_OUT : 0);
     else
         p.nseg = p.pitch >= 3 * TASK_CELLS ? (p.pitch - 2 * TASK_CELLS + M_OUT - 1) / M_OUT : 0;
     const int rows = p.nyl - 2;
@@ -485,16 +485,18 @@ void march_plan(Step2Params &p, int nsm) {
     if (p.quota < 1) p.quota = 1;
 }
 
-// The inlet and outlet columns can be part of the fused kernel's domain when the row has no padding
-// (the outlet cell is the last cell of the last task) and the two do not share a task.  All slabs of
-// a lattice decide alike: the rule looks at the global width and the environment only.
+// The inlet and outlet columns can be part of the fused kernel's domain when the last segment, which
+// ends with the outlet cell, starts on a 16-byte boundary (nx a multiple of 4) and does not overlap
+// the first one.  All slabs of a lattice decide alike: the rule looks at the global width and the
+// environment only.
 bool march_edges_enabled(int nx, int pitch) {
     static int env = -1;
     if (env < 0) {
         const char *e = getenv("AEROLAB_LBM_MARCH_EDGES");
         env = e ? atoi(e) : 1;
     }
-    return env != 0 && nx == pitch && pitch >= 2 * TASK_CELLS;
+    (void)pitch;
+    return env != 0 && nx % 4 == 0 && nx >= 2 * TASK_CELLS;
 }
 
 int march_out_width() { return M_OUT; }

@@ -289,8 +289,8 @@ int alb_set_external_halo(alb_handle *h, int on);
 /* Two LBM steps per pass over HBM (temporal blocking): the
  * deep interior of the lattice is advanced by a fused two-step kernel, everything
  * near borders, the body and slab edges by two list-driven single-step passes.
- * Bit-identical to single steps.  mode: -1 automatic (lattices at least 4096 wide
- * with 8 Mi cells or more),
+ * Bit-identical to single steps.  mode: -1 automatic (lattices at least 1024 wide
+ * with 1.9 million cells or more),
  * 0 never, 1 whenever a batch has three or more steps left.  All slabs of one
  * lattice must use the same mode.  The environment variable AEROLAB_LBM_DOUBLE
  * (0/1) sets the initial mode of new handles. */

@@ -208,10 +208,13 @@ def test_double_steps_restart(al):
     (512, 33, 0.0),
     (1280, 130, 0.0005),
     (2048, 48, 0.0),
+    (260, 40, 0.0),                     # padded rows: the last task holds three plain cells, the outlet cell and padding
+    (500, 45, 0.001),                   # the last segment straddles the last two tasks
+    (2000, 50, 0.0),
 ])
 def test_double_steps_inlet_and_outlet_columns(al, nx, ny, dens):
-    """Rows without padding (nx a multiple of 128): the inlet column x = 0 and the outlet column
-    x = nx-1 are part of the fused kernel's domain (alb_march.cu patches the one special cell).
+    """Widths that are a multiple of 4: the inlet column x = 0 and the outlet column x = nx-1 are part
+    of the fused kernel's domain (alb_march.cu patches the one special cell).
     A perturbed state makes the outlet copy (HTML:301-312) visible; solids next to and on the two
     columns leave some edge tasks to the list-driven passes."""
     rng = np.random.default_rng(nx * 131 + ny)

@@ -3,11 +3,11 @@
 march2_kernel hands (row segment x column segment) units to independent warps.  A warp stages 128
 columns and writes the middle 120, so: the column segments must cover every column that can be
 deep, no staged column may lie outside the row, and the row segments must cover rows
-2 .. ny_local-1.  Rows with padding (nx not a multiple of 128) or of a single task: the first and
-the last task hold the borders and cannot be deep, the segments cover [128, pitch - 128).  Rows
-without padding: the inlet and outlet columns are part of the domain; the first segment stages
-[0, 128) and writes [0, 124), the last stages [pitch - 128, pitch) and writes [pitch - 124, pitch),
-the ones between write 120 columns each from column 124 on."""
+2 .. ny_local-1.  Widths that are not a multiple of 4, or below 256: the first and the last task
+hold the borders and cannot be deep, the segments cover [128, pitch - 128).  Otherwise the inlet
+and outlet columns are part of the domain; the first segment stages [0, 128) and writes [0, 124),
+the last stages [nx - 128, nx) (16-byte aligned) and writes [nx - 124, nx), the ones between write
+120 columns each from column 124 on."""
 import ctypes as C
 
 import pytest
@@ -19,19 +19,19 @@ def plan(lib, nx, nyl, nsm=148):
     return dict(nseg=out[0], wo=out[1], hs=out[2], nunits=out[3], warps=out[4], wi=128)
 
 
-@pytest.mark.parametrize("nx", [128, 130, 320, 384, 385, 504, 505, 633, 1100, 2048, 4096, 8191, 8192, 32768, 100000])
+@pytest.mark.parametrize("nx", [128, 130, 252, 256, 260, 320, 384, 385, 504, 505, 633, 1100, 2000, 2048, 4096, 8191, 8192, 32768, 100000])
 @pytest.mark.parametrize("nyl", [1, 2, 3, 4, 7, 66, 160, 1024, 2048, 16384, 65000])
 def test_plan_covers_the_lattice(built_lib, nx, nyl):
     p = plan(built_lib, nx, nyl)
     pitch = (nx + 127) // 128 * 128
     assert p["wo"] == 120 and p["warps"] in (12, 16)
     rows = nyl - 2
-    if nx == pitch and pitch >= 256:
+    if nx % 4 == 0 and nx >= 256:
         nmid = p["nseg"] - 2
         assert nmid >= 0
-        assert 124 + nmid * p["wo"] >= pitch - 124              # the middle segments reach the last segment's columns ...
-        assert nmid == 0 or 124 + (nmid - 1) * p["wo"] < pitch - 124   # ... and none of them is empty
-        assert nmid == 0 or 120 * nmid + p["wi"] <= pitch       # middle segment s stages [120 s, 120 s + 128)
+        assert 124 + nmid * p["wo"] >= nx - 124                 # the middle segments reach the last segment's columns ...
+        assert nmid == 0 or 124 + (nmid - 1) * p["wo"] < nx - 124      # ... and none of them is empty
+        assert nmid == 0 or 120 * nmid + p["wi"] <= nx          # middle segment s stages [120 s, 120 s + 128)
         if rows > 0:
             nsegs = -(-rows // p["hs"])
             assert p["hs"] >= 1 and p["nunits"] == p["nseg"] * nsegs
