@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <chrono>
 #include <string.h>
 
 #include <map>
@@ -484,11 +485,23 @@ int check_wait_error(alb_handle *h) {
 
 void free_handle(alb_handle *h) {
     if (!h) return;
+    // AEROLAB_LBM_TRACE_DESTROY=1 (measurement aid): where the time of alb_destroy goes
+    static const bool trace = getenv("AEROLAB_LBM_TRACE_DESTROY") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_prev = now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        const auto t = now();
+        fprintf(stderr, "[alb destroy] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+        t_prev = t;
+    };
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    lap("stream sync");
     if (h->lo.ipc_base) cudaIpcCloseMemHandle(h->lo.ipc_base);
     if (h->hi.ipc_base) cudaIpcCloseMemHandle(h->hi.ipc_base);
     cudaFree(h->block);
+    lap("populations");
     cudaFree(h->rho);
     cudaFree(h->ux);
     cudaFree(h->uy);
@@ -506,10 +519,13 @@ void free_handle(alb_handle *h) {
     cudaFree(h->me);
     cudaFree(h->parts);
     cudaFree(h->d_frame);
+    lap("device arrays");
     if (h->h_frame) cudaFreeHost(h->h_frame);
     if (h->h_rows) cudaFreeHost(h->h_rows);
+    lap("pinned frame buffers");
     cudaFree(h->part_ctr);
     if (h->graph) cudaGraphExecDestroy(h->graph);
+    lap("graph");
     cudaFree(h->clamp_hits);
     cudaFree(h->d_xp);
     cudaFree(h->d_yp);
@@ -517,10 +533,12 @@ void free_handle(alb_handle *h) {
     for (auto &t : h->d_tmp) cudaFree(t);
     for (auto &ev : h->tev)
         if (ev) cudaEventDestroy(ev);
+    lap("more device arrays, events");
     if (h->h_part) cudaFreeHost(h->h_part);
     if (h->h_err) cudaFreeHost(h->h_err);
     if (h->h_diag) cudaFreeHost(h->h_diag);
     if (h->h_diag_init) cudaFreeHost(h->h_diag_init);
+    lap("pinned small buffers");
     cudaFree(h->d_diag);
     cudaFree(h->d_diag_pub);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -532,6 +550,7 @@ void free_handle(alb_handle *h) {
     if (h->aux) cudaStreamDestroy(h->aux);
     if (h->aux2) cudaStreamDestroy(h->aux2);
     if (h->stream) cudaStreamDestroy(h->stream);
+    lap("events, streams");
     delete h;
 }
 
@@ -1607,15 +1626,22 @@ int alb_get_me_history(alb_handle *h, int n, long long *fxfy) {
     CK(cudaStreamSynchronize(h->stream));
     struct { long long acc[2][2]; long long count; int pending; int pad; } head;
     CK(cudaMemcpy(&head, h->me, sizeof head, cudaMemcpyDeviceToHost));
-    for (int k = 0; k < n; k++) {
+    for (int k = 0; k < n;) {
         const long long step = h->sync_steps - n + k;
         if (step < head.count) {
-            CK(cudaMemcpy(fxfy + 2 * k, &h->me->ring[step % ME_RING][0], sizeof(long long) * 2, cudaMemcpyDeviceToHost));
+            // committed steps sit in the ring: one copy per contiguous run (the ring wraps at most once)
+            const long long slot = step % ME_RING;
+            long long run = head.count - step;
+            if (run > n - k) run = n - k;
+            if (run > ME_RING - slot) run = ME_RING - slot;
+            CK(cudaMemcpy(fxfy + 2 * k, &h->me->ring[slot][0], sizeof(long long) * 2 * (size_t)run, cudaMemcpyDeviceToHost));
+            k += (int)run;
         } else {
             // the last step: still in the accumulator of its parity (= the buffer it read from)
             const int parity = h->parity ^ 1;
             fxfy[2 * k] = head.acc[parity][0];
             fxfy[2 * k + 1] = head.acc[parity][1];
+            k++;
         }
     }
     return check_wait_error(h);
