@@ -17,9 +17,15 @@
 //   * step 2 of a cell needs step 1 of its x-neighbours, so only lanes 1..30 produce output (120
 //     columns per warp, segments overlap by 8 columns: 6.7 % redundant arithmetic instead of a
 //     shared intermediate ring and its barriers);
+//   * the inlet column x = 0 and the outlet column x = nx-1 belong to the first and the last column
+//     segment (widths that are a multiple of 4, march_edges_enabled()): lane 0 overwrites the inlet
+//     cell with the equilibrium constants after either collision; the outlet cell copies its left
+//     neighbour's previous state (HTML:301-312), which lane 31 has at hand -- the neighbour's
+//     intermediate state is in its own registers, and of the source state only f6, f7 of one cell
+//     per row are not staged anyway (two 4-byte cp.async in the same group);
 //   * units (row segment x column segment) are handed out through an atomic queue to the persistent
-//     warps of one CTA per SM, so there is no wave tail, and any lattice with at least three
-//     128-cell tasks per row can use it (2048- and 4096-wide lattices included).
+//     warps of one CTA per SM, so there is no wave tail, and any lattice at least 256 cells wide can
+//     use it (2048- and 4096-wide lattices included).
 //
 // Measured and rejected (profiles/r2a_*): staging with TMA bulk copies (nine 512-byte
 // cp.async.bulk per row and warp on the warp's own mbarrier).  UBLKCP takes its operands from
